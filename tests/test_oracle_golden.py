@@ -1,0 +1,70 @@
+"""Pins the oracle (oracle/newsrec_oracle.py) against golden vectors minted from the
+live reference modules (oracle/make_golden.py, reference @ 8323a4f).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import newsrec_oracle as O
+from golden_util import case_params, grad_summary, load_case, oracle_forward, unique_params
+
+CASES = ["nrms", "naml", "naml_f400", "tanr", "lstur_ini", "lstur_con"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_fp32(case):
+    g = load_case(case)
+    p = case_params(case, g)
+    logits, topic = oracle_forward(case, g, p)
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits"], rtol=2e-5, atol=2e-5)
+    loss = O.click_loss(logits)
+    assert abs(loss.item() - float(g["loss"])) < 2e-5 * max(1.0, abs(float(g["loss"])))
+    total = loss
+    if topic is not None:
+        assert abs(topic.item() - float(g["topic_loss"])) < 2e-5 * max(1.0, abs(float(g["topic_loss"])))
+        total = loss + 0.1 * topic
+    total.backward()
+    # the reference names tied parameters by their first registration; match by summary over all names
+    for k, prm in unique_params(p).items():
+        key = k if ("gsum:" + k) in g else None
+        if key is None:  # tied tensor registered under the sibling name in the reference
+            sib = {"title": "abstract", "abstract": "title", "category": "subcategory", "subcategory": "category"}
+            for a, b in sib.items():
+                kk = k.replace(f".{a}.", f".{b}.")
+                if ("gsum:" + kk) in g:
+                    key = kk
+        assert key is not None, f"no golden gradient for {k}"
+        assert prm.grad is not None, k
+        s, samp = grad_summary(prm.grad, key)
+        ref_s, ref_samp = g["gsum:" + key], g["gsamp:" + key]
+        scale = max(ref_s[0], 1e-3)  # W_K.bias grads are ~0 analytically (pure rounding noise)
+        assert abs(s[0] - ref_s[0]) <= 1e-4 * scale, (k, s, ref_s)
+        assert abs(s[1] - ref_s[1]) <= 1e-4 * scale, (k, s, ref_s)
+        np.testing.assert_allclose(samp, ref_samp, rtol=1e-3, atol=2e-5 * scale)
+
+
+def test_embedding_row0_grad_is_zero_and_value_used():
+    g = load_case("nrms")
+    p = case_params("nrms", g)
+    assert float(p["news_encoder.word_embedding.weight"][0].detach().abs().sum()) > 0  # non-zero pad row is READ
+    logits, _ = oracle_forward("nrms", g, p)
+    O.click_loss(logits).backward()
+    assert torch.equal(p["news_encoder.word_embedding.weight"].grad[0], torch.zeros(300))
+
+
+@pytest.mark.parametrize("case", ["nrms", "tanr"])
+def test_bf16_contract_is_close_to_fp32(case):
+    """Documents the size of the bf16 storage error the CUDA path is allowed."""
+    g = load_case(case)
+    with torch.no_grad():
+        exact, _ = oracle_forward(case, g, case_params(case, g, requires_grad=False))
+        bf, _ = oracle_forward(case, g, case_params(case, g, requires_grad=False), O.BF16)
+    rel = (bf - exact).norm() / exact.norm()
+    assert rel < 2e-2, rel
+
+
+def test_fp64_restatement_agrees():
+    g = load_case("nrms")
+    p = case_params("nrms", g, dtype=torch.float64, requires_grad=False)
+    with torch.no_grad():
+        logits, _ = oracle_forward("nrms", g, p)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-5, atol=1e-5)
