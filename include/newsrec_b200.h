@@ -1,0 +1,149 @@
+/* newsrec_b200 -- C ABI of the Blackwell-native (sm_100a) NRMS / NAML / LSTUR / TANR hot path.
+ *
+ * Drop-in boundary for the reference's Python modules (yusanshi/news-recommendation @ 8323a4f).  The
+ * reference has no FFI of its own (pure PyTorch); these are the entry points a maintainer binds with
+ * ctypes from src/model/general/**, src/model/<NAME>/{news,user}_encoder.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns every buffer
+ *     (PyTorch caching allocator); the library allocates nothing persistent;
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no implicit syncs;
+ *   - return 0 on success, a positive cudaError_t on a CUDA failure, -1 on an argument/shape violation
+ *     (detected before any launch); nr_last_error() returns the message for the calling thread;
+ *   - bf16 operand matrices are row-major with a pitch ("ld", in elements) that is a multiple of 8;
+ *     an activation matrix of logical width D carries a constant 1.0 in column D (it turns the next
+ *     weight-gradient GEMM's extra column into the bias gradient) and zeros behind it;
+ *   - token ids are int64 exactly as the reference's DataLoader produces them; indexing is bit exact;
+ *     id 0 is padding_idx: its row is READ like any other (reference behaviour) and its gradient skipped.
+ *   - re-entrant; the only global state is a launch counter and the device watchdog record.
+ */
+#ifndef NEWSREC_B200_H
+#define NEWSREC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state ------------------------------------------------------------------------------ */
+int nr_version(void);                       /* ABI version, currently 1 */
+const char* nr_last_error(void);            /* message of the last failing call on this thread */
+int nr_device_error(int out4[4]);           /* watchdog record {code, block, thread, aux}; code 0 = none */
+long long nr_launch_count(void);            /* kernels this library has launched so far */
+int nr_num_sms(void);
+
+/* ---- operand preparation ------------------------------------------------------------------------- */
+/* fp32 [R][C] (pitch lds) -> zero padded bf16 [R][ld]; transpose!=0: dst is [C][ld] with dst[c][r]=src[r][c] */
+int nr_cast_pad_bf16(const float* src, int R, int C, int lds, void* dst_bf16, int ld, int transpose, void* stream);
+/* fp32 rows [n][D] with element strides -> bf16 [n][ld] + ones column */
+int nr_rows_to_bf16(const float* src, long long n, int D, long long s_row, long long s_col, void* dst_bf16, int ld,
+                    void* stream);
+
+/* ---- reference: nn.Embedding lookup (src/model/NRMS/news_encoder.py:38 etc.) --------------------- */
+/* X[row(seg,t)] = table[ids[seg*T+t]]; padded!=0 writes the zero-padded CNN layout (T+2 rows per segment).
+ * *bad_id_flag (device int) is set to 1 if an id is outside [0,V) (the reference would raise IndexError). */
+int nr_gather_rows(const long long* ids, long long n_tok, int T, const void* table_bf16, int V, int D, int ld,
+                   void* X_bf16, int padded, float p_drop, unsigned long long seed, int* bad_id_flag, void* stream);
+
+/* ---- reference: nn.Linear / nn.Conv2d(1,F,(3,d)) as a tcgen05 GEMM with fused bias/ReLU/dropout --- */
+/* out[M][N] = act(A . W^T + bias); taps==3: window-3 conv over the padded layout (rows_per_tile = k*(T+2)) */
+int nr_linear(const void* A_bf16, int M, int lda, const void* W_bf16, int N, int ldw, int K, int taps, int w_tap_rows,
+              int rows_per_tile, const float* bias, int relu, void* out, int ld_out, int out_is_bf16, void* stream);
+
+/* D[Ma][Nb] += A[:, :Ma]^T . B[rows+shift, b_col0:b_col0+Nb]   (weight gradients; fp32 accumulate) */
+int nr_gemm_tn(const void* A_bf16, int Kr, int Ma, int lda, const void* B_bf16, int b_rows, int b_cols, int ldb,
+               int b_col0, int Nb, int b_row_shift, float* D, int ldd, void* stream);
+
+/* ---- reference: MultiHeadSelfAttention core (src/model/general/attention/multihead_self.py:15-23) -- */
+int nr_mhsa_core_fwd(const void* qkv_bf16, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx_bf16,
+                     int ld_ctx, float p_drop, unsigned long long seed, void* stream);
+int nr_mhsa_core_bwd(const void* qkv_bf16, int ld_qkv, const void* dctx_bf16, int ld_dctx, long long n_seq, int T,
+                     int heads, int dk, void* dqkv_bf16, int ld_dqkv, void* stream);
+
+/* ---- reference: AdditiveAttention.forward (src/model/general/attention/additive.py:27-53) ----------- */
+/* X bf16 [n_seg*seg_len][ldx] (ones column at D) -> out fp32 [n_seg][ldo]; w_out [rows] saved for backward */
+int nr_additive_attention_fwd(const void* X_bf16, long long n_seg, int seg_len, int D, int ldx, const void* Wa_bf16,
+                              int q, int ldw, const float* ba, const float* qv, float* out, int ldo, float* w_out,
+                              void* stream);
+/* backward.  dX bf16 [rows][ld_dx] (=), dWa_ext fp32 [q][ldx] (+=, column D is d(bias)), dqv [q] (+=).
+ * workspace: nr_additive_attention_bwd_workspace(...) bytes. */
+long long nr_additive_attention_bwd_workspace(long long n_seg, int seg_len, int q);
+int nr_additive_attention_bwd(const void* X_bf16, long long n_seg, int seg_len, int D, int ldx, const void* Wa_bf16,
+                              const void* WaT_bf16, int q, int ldw, int ldwT, const float* ba, const float* qv,
+                              const float* w, const float* dout, int ldo, void* dX_bf16, int ld_dx, float* dWa_ext,
+                              float* dqv, void* workspace, long long workspace_bytes, void* stream);
+
+/* ---- reference: DotProductClickPredictor.forward (src/model/general/click_predictor/dot_product.py) - */
+int nr_dot_score_fwd(const float* cand, const float* user, int B, int C, int D, float* logits, void* stream);
+int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
+                     float* duser, void* stream);
+
+/* ---- reference: NRMS NewsEncoder.forward / UserEncoder.forward -------------------------------------
+ *   news  (src/model/NRMS/news_encoder.py:27-48): embedding -> dropout -> MHSA -> dropout -> additive pool
+ *   user  (src/model/NRMS/user_encoder.py:15-26): MHSA -> additive pool over dense fp32 news vectors     */
+typedef struct {
+    long long n_seq;          /* titles (news) or users                                             */
+    int T;                    /* tokens per title / history length                                  */
+    int d;                    /* model width (word_embedding_dim)                                   */
+    int heads;                /* num_attention_heads, d % heads == 0                                */
+    int q;                    /* query_vector_dim                                                   */
+    int ldx;                  /* pitch of X / C / weight operands: multiple of 8, >= d+1            */
+    int ld3;                  /* pitch of QKV: multiple of 8, >= 3d                                 */
+    /* input: ids+table (news encoder) or dense (user encoder) */
+    const long long* ids;     /* [n_seq*T] or NULL                                                  */
+    const void* table_bf16;   /* [V][ldx]                                                           */
+    int V;
+    const float* dense;       /* fp32 [n_seq][T][d] with element strides below, or NULL             */
+    long long dense_s_seq, dense_s_tok, dense_s_col;
+    /* parameters as prepared operands */
+    const void* wqkv_bf16;    /* [3d][ldx]  rows = W_Q | W_K | W_V                                  */
+    const float* bqkv;        /* [3d]                                                               */
+    const void* wa_bf16;      /* [q][ldx]                                                           */
+    const float* ba;          /* [q]                                                                */
+    const float* qv;          /* [q]                                                                */
+    float p_drop;             /* dropout_probability when training, else 0                          */
+    unsigned long long seed;
+    /* outputs; X/QKV/C/w are what backward needs (the caller keeps them alive) */
+    void* X_bf16;             /* [n_seq*T][ldx]                                                     */
+    void* QKV_bf16;           /* [n_seq*T][ld3]                                                     */
+    void* C_bf16;             /* [n_seq*T][ldx]                                                     */
+    float* w;                 /* [n_seq*T] additive-attention weights                               */
+    float* out;               /* [n_seq][d] fp32                                                    */
+    int* bad_id_flag;         /* device int, set if an id is out of range                           */
+} nr_mhsa_encoder_fwd_args;
+int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream);
+
+typedef struct {
+    long long n_seq;
+    int T, d, heads, q, ldx, ld3, ldq;   /* ldq: pitch of dPre / WaT, multiple of 8, >= q               */
+    const long long* ids;                /* NULL for the dense (user) variant                            */
+    int V;
+    const void* wqkvT_bf16;              /* [d][ld3]  = (W_Q|W_K|W_V)^T                                  */
+    const void* wa_bf16;                 /* [q][ldx]                                                     */
+    const void* waT_bf16;                /* [d][ldq]                                                     */
+    const float* ba;
+    const float* qv;
+    float p_drop;
+    unsigned long long seed;
+    const void* X_bf16;
+    const void* QKV_bf16;
+    const void* C_bf16;
+    const float* w;
+    const float* dout;                   /* [n_seq][d] fp32                                              */
+    /* gradients */
+    float* dWqkv_ext;                    /* [3d][ldx] (+=)  column d = d(bias)                           */
+    float* dWa_ext;                      /* [q][ldx]  (+=)  column d = d(bias)                           */
+    float* dqv;                          /* [q] (+=)                                                     */
+    float* demb;                         /* [V][d] (+=) embedding gradient (ids variant)                 */
+    float* ddense;                       /* [n_seq*T][d] (=) input gradient (dense variant)              */
+    void* workspace;
+    long long workspace_bytes;
+} nr_mhsa_encoder_bwd_args;
+long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q);
+int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEWSREC_B200_H */

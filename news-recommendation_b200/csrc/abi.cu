@@ -1,0 +1,210 @@
+// extern "C" surface declared in include/newsrec_b200.h: argument validation + kernel sequencing.
+#include <cstring>
+
+#include "../../include/newsrec_b200.h"
+#include "nr_common.cuh"
+#include "nr_ops.h"
+
+namespace nr {
+const char* last_error();
+int read_device_error(int* out4);
+extern int g_launches;
+}  // namespace nr
+
+using namespace nr;
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+static const RowMapCfg kIdentity = {0, 0, 0, 0, 0};
+static const DropoutCfg kNoDrop = {0.f, 0};
+
+extern "C" {
+
+int nr_version(void) { return 1; }
+const char* nr_last_error(void) { return last_error(); }
+int nr_device_error(int out4[4]) { return read_device_error(out4); }
+long long nr_launch_count(void) { return g_launches; }
+int nr_num_sms(void) { return num_sms(); }
+
+int nr_cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, int transpose, void* stream) {
+    NR_REQUIRE(src && dst && R >= 0 && C >= 0 && ld % 8 == 0 && ld >= (transpose ? R : C),
+               "nr_cast_pad_bf16: R=%d C=%d ld=%d transpose=%d", R, C, ld, transpose);
+    return cast_pad_bf16(src, R, C, lds, dst, ld, transpose, S(stream));
+}
+int nr_rows_to_bf16(const float* src, long long n, int D, long long s_row, long long s_col, void* dst, int ld,
+                    void* stream) {
+    NR_REQUIRE(src && dst && n >= 0 && ld % 8 == 0, "nr_rows_to_bf16: n=%lld ld=%d", n, ld);
+    return rows_to_bf16(src, n, 1, D, s_row, 0, s_col, dst, ld, S(stream));
+}
+int nr_gather_rows(const long long* ids, long long n_tok, int T, const void* table, int V, int D, int ld, void* X,
+                   int padded, float p_drop, unsigned long long seed, int* bad_id_flag, void* stream) {
+    NR_REQUIRE(ids && table && X && bad_id_flag && T >= 1 && n_tok % T == 0 && p_drop >= 0.f && p_drop < 1.f,
+               "nr_gather_rows: n_tok=%lld T=%d p=%f", n_tok, T, p_drop);
+    return gather_rows(ids, n_tok, T, table, V, D, ld, X, ld, padded, DropoutCfg{p_drop, seed}, bad_id_flag, S(stream));
+}
+int nr_linear(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
+              int rows_per_tile, const float* bias, int relu, void* out, int ld_out, int out_is_bf16, void* stream) {
+    NR_REQUIRE(A && W && out && (taps == 1 || taps == 3), "nr_linear: null operand or taps=%d", taps);
+    return gemm_store(A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, bias, relu, out, ld_out, out_is_bf16,
+                      kIdentity, 0, kNoDrop, -1, 0, S(stream));
+}
+int nr_gemm_tn(const void* A, int Kr, int Ma, int lda, const void* B, int b_rows, int b_cols, int ldb, int b_col0,
+               int Nb, int b_row_shift, float* D, int ldd, void* stream) {
+    NR_REQUIRE(A && B && D, "nr_gemm_tn: null operand");
+    return gemm_tn_accumulate(A, Kr, Ma, lda, B, b_rows, b_cols, ldb, b_col0, Nb, b_row_shift, D, ldd, S(stream));
+}
+int nr_mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
+                     float p_drop, unsigned long long seed, void* stream) {
+    NR_REQUIRE(qkv && ctx, "nr_mhsa_core_fwd: null operand");
+    return mhsa_core_fwd(qkv, ld_qkv, n_seq, T, heads, dk, ctx, ld_ctx, DropoutCfg{p_drop, seed}, S(stream));
+}
+int nr_mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads,
+                     int dk, void* dqkv, int ld_dqkv, void* stream) {
+    NR_REQUIRE(qkv && dctx && dqkv, "nr_mhsa_core_bwd: null operand");
+    return mhsa_core_bwd(qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, S(stream));
+}
+
+// ---- AdditiveAttention ---------------------------------------------------------------------------
+int nr_additive_attention_fwd(const void* X, long long n_seg, int seg_len, int D, int ldx, const void* Wa, int q, int ldw,
+                              const float* ba, const float* qv, float* out, int ldo, float* w_out, void* stream) {
+    NR_REQUIRE(X && Wa && ba && qv && out, "nr_additive_attention_fwd: null operand");
+    NR_REQUIRE(n_seg * seg_len < (1ll << 31), "nr_additive_attention_fwd: too many rows");
+    return gemm_additive_pool(X, static_cast<int>(n_seg * seg_len), ldx, D, Wa, q, ldw, ba, qv, seg_len, out, ldo, w_out,
+                              S(stream));
+}
+static inline long long align256(long long x) { return (x + 255) & ~255ll; }
+long long nr_additive_attention_bwd_workspace(long long n_seg, int seg_len, int q) {
+    const long long rows = n_seg * seg_len;
+    return align256(rows * 4) + align256(rows * ((q + 7) & ~7) * 2) + 256;
+}
+int nr_additive_attention_bwd(const void* X, long long n_seg, int seg_len, int D, int ldx, const void* Wa,
+                              const void* WaT, int q, int ldw, int ldwT, const float* ba, const float* qv, const float* w,
+                              const float* dout, int ldo, void* dX, int ld_dx, float* dWa_ext, float* dqv,
+                              void* workspace, long long workspace_bytes, void* stream) {
+    NR_REQUIRE(X && Wa && WaT && ba && qv && w && dout && dX && dWa_ext && dqv && workspace,
+               "nr_additive_attention_bwd: null operand");
+    NR_REQUIRE(workspace_bytes >= nr_additive_attention_bwd_workspace(n_seg, seg_len, q),
+               "nr_additive_attention_bwd: workspace too small");
+    const long long rows = n_seg * seg_len;
+    NR_REQUIRE(rows < (1ll << 31), "nr_additive_attention_bwd: too many rows");
+    const int M = static_cast<int>(rows);
+    const int ldq = (q + 7) & ~7;
+    char* ws = static_cast<char*>(workspace);
+    float* dscore = reinterpret_cast<float*>(ws);
+    void* dpre = ws + align256(rows * 4);
+    NR_PROPAGATE(pool_dscore(X, ldx, D, n_seg, seg_len, w, dout, ldo, dscore, S(stream)));
+    NR_PROPAGATE(gemm_additive_dpre(X, M, ldx, D, Wa, q, ldw, ba, qv, dscore, dpre, ldq, dqv, S(stream)));
+    NR_PROPAGATE(gemm_pool_dinput(dpre, M, ldq, q, WaT, D, ldwT, w, dout, ldo, seg_len, dX, ld_dx, kIdentity, 0, kNoDrop,
+                                  nullptr, 0, S(stream)));
+    // dWa_ext[q][0:D] += dPre^T . X ; column D (the ones column of X) accumulates d(bias)
+    NR_PROPAGATE(gemm_tn_accumulate(dpre, M, q, ldq, X, M, D + 1, ldx, 0, D + 1, 0, dWa_ext, ldx, S(stream)));
+    return 0;
+}
+
+int nr_dot_score_fwd(const float* cand, const float* user, int B, int C, int D, float* logits, void* stream) {
+    NR_REQUIRE(cand && user && logits, "nr_dot_score_fwd: null operand");
+    return dot_score_fwd(cand, user, B, C, D, logits, S(stream));
+}
+int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
+                     float* duser, void* stream) {
+    NR_REQUIRE(cand && user && dlogits && dcand && duser, "nr_dot_score_bwd: null operand");
+    return dot_score_bwd(cand, user, dlogits, B, C, D, dcand, duser, S(stream));
+}
+
+// ---- NRMS encoders ---------------------------------------------------------------------------------
+static int check_mhsa_shape(long long n_seq, int T, int d, int heads, int q, int ldx, int ld3) {
+    NR_REQUIRE(n_seq >= 0 && T >= 1 && T <= 64 && d >= 8 && heads >= 1 && d % heads == 0 && q >= 1 && q <= 256,
+               "mhsa encoder: bad shape n_seq=%lld T=%d d=%d heads=%d q=%d", n_seq, T, d, heads, q);
+    NR_REQUIRE(ldx % 8 == 0 && ldx >= d + 1 && ld3 % 8 == 0 && ld3 >= 3 * d, "mhsa encoder: bad pitches ldx=%d ld3=%d", ldx,
+               ld3);
+    NR_REQUIRE(n_seq * T < (1ll << 31), "mhsa encoder: too many tokens (%lld)", n_seq * T);
+    return 0;
+}
+
+int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
+    NR_REQUIRE(a != nullptr, "nr_mhsa_encoder_fwd: null args");
+    NR_PROPAGATE(check_mhsa_shape(a->n_seq, a->T, a->d, a->heads, a->q, a->ldx, a->ld3));
+    NR_REQUIRE((a->ids != nullptr) != (a->dense != nullptr), "nr_mhsa_encoder_fwd: exactly one of ids / dense");
+    NR_REQUIRE(a->wqkv_bf16 && a->bqkv && a->wa_bf16 && a->ba && a->qv && a->X_bf16 && a->QKV_bf16 && a->C_bf16 && a->w &&
+                   a->out, "nr_mhsa_encoder_fwd: null operand");
+    NR_REQUIRE(a->p_drop >= 0.f && a->p_drop < 1.f, "nr_mhsa_encoder_fwd: dropout p=%f", a->p_drop);
+    if (a->n_seq == 0) return 0;
+    const int M = static_cast<int>(a->n_seq * a->T);
+    const cudaStream_t st = S(stream);
+    if (a->ids != nullptr) {
+        NR_REQUIRE(a->table_bf16 && a->bad_id_flag && a->V >= 1, "nr_mhsa_encoder_fwd: table / bad_id_flag missing");
+        NR_PROPAGATE(gather_rows(a->ids, M, a->T, a->table_bf16, a->V, a->d, a->ldx, a->X_bf16, a->ldx, 0,
+                                 DropoutCfg{a->p_drop, a->seed}, a->bad_id_flag, st));
+    } else {
+        NR_PROPAGATE(rows_to_bf16(a->dense, a->n_seq, a->T, a->d, a->dense_s_seq, a->dense_s_tok, a->dense_s_col,
+                                  a->X_bf16, a->ldx, st));
+    }
+    // Q|K|V = X . Wqkv^T + b   (multihead_self.py:53-58)
+    NR_PROPAGATE(gemm_store(a->X_bf16, M, a->ldx, a->wqkv_bf16, 3 * a->d, a->ldx, a->d, 1, 0, 128, a->bqkv, 0,
+                            a->QKV_bf16, a->ld3, 1, kIdentity, 0, kNoDrop, -1, 0, st));
+    // per-head attention (multihead_self.py:15-23), dropout on the context only in the news encoder
+    const DropoutCfg cdrop = {a->ids != nullptr ? a->p_drop : 0.f, a->seed ^ 0x5bd1e995u};
+    NR_PROPAGATE(mhsa_core_fwd(a->QKV_bf16, a->ld3, a->n_seq, a->T, a->heads, a->d / a->heads, a->C_bf16, a->ldx, cdrop,
+                               st));
+    // additive pooling (additive.py:35-53)
+    NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
+                                    a->w, st));
+    return 0;
+}
+
+long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q) {
+    const long long rows = n_seq * T;
+    const long long ldx = (d + 1 + 7) & ~7, ld3 = (3 * d + 7) & ~7, ldq = (q + 7) & ~7;
+    return align256(rows * 4) + align256(rows * ldq * 2) + align256(rows * ldx * 2) + align256(rows * ld3 * 2) + 256;
+}
+
+int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
+    NR_REQUIRE(a != nullptr, "nr_mhsa_encoder_bwd: null args");
+    NR_PROPAGATE(check_mhsa_shape(a->n_seq, a->T, a->d, a->heads, a->q, a->ldx, a->ld3));
+    NR_REQUIRE(a->ldq % 8 == 0 && a->ldq >= a->q, "nr_mhsa_encoder_bwd: ldq=%d", a->ldq);
+    NR_REQUIRE(a->ldx == ((a->d + 8) & ~7) && a->ld3 == ((3 * a->d + 7) & ~7) && a->ldq == ((a->q + 7) & ~7),
+               "nr_mhsa_encoder_bwd: pitches must be the canonical round-up-to-8 values");
+    NR_REQUIRE(a->wqkvT_bf16 && a->wa_bf16 && a->waT_bf16 && a->ba && a->qv && a->X_bf16 && a->QKV_bf16 && a->C_bf16 &&
+                   a->w && a->dout && a->dWqkv_ext && a->dWa_ext && a->dqv && a->workspace,
+               "nr_mhsa_encoder_bwd: null operand");
+    NR_REQUIRE((a->ids != nullptr) ? (a->demb != nullptr) : (a->ddense != nullptr),
+               "nr_mhsa_encoder_bwd: missing input-gradient buffer");
+    NR_REQUIRE(a->workspace_bytes >= nr_mhsa_encoder_bwd_workspace(a->n_seq, a->T, a->d, a->q),
+               "nr_mhsa_encoder_bwd: workspace too small (%lld bytes)", a->workspace_bytes);
+    if (a->n_seq == 0) return 0;
+    const long long rows = a->n_seq * a->T;
+    const int M = static_cast<int>(rows);
+    const cudaStream_t st = S(stream);
+    char* ws = static_cast<char*>(a->workspace);
+    float* dscore = reinterpret_cast<float*>(ws);
+    ws += align256(rows * 4);
+    void* dpre = ws;
+    ws += align256(rows * a->ldq * 2);
+    void* dC = ws;
+    ws += align256(rows * a->ldx * 2);
+    void* dQKV = ws;
+
+    // --- additive pooling backward ---
+    NR_PROPAGATE(pool_dscore(a->C_bf16, a->ldx, a->d, a->n_seq, a->T, a->w, a->dout, a->d, dscore, st));
+    NR_PROPAGATE(gemm_additive_dpre(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, dscore, dpre, a->ldq,
+                                    a->dqv, st));
+    const DropoutCfg cdrop = {a->ids != nullptr ? a->p_drop : 0.f, a->seed ^ 0x5bd1e995u};
+    NR_PROPAGATE(gemm_pool_dinput(dpre, M, a->ldq, a->q, a->waT_bf16, a->d, a->ldq, a->w, a->dout, a->d, a->T, dC, a->ldx,
+                                  kIdentity, 0, cdrop, nullptr, 0, st));
+    NR_PROPAGATE(gemm_tn_accumulate(dpre, M, a->q, a->ldq, a->C_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWa_ext,
+                                    a->ldx, st));
+    // --- attention backward ---
+    NR_PROPAGATE(mhsa_core_bwd(a->QKV_bf16, a->ld3, dC, a->ldx, a->n_seq, a->T, a->heads, a->d / a->heads, dQKV, a->ld3, st));
+    // --- projection backward: weights (+bias through the ones column of X), then the input ---
+    NR_PROPAGATE(gemm_tn_accumulate(dQKV, M, 3 * a->d, a->ld3, a->X_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWqkv_ext,
+                                    a->ldx, st));
+    if (a->ids != nullptr) {
+        NR_PROPAGATE(gemm_scatter_emb(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, a->ids, a->demb, a->d,
+                                      kIdentity, DropoutCfg{a->p_drop, a->seed}, a->ldx, st));
+    } else {
+        NR_PROPAGATE(gemm_store(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, nullptr, 0, a->ddense, a->d,
+                                0, kIdentity, 0, kNoDrop, -1, 0, st));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,466 @@
+// Memory-bound companions of the tcgen05 GEMMs: operand preparation, the embedding-row gather,
+// the per-(sequence, head) self-attention core (fwd/bwd), pooling-backward row dots, the dot-product
+// click scorer.  All HBM-bound integer/byte or small-reduction work: coalesced 16-byte accesses,
+// warp-shuffle reductions, no tensor cores.
+#include <algorithm>
+
+#include "nr_common.cuh"
+#include "nr_ops.h"
+
+namespace nr {
+
+extern int g_launches;
+
+// ------------------------------------------------------------------------------------------------
+// fp32 parameter -> zero-padded bf16 operand (optionally transposed)
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_pad_kernel(const float* __restrict__ src, int R, int C, int lds, __nv_bfloat16* __restrict__ dst,
+                                int ld, int transpose) {
+    const long long n_rows = transpose ? C : R;
+    const long long total = n_rows * ld;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / ld;
+        const int c = static_cast<int>(i - r * ld);
+        float v = 0.f;
+        if (!transpose) {
+            if (c < C) v = src[r * lds + c];
+        } else {
+            if (c < R) v = src[static_cast<long long>(c) * lds + r];
+        }
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+int cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, int transpose, cudaStream_t stream) {
+    const long long total = static_cast<long long>(transpose ? C : R) * ld;
+    if (total == 0) return 0;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    cast_pad_kernel<<<blocks, 256, 0, stream>>>(src, R, C, lds, static_cast<__nv_bfloat16*>(dst), ld, transpose);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// fp32 rows [n_seq][T][D] (arbitrary element strides) -> bf16 rows [n_seq*T x ld] with a ones column at D
+__global__ void rows_to_bf16_kernel(const float* __restrict__ src, long long n_rows, int T, int D, long long s_seq,
+                                    long long s_tok, long long s_col, __nv_bfloat16* __restrict__ dst, int ld) {
+    const long long total = n_rows * ld;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / ld;
+        const int c = static_cast<int>(i - r * ld);
+        const long long seq = r / T;
+        const long long tok = r - seq * T;
+        float v = 0.f;
+        if (c < D) v = src[seq * s_seq + tok * s_tok + c * s_col];
+        else if (c == D) v = 1.0f;
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+int rows_to_bf16(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col,
+                 void* dst, int ld, cudaStream_t stream) {
+    const long long n = n_seq * T;
+    if (n == 0) return 0;
+    NR_REQUIRE(ld >= D + 1, "rows_to_bf16: pitch %d too small for D=%d plus the ones column", ld, D);
+    const int blocks = static_cast<int>(std::min<long long>((n * ld + 255) / 256, 148 * 16));
+    rows_to_bf16_kernel<<<blocks, 256, 0, stream>>>(src, n, T, D, s_seq, s_tok, s_col, static_cast<__nv_bfloat16*>(dst),
+                                                    ld);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Embedding-row gather: one warp per token, 16-byte lanes.  The copy is bit exact (bf16 table rows).
+// Column D of every gathered row is set to 1.0 (bias-gradient trick), columns after it stay 0.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float drop_mult(uint64_t seed, uint32_t thresh, float scale, long long row, int ld, int col) {
+    const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row) * ld + col) >> 2);
+    return (((bits >> (16 * (col & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
+}
+
+__global__ void gather_rows_kernel(const long long* __restrict__ ids, long long n_tok, int T,
+                                   const uint4* __restrict__ table, int V, int D, int ld, uint4* __restrict__ X,
+                                   int padded, float p, uint64_t seed, int* bad_flag) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int chunks = ld >> 3;  // 16-byte chunks per row
+    const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (long long tok = warp0; tok < n_tok; tok += nwarps) {
+        long long id = ids[tok];
+        if (id < 0 || id >= V) {
+            if (lane == 0) atomicExch(bad_flag, 1);
+            id = 0;
+        }
+        const long long seg = tok / T;
+        const int t = static_cast<int>(tok - seg * T);
+        const long long xr = padded ? seg * (T + 2) + 1 + t : tok;
+        const uint4* src = table + id * chunks;
+        uint4* dst = X + xr * chunks;
+        for (int c = lane; c < chunks; c += 32) {
+            uint4 u = __ldg(src + c);
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            const int col = c * 8;
+            if (p > 0.f) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 f = unpack_bf16x2(w[j]);
+                    f.x *= drop_mult(seed, thresh, scale, xr, ld, col + 2 * j);
+                    f.y *= drop_mult(seed, thresh, scale, xr, ld, col + 2 * j + 1);
+                    w[j] = pack_bf16x2(f.x, f.y);
+                }
+            }
+            if (D >= col && D < col + 8) {  // ones column, zeros behind it
+                __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(w);
+                for (int j = D - col; j < 8; ++j) e[j] = __float2bfloat16_rn(j == D - col ? 1.0f : 0.f);
+            }
+            dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (padded) {
+            if (t == 0)
+                for (int c = lane; c < chunks; c += 32) X[(xr - 1) * chunks + c] = make_uint4(0, 0, 0, 0);
+            if (t == T - 1)
+                for (int c = lane; c < chunks; c += 32) X[(xr + 1) * chunks + c] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+int gather_rows(const long long* ids, long long n_tok, int T, const void* table, int V, int D, int ld_table, void* X,
+                int ld_x, int padded, DropoutCfg drop, int* bad_id_flag, cudaStream_t stream) {
+    if (n_tok == 0) return 0;
+    NR_REQUIRE(ld_table == ld_x && ld_x % 8 == 0 && ld_x >= D + 1, "gather_rows: pitch %d/%d for D=%d", ld_table, ld_x, D);
+    const int blocks = static_cast<int>(std::min<long long>((n_tok + 7) / 8, 148 * 8));
+    gather_rows_kernel<<<blocks, 256, 0, stream>>>(ids, n_tok, T, static_cast<const uint4*>(table), V, D, ld_x,
+                                                   static_cast<uint4*>(X), padded, drop.p, drop.seed, bad_id_flag);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-attention core, one (sequence, head) per thread group, one query row per thread.
+// Reference semantics (multihead_self.py:15-23): A = exp(S) / (sum exp(S) + 1e-8), S = QK^T/sqrt(dk),
+// no mask.  Implemented in the numerically safe equivalent form exp(S-m) / (sum exp(S-m) + 1e-8 e^{-m}).
+// ------------------------------------------------------------------------------------------------
+template <int DK>
+__global__ void __launch_bounds__(64) mhsa_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
+                                                      int T, int heads, __nv_bfloat16* __restrict__ ctx, int ld_ctx,
+                                                      float p, uint64_t seed, int hpb) {
+    extern __shared__ float sm[];  // K[hpb][T][DK], V[hpb][T][DK]
+    const int d = heads * DK;
+    const int groups = (heads + hpb - 1) / hpb;
+    const long long seq = blockIdx.x / groups;
+    const int h0 = (blockIdx.x % groups) * hpb;
+    const int nh = min(hpb, heads - h0);
+    float* Ks = sm;
+    float* Vs = sm + hpb * T * DK;
+    const __nv_bfloat16* base = qkv + seq * T * static_cast<long long>(ld);
+    for (int i = threadIdx.x; i < nh * T * DK; i += blockDim.x) {
+        const int hh = i / (T * DK);
+        const int rem = i - hh * T * DK;
+        const int j = rem / DK, dd = rem - j * DK;
+        const long long off = static_cast<long long>(j) * ld + (h0 + hh) * DK + dd;
+        Ks[i] = __bfloat162float(base[off + d]);
+        Vs[i] = __bfloat162float(base[off + 2 * d]);
+    }
+    __syncthreads();
+    const int hh = threadIdx.x / T;
+    const int i = threadIdx.x - hh * T;
+    if (hh >= nh) return;
+    const int h = h0 + hh;
+    float q[DK];
+    const float scale = rsqrtf(static_cast<float>(DK)) * 1.4426950408889634f;  // fold log2(e): exp(x) = exp2(x*log2e)
+#pragma unroll
+    for (int dd = 0; dd < DK; ++dd) q[dd] = __bfloat162float(base[static_cast<long long>(i) * ld + h * DK + dd]) * scale;
+    float m = -INFINITY, l = 0.f, acc[DK];
+#pragma unroll
+    for (int dd = 0; dd < DK; ++dd) acc[dd] = 0.f;
+    const float* kh = Ks + hh * T * DK;
+    const float* vh = Vs + hh * T * DK;
+    for (int j = 0; j < T; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int dd = 0; dd < DK; ++dd) s = fmaf(q[dd], kh[j * DK + dd], s);
+        const float mn = fmaxf(m, s);
+        const float corr = exp2f(m - mn);
+        const float pj = exp2f(s - mn);
+        l = l * corr + pj;
+#pragma unroll
+        for (int dd = 0; dd < DK; ++dd) acc[dd] = fmaf(pj, vh[j * DK + dd], acc[dd] * corr);
+        m = mn;
+    }
+    const float inv = 1.f / (l + 1e-8f * exp2f(-m));
+    const long long row = seq * T + i;
+    __nv_bfloat16* o = ctx + row * ld_ctx + h * DK;
+    const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    const float dscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+#pragma unroll
+    for (int dd = 0; dd < DK; ++dd) {
+        float v = acc[dd] * inv;
+        if (p > 0.f) v *= drop_mult(seed, thresh, dscale, row, ld_ctx, h * DK + dd);
+        o[dd] = __float2bfloat16_rn(v);
+    }
+    if (h == 0) {  // ones column + zero tail of the padded row
+        __nv_bfloat16* r = ctx + row * ld_ctx;
+        r[d] = __float2bfloat16_rn(1.0f);
+        for (int c = d + 1; c < ld_ctx; ++c) r[c] = __float2bfloat16_rn(0.f);
+    }
+}
+
+template <int DK>
+__global__ void __launch_bounds__(64) mhsa_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
+                                                      const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
+                                                      long long n_seq, int T, int heads,
+                                                      __nv_bfloat16* __restrict__ dqkv, int ld_d, int hpb) {
+    extern __shared__ float sm[];
+    const int d = heads * DK;
+    const int groups = (heads + hpb - 1) / hpb;
+    const long long seq = blockIdx.x / groups;
+    const int h0 = (blockIdx.x % groups) * hpb;
+    const int nh = min(hpb, heads - h0);
+    const int TD = T * DK, TT = T * T;
+    float* Qs = sm;                  // [hpb][T][DK]
+    float* Ks = Qs + hpb * TD;
+    float* Vs = Ks + hpb * TD;
+    float* Gs = Vs + hpb * TD;       // dCtx
+    float* Ps = Gs + hpb * TD;       // [hpb][T][T]  P
+    float* Ss = Ps + hpb * TT;       // [hpb][T][T]  dS (scaled)
+    const __nv_bfloat16* base = qkv + seq * T * static_cast<long long>(ld);
+    const __nv_bfloat16* gbase = dctx + seq * T * static_cast<long long>(ld_dctx);
+    for (int i = threadIdx.x; i < nh * TD; i += blockDim.x) {
+        const int hh = i / TD;
+        const int rem = i - hh * TD;
+        const int j = rem / DK, dd = rem - j * DK;
+        const int col = (h0 + hh) * DK + dd;
+        const long long off = static_cast<long long>(j) * ld + col;
+        Qs[i] = __bfloat162float(base[off]);
+        Ks[i] = __bfloat162float(base[off + d]);
+        Vs[i] = __bfloat162float(base[off + 2 * d]);
+        Gs[i] = __bfloat162float(gbase[static_cast<long long>(j) * ld_dctx + col]);
+    }
+    __syncthreads();
+    const int hh = threadIdx.x / T;
+    const int i = threadIdx.x - hh * T;
+    const bool active = hh < nh;
+    const int h = h0 + hh;
+    const float rs = rsqrtf(static_cast<float>(DK));
+    const float* qh = Qs + hh * TD;
+    const float* kh = Ks + hh * TD;
+    const float* vh = Vs + hh * TD;
+    const float* gh = Gs + hh * TD;
+    float* ph = Ps + hh * TT;
+    float* sh = Ss + hh * TT;
+    if (active) {
+        // phase A (row i): scores, softmax-with-epsilon, dP, delta, dS, dQ
+        float q[DK], g[DK];
+#pragma unroll
+        for (int dd = 0; dd < DK; ++dd) {
+            q[dd] = qh[i * DK + dd] * (rs * 1.4426950408889634f);
+            g[dd] = gh[i * DK + dd];
+        }
+        float m = -INFINITY;
+        for (int j = 0; j < T; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int dd = 0; dd < DK; ++dd) s = fmaf(q[dd], kh[j * DK + dd], s);
+            ph[i * T + j] = s;
+            m = fmaxf(m, s);
+        }
+        float l = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const float e = exp2f(ph[i * T + j] - m);
+            ph[i * T + j] = e;
+            l += e;
+        }
+        const float inv = 1.f / (l + 1e-8f * exp2f(-m));
+        float delta = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const float pij = ph[i * T + j] * inv;
+            float dp = 0.f;
+#pragma unroll
+            for (int dd = 0; dd < DK; ++dd) dp = fmaf(g[dd], vh[j * DK + dd], dp);
+            ph[i * T + j] = pij;
+            sh[i * T + j] = dp;
+            delta = fmaf(pij, dp, delta);
+        }
+        float dq[DK];
+#pragma unroll
+        for (int dd = 0; dd < DK; ++dd) dq[dd] = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const float ds = ph[i * T + j] * (sh[i * T + j] - delta) * rs;
+            sh[i * T + j] = ds;
+#pragma unroll
+            for (int dd = 0; dd < DK; ++dd) dq[dd] = fmaf(ds, kh[j * DK + dd], dq[dd]);
+        }
+        __nv_bfloat16* o = dqkv + (seq * T + i) * static_cast<long long>(ld_d) + h * DK;
+#pragma unroll
+        for (int dd = 0; dd < DK; ++dd) o[dd] = __float2bfloat16_rn(dq[dd]);
+    }
+    __syncthreads();
+    if (active) {
+        // phase B (column j = i): dK_j = sum_i dS_ij Q_i ; dV_j = sum_i P_ij dCtx_i
+        const int j = i;
+        float dk[DK], dv[DK];
+#pragma unroll
+        for (int dd = 0; dd < DK; ++dd) { dk[dd] = 0.f; dv[dd] = 0.f; }
+        for (int r = 0; r < T; ++r) {
+            const float ds = sh[r * T + j];
+            const float pp = ph[r * T + j];
+#pragma unroll
+            for (int dd = 0; dd < DK; ++dd) {
+                dk[dd] = fmaf(ds, qh[r * DK + dd], dk[dd]);
+                dv[dd] = fmaf(pp, gh[r * DK + dd], dv[dd]);
+            }
+        }
+        __nv_bfloat16* o = dqkv + (seq * T + j) * static_cast<long long>(ld_d) + h * DK;
+#pragma unroll
+        for (int dd = 0; dd < DK; ++dd) {
+            o[d + dd] = __float2bfloat16_rn(dk[dd]);
+            o[2 * d + dd] = __float2bfloat16_rn(dv[dd]);
+        }
+    }
+}
+
+template <int DK>
+static int mhsa_launch(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T,
+                       int heads, void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
+    const int hpb = std::max(1, 64 / T);
+    const int groups = ceil_div(heads, hpb);
+    const long long blocks = n_seq * groups;
+    NR_REQUIRE(blocks < (1ll << 31), "mhsa: too many (sequence, head-group) blocks");
+    if (!bwd) {
+        const size_t smem = sizeof(float) * 2 * hpb * T * DK;
+        mhsa_fwd_kernel<DK><<<static_cast<unsigned>(blocks), 64, smem, stream>>>(
+            static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T, heads, static_cast<__nv_bfloat16*>(out), ld_out,
+            drop.p, drop.seed, hpb);
+    } else {
+        const size_t smem = sizeof(float) * (4 * hpb * T * DK + 2 * hpb * T * T);
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        mhsa_bwd_kernel<DK><<<static_cast<unsigned>(blocks), 64, smem, stream>>>(
+            static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<const __nv_bfloat16*>(dctx), ld_dctx, n_seq, T,
+            heads, static_cast<__nv_bfloat16*>(out), ld_out, hpb);
+    }
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+#define NR_DK_DISPATCH(dk, ...)                                                        \
+    switch (dk) {                                                                      \
+        case 10: return mhsa_launch<10>(__VA_ARGS__);                                  \
+        case 12: return mhsa_launch<12>(__VA_ARGS__);                                  \
+        case 15: return mhsa_launch<15>(__VA_ARGS__);                                  \
+        case 20: return mhsa_launch<20>(__VA_ARGS__);                                  \
+        case 25: return mhsa_launch<25>(__VA_ARGS__);                                  \
+        case 30: return mhsa_launch<30>(__VA_ARGS__);                                  \
+        default: set_error("mhsa: unsupported head size d_k=%d (supported: 10,12,15,20,25,30)", dk); return -1; \
+    }
+
+int mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
+                  DropoutCfg drop, cudaStream_t stream) {
+    if (n_seq == 0) return 0;
+    NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
+    NR_REQUIRE(ld_ctx >= heads * dk + 1, "mhsa: context pitch %d has no room for the ones column", ld_ctx);
+    NR_DK_DISPATCH(dk, false, qkv, ld_qkv, nullptr, 0, n_seq, T, heads, ctx, ld_ctx, drop, stream);
+}
+int mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+                  void* dqkv, int ld_dqkv, cudaStream_t stream) {
+    if (n_seq == 0) return 0;
+    NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
+    DropoutCfg nodrop{0.f, 0};
+    NR_DK_DISPATCH(dk, true, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dqkv, ld_dqkv, nodrop, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling backward, scalar part: dw_r = dOut[seg] . X_r ; dscore_r = w_r (dw_r - sum_seg w dw)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pool_dscore_kernel(const __nv_bfloat16* __restrict__ X, int lda, int D,
+                                                          long long n_seg, int seg_len, const float* __restrict__ w,
+                                                          const float* __restrict__ dout, int ldo,
+                                                          float* __restrict__ dscore) {
+    __shared__ float s_dw[128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+        const float* dob = dout + seg * ldo;
+        for (int t = warp; t < seg_len; t += 4) {
+            const __nv_bfloat16* xr = X + (seg * seg_len + t) * static_cast<long long>(lda);
+            float a = 0.f;
+            for (int c = 2 * lane; c < D; c += 64) {
+                const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
+                a = fmaf(f.x, dob[c], a);
+                a = fmaf(f.y, dob[c + 1], a);
+            }
+            a = warp_sum(a);
+            if (lane == 0) s_dw[t] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x < seg_len) {
+            const float* wr = w + seg * seg_len;
+            float dot = 0.f;
+            for (int t = 0; t < seg_len; ++t) dot = fmaf(wr[t], s_dw[t], dot);
+            dscore[seg * seg_len + threadIdx.x] = wr[threadIdx.x] * (s_dw[threadIdx.x] - dot);
+        }
+        __syncthreads();
+    }
+}
+int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, const float* w, const float* dout, int ldo,
+                float* dscore, cudaStream_t stream) {
+    if (n_seg == 0) return 0;
+    NR_REQUIRE(seg_len <= 128 && D % 2 == 0, "pool_dscore: seg_len=%d D=%d", seg_len, D);
+    const int blocks = static_cast<int>(std::min<long long>(n_seg, 148 * 16));
+    pool_dscore_kernel<<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(X), lda, D, n_seg, seg_len, w, dout,
+                                                   ldo, dscore);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dot-product click predictor (reference dot_product.py:8-19): one warp per (impression, candidate)
+// ------------------------------------------------------------------------------------------------
+__global__ void dot_fwd_kernel(const float* __restrict__ cand, const float* __restrict__ user, int B, int C, int D,
+                               float* __restrict__ logits) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= B * C) return;
+    const int b = wid / C;
+    const float* cv = cand + static_cast<size_t>(wid) * D;
+    const float* uv = user + static_cast<size_t>(b) * D;
+    float a = 0.f;
+    for (int c = lane; c < D; c += 32) a = fmaf(cv[c], uv[c], a);
+    a = warp_sum(a);
+    if (lane == 0) logits[wid] = a;
+}
+__global__ void dot_bwd_kernel(const float* __restrict__ cand, const float* __restrict__ user,
+                               const float* __restrict__ dlogits, int B, int C, int D, float* __restrict__ dcand,
+                               float* __restrict__ duser) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        const float u = user[static_cast<size_t>(b) * D + c];
+        float du = 0.f;
+        for (int j = 0; j < C; ++j) {
+            const float g = dlogits[b * C + j];
+            dcand[(static_cast<size_t>(b) * C + j) * D + c] = g * u;
+            du = fmaf(g, cand[(static_cast<size_t>(b) * C + j) * D + c], du);
+        }
+        duser[static_cast<size_t>(b) * D + c] = du;
+    }
+}
+int dot_score_fwd(const float* cand, const float* user, int B, int C, int D, float* logits, cudaStream_t stream) {
+    if (B * C == 0) return 0;
+    dot_fwd_kernel<<<ceil_div(B * C * 32, 256), 256, 0, stream>>>(cand, user, B, C, D, logits);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
+                  float* duser, cudaStream_t stream) {
+    if (B == 0) return 0;
+    dot_bwd_kernel<<<B, 128, 0, stream>>>(cand, user, dlogits, B, C, D, dcand, duser);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace nr

@@ -1,0 +1,383 @@
+// Fused epilogue functors for gemm_nt.  Each epilogue thread owns one accumulator row (= TMEM lane)
+// and walks its columns in chunks of 32 fp32 values.  Contract for every functor:
+//   * all 128 threads call acc.load32() the same number of times (tcgen05.ld is warp-collective)
+//   * every thread calls acc.release() exactly once per tile, after its last load32
+//   * init()/finish() bracket the CTA's whole tile loop (all 128 epilogue threads call them)
+#pragma once
+#include "nr_gemm.cuh"
+
+namespace nr {
+
+// Row re-mapping between the compact token layout (segment s, token t -> row s*T + t) and the
+// zero-padded CNN layout (row s*(T+2) + 1 + t; rows 0 and T+1 of every segment are zero).
+struct RowMap {
+    int seg_in;   // 0 => identity
+    int in_off;
+    int seg_len;
+    int seg_out;
+    int out_off;
+    __device__ __forceinline__ bool map(int grow, long long& orow, int& t_out) const {
+        if (seg_in == 0) { orow = grow; t_out = 0; return true; }
+        const int s = grow / seg_in;
+        const int t = grow - s * seg_in - in_off;
+        t_out = t;
+        orow = static_cast<long long>(s) * seg_out + t + out_off;
+        return t >= 0 && t < seg_len;
+    }
+};
+
+__device__ __forceinline__ void zero_row_bf16(__nv_bfloat16* row, int ld) {  // ld % 8 == 0, 16B aligned
+    for (int i = 0; i < ld; i += 8) *reinterpret_cast<uint4*>(row + i) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+struct Dropout {
+    float p;          // 0 => off
+    float scale;      // 1/(1-p)
+    uint32_t thresh;  // keep iff 16-bit lane >= thresh
+    uint64_t seed;
+    // multiplier for element (row, col) of a matrix with pitch ld; cols are visited in aligned groups of 4
+    __device__ __forceinline__ void mask4(long long row, int ld, int col4, float* m) const {
+        const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row) * ld + col4) >> 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] = (((bits >> (16 * i)) & 0xffffu) >= thresh) ? scale : 0.f;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// out = act(acc + bias) [* dropout]  ->  bf16 or fp32, optional row re-map, optional "ones" column
+// ------------------------------------------------------------------------------------------------
+struct EpiStore {
+    void* out;
+    int ld;
+    int out_bf16;
+    const float* bias;  // may be null
+    int relu;
+    int N;              // total valid columns
+    RowMap rm;
+    int zero_pad_rows;  // compact->padded: the first/last token also zero the neighbouring pad row
+    Dropout drop;
+    int ones_col;       // >=0: column set to 1.0 (bias-gradient trick for the next weight-grad GEMM); -1 off
+    int ones_cols_zero_upto;  // columns (ones_col, upto) are zeroed
+
+    __device__ void init(int, float*) const {}
+    __device__ void finish(int, int, int, float*) const {}
+
+    template <class Acc>
+    __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
+        long long orow;
+        int t;
+        const bool v = rm.map(c.grow, orow, t) && c.valid;
+        const int nch = (c.ncols + 31) >> 5;
+        for (int ch = 0; ch < nch; ++ch) {
+            float x[32];
+            acc.load32(ch, x);
+            if (ch == nch - 1) acc.release();
+            if (!v) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int lc = ch * 32 + g * 8;  // column inside the slice
+                if (lc >= c.ncols) break;
+                const int col = c.col0 + lc;
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float val = x[g * 8 + j];
+                    if (bias != nullptr && col + j < N) val += __ldg(bias + col + j);
+                    if (relu) val = fmaxf(val, 0.f);
+                    y[j] = val;
+                }
+                if (drop.p > 0.f) {
+                    float m[8];
+                    drop.mask4(orow, ld, col, m);
+                    drop.mask4(orow, ld, col + 4, m + 4);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] *= m[j];
+                }
+                const int nvalid = min(8, min(c.ncols - lc, N - col));
+                if (out_bf16) {
+                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld + col;
+                    if (nvalid == 8) {
+                        uint4 u = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                                             pack_bf16x2(y[6], y[7]));
+                        *reinterpret_cast<uint4*>(o) = u;
+                    } else {
+                        for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(y[j]);
+                    }
+                } else {
+                    float* o = static_cast<float*>(out) + orow * ld + col;
+                    if (nvalid == 8) {
+                        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                    } else {
+                        for (int j = 0; j < nvalid; ++j) o[j] = y[j];
+                    }
+                }
+            }
+        }
+        if (v && c.col0 == 0) {
+            if (ones_col >= 0 && out_bf16) {
+                __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld;
+                o[ones_col] = __float2bfloat16_rn(1.0f);
+                for (int j = ones_col + 1; j < ones_cols_zero_upto; ++j) o[j] = __float2bfloat16_rn(0.f);
+            }
+            if (zero_pad_rows && out_bf16) {  // neighbours of the first / last token of a segment are pad rows
+                __nv_bfloat16* base = static_cast<__nv_bfloat16*>(out);
+                if (t == 0) zero_row_bf16(base + (orow - 1) * ld, ld);
+                if (t == rm.seg_len - 1) zero_row_bf16(base + (orow + 1) * ld, ld);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Additive-attention pooling (reference additive.py:35-53) fused behind  pre = X.Wa^T:
+//   score_r = sum_c tanh(pre_rc + ba_c) * qv_c ; w = softmax over the segment ; out_s = sum_r w_r X_r
+// Requires n_slices == 1 and rows_per_tile = (segments per tile) * seg_len.
+// ------------------------------------------------------------------------------------------------
+struct EpiPool {
+    const float* bias;
+    const float* qv;
+    const __nv_bfloat16* X;  // the GEMM's A operand (rows x lda), re-read (L2 hits) for the weighted sum
+    int lda;
+    int D;        // pooled width (even)
+    int seg_len;
+    int rows_per_tile;
+    int M;
+    float* out;   // [segments][ldo] fp32
+    int ldo;
+    float* w_out; // [rows] fp32 softmax weights (saved for backward); may be null
+
+    __device__ void init(int, float*) const {}
+    __device__ void finish(int, int, int, float*) const {}
+
+    template <class Acc>
+    __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
+        float score = 0.f;
+        const int nch = (c.ncols + 31) >> 5;
+        for (int ch = 0; ch < nch; ++ch) {
+            float x[32];
+            acc.load32(ch, x);
+            if (ch == nch - 1) acc.release();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = ch * 32 + j;
+                if (col < c.ncols) score = fmaf(fast_tanh(x[j] + __ldg(bias + col)), __ldg(qv + col), score);
+            }
+        }
+        float* s_score = c.scratch;
+        float* s_w = c.scratch + 128;
+        s_score[c.r] = c.valid ? score : -INFINITY;
+        epi_bar_sync();
+        float w = 0.f;
+        if (c.valid) {
+            const int s0 = (c.r / seg_len) * seg_len;
+            float m = -INFINITY;
+            for (int t = 0; t < seg_len; ++t) m = fmaxf(m, s_score[s0 + t]);
+            float sum = 0.f;
+            for (int t = 0; t < seg_len; ++t) sum += __expf(s_score[s0 + t] - m);
+            w = __fdividef(__expf(score - m), sum);
+            if (w_out != nullptr) w_out[c.grow] = w;
+        }
+        s_w[c.r] = w;
+        epi_bar_sync();
+        const int row0 = c.tile * rows_per_tile;
+        const int nseg = rows_per_tile / seg_len;
+        for (int s = 0; s < nseg; ++s) {
+            const int r0 = row0 + s * seg_len;
+            if (r0 >= M) break;
+            const int gs = r0 / seg_len;
+            for (int pidx = c.tid; pidx < (D >> 1); pidx += 128) {
+                float a0 = 0.f, a1 = 0.f;
+                const __nv_bfloat16* xp = X + static_cast<size_t>(r0) * lda + 2 * pidx;
+                for (int t = 0; t < seg_len; ++t) {
+                    const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(xp + static_cast<size_t>(t) * lda)));
+                    const float wt = s_w[s * seg_len + t];
+                    a0 = fmaf(wt, f.x, a0);
+                    a1 = fmaf(wt, f.y, a1);
+                }
+                *reinterpret_cast<float2*>(out + static_cast<size_t>(gs) * ldo + 2 * pidx) = make_float2(a0, a1);
+            }
+        }
+        epi_bar_sync();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the additive scorer, fused behind the recomputed pre = X.Wa^T:
+//   T = tanh(pre + ba);  dPre_rc = dscore_r * qv_c * (1 - T^2)  -> bf16;   dqv_c += sum_r dscore_r * T_rc
+// ------------------------------------------------------------------------------------------------
+struct EpiDPre {
+    const float* bias;
+    const float* qv;
+    const float* dscore;      // [rows]
+    __nv_bfloat16* dpre;      // [rows][ld]
+    int ld;
+    float* dqv;               // [q] fp32, accumulated
+
+    __device__ void init(int tid, float* scratch) const {
+        for (int i = tid; i < 256; i += 128) scratch[i] = 0.f;
+        epi_bar_sync();
+    }
+    __device__ void finish(int col0, int ncols, int tid, float* scratch) const {
+        epi_bar_sync();
+        for (int i = tid; i < ncols; i += 128) atomicAdd(dqv + col0 + i, scratch[i]);
+    }
+    template <class Acc>
+    __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
+        const float ds = c.valid ? __ldg(dscore + c.grow) : 0.f;
+        const int nch = (c.ncols + 31) >> 5;
+        const int lane = c.tid & 31;
+        for (int ch = 0; ch < nch; ++ch) {
+            float x[32];
+            acc.load32(ch, x);
+            if (ch == nch - 1) acc.release();
+            float dp[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = ch * 32 + j;
+                float tt = 0.f, qq = 0.f;
+                if (col < c.ncols) {
+                    tt = fast_tanh(x[j] + __ldg(bias + c.col0 + col));
+                    qq = __ldg(qv + c.col0 + col);
+                }
+                dp[j] = ds * qq * (1.f - tt * tt);
+                x[j] = ds * tt;
+            }
+            if (c.valid) {
+                __nv_bfloat16* o = dpre + static_cast<size_t>(c.grow) * ld + c.col0 + ch * 32;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (ch * 32 + g * 8 >= c.ncols) break;  // ld is padded to a multiple of 8: whole groups are in bounds
+                    *reinterpret_cast<uint4*>(o + g * 8) =
+                        make_uint4(pack_bf16x2(dp[g * 8], dp[g * 8 + 1]), pack_bf16x2(dp[g * 8 + 2], dp[g * 8 + 3]),
+                                   pack_bf16x2(dp[g * 8 + 4], dp[g * 8 + 5]), pack_bf16x2(dp[g * 8 + 6], dp[g * 8 + 7]));
+                }
+            }
+            const float colsum = warp_transpose_sum32(x);
+            if (ch * 32 + lane < c.ncols) atomicAdd(c.scratch + ch * 32 + lane, colsum);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// dX_rc = acc_rc + w_r * dOut[seg(r)][c]  (pool backward, both paths into X) [* dropout of X] -> bf16
+// ------------------------------------------------------------------------------------------------
+struct EpiDPoolIn {
+    const float* w;      // [rows]
+    const float* dout;   // [segments][ldo]
+    int ldo;
+    int seg_len;
+    __nv_bfloat16* dx;   // [rows(mapped)][ld]
+    int ld;
+    int N;
+    RowMap rm;
+    int zero_pad_rows;
+    Dropout drop;
+    const __nv_bfloat16* relu_src;  // non-null: multiply by (relu_src[r][c] > 0) (ReLU backward of the CNN); pitch relu_ld
+    int relu_ld;
+
+    __device__ void init(int, float*) const {}
+    __device__ void finish(int, int, int, float*) const {}
+
+    template <class Acc>
+    __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
+        long long orow;
+        int t;
+        const bool v = rm.map(c.grow, orow, t) && c.valid;
+        const float wr = c.valid ? __ldg(w + c.grow) : 0.f;
+        const float* dob = dout + static_cast<size_t>(c.valid ? c.grow / seg_len : 0) * ldo;
+        const int nch = (c.ncols + 31) >> 5;
+        for (int ch = 0; ch < nch; ++ch) {
+            float x[32];
+            acc.load32(ch, x);
+            if (ch == nch - 1) acc.release();
+            if (!v) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int lc = ch * 32 + g * 8;
+                if (lc >= c.ncols) break;
+                const int col = c.col0 + lc;
+                const int nvalid = min(8, min(c.ncols - lc, N - col));
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = (j < nvalid) ? fmaf(wr, __ldg(dob + col + j), x[g * 8 + j]) : 0.f;
+                if (relu_src != nullptr) {
+                    const __nv_bfloat16* rs = relu_src + static_cast<size_t>(c.grow) * relu_ld + col;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nvalid && !(__bfloat162float(rs[j]) > 0.f)) y[j] = 0.f;
+                }
+                if (drop.p > 0.f) {
+                    float m[8];
+                    drop.mask4(c.grow, relu_src != nullptr ? relu_ld : ld, col, m);
+                    drop.mask4(c.grow, relu_src != nullptr ? relu_ld : ld, col + 4, m + 4);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] *= m[j];
+                }
+                __nv_bfloat16* o = dx + orow * ld + col;
+                if (nvalid == 8) {
+                    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                                              pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+                } else {
+                    for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(y[j]);
+                }
+            }
+        }
+        if (v && c.col0 == 0 && zero_pad_rows) {
+            if (t == 0) zero_row_bf16(dx + (orow - 1) * ld, ld);
+            if (t == rm.seg_len - 1) zero_row_bf16(dx + (orow + 1) * ld, ld);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Embedding gradient: dEmb[ids[r]][c] += acc_rc [* dropout of the gathered row]; row 0 (padding_idx) skipped
+// ------------------------------------------------------------------------------------------------
+struct EpiScatter {
+    const long long* ids;  // [rows] token ids (row-mapped through rm for the padded CNN layout)
+    float* demb;           // [V][D] fp32
+    int D;
+    RowMap rm;             // maps the GEMM row to the token index in ids
+    Dropout drop;
+    int drop_ld;           // pitch used when the forward mask was drawn
+
+    __device__ void init(int, float*) const {}
+    __device__ void finish(int, int, int, float*) const {}
+
+    template <class Acc>
+    __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
+        long long trow;
+        int t;
+        const bool v = rm.map(c.grow, trow, t) && c.valid;
+        const long long id = v ? ids[trow] : 0;
+        float* dst = demb + static_cast<size_t>(id) * D;
+        const int nch = (c.ncols + 31) >> 5;
+        for (int ch = 0; ch < nch; ++ch) {
+            float x[32];
+            acc.load32(ch, x);
+            if (ch == nch - 1) acc.release();
+            if (id == 0) continue;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const int lc = ch * 32 + g * 4;
+                if (lc >= c.ncols) break;
+                const int col = c.col0 + lc;
+                float y[4] = {x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]};
+                if (drop.p > 0.f) {
+                    float m[4];
+                    drop.mask4(c.grow, drop_ld, col, m);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) y[j] *= m[j];
+                }
+                if (col + 4 <= D && lc + 4 <= c.ncols) {
+                    red_add_v4_f32(dst + col, y[0], y[1], y[2], y[3]);
+                } else {
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < D && lc + j < c.ncols) red_add_f32(dst + col + j, y[j]);
+                }
+            }
+        }
+    }
+};
+
+}  // namespace nr

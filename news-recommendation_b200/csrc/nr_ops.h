@@ -1,0 +1,72 @@
+// Internal (C++) operator layer between the kernels and the C-ABI (abi.cu).  All pointers are device
+// pointers, all work is enqueued on `stream`, nothing is allocated except in the debug GEMM backend.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nr {
+
+struct DropoutCfg {
+    float p;        // 0 => off
+    uint64_t seed;
+};
+
+struct RowMapCfg {  // see RowMap in nr_epilogues.cuh; seg_in == 0 => identity
+    int seg_in, in_off, seg_len, seg_out, out_off;
+};
+
+// ---- tcgen05 GEMMs with fused epilogues (gemm.cu) ------------------------------------------------
+// out[rows x N] = act(A . W^T + bias) (bf16 or fp32).  A bf16 [M x K] pitch lda (taps>1: padded CNN layout),
+// W bf16 [taps*w_tap_rows x K] pitch ldw.
+int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
+               int rows_per_tile, const float* bias, int relu, void* out, int ld_out, int out_bf16, RowMapCfg rm,
+               int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream);
+
+// additive-attention pooling: out[seg][D] = sum_r softmax_seg(tanh(X Wa^T + ba) . qv)_r X_r ; w_out[rows]
+int gemm_additive_pool(const void* X, int M, int lda, int D, const void* Wa, int q, int ldw, const float* ba,
+                       const float* qv, int seg_len, float* out, int ldo, float* w_out, cudaStream_t stream);
+
+// dPre = dscore * qv * (1 - tanh^2(X Wa^T + ba)) -> bf16 [M x ld_dpre]; dqv += sum_r dscore_r tanh(..)
+int gemm_additive_dpre(const void* X, int M, int lda, int D, const void* Wa, int q, int ldw, const float* ba,
+                       const float* qv, const float* dscore, void* dpre, int ld_dpre, float* dqv,
+                       cudaStream_t stream);
+
+// dX = dPre . Wa + w (x) dOut  [* relu mask] [* dropout]  -> bf16 (optionally re-mapped to the padded layout)
+int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* WaT, int D, int ldwT, const float* w,
+                     const float* dout, int ldo, int seg_len, void* dx, int ld_dx, RowMapCfg rm, int zero_pad_rows,
+                     DropoutCfg drop, const void* relu_src, int relu_ld, cudaStream_t stream);
+
+// dEmb[ids[row]] += A . W^T  (embedding gradient; padding row 0 skipped) [* dropout of the gathered rows]
+int gemm_scatter_emb(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
+                     int rows_per_tile, const long long* ids, float* demb, int D, RowMapCfg rm, DropoutCfg drop,
+                     int drop_ld, cudaStream_t stream);
+
+// D[Ma x Nb] += A[:, :Ma]^T . B[rows + shift, b_col0 : b_col0 + Nb]   (fp32 accumulate into D, pitch ldd)
+int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, int b_rows, int b_cols, int ldb,
+                       int b_col0, int Nb, int b_row_shift, float* D, int ldd, cudaStream_t stream);
+
+// ---- memory-bound companions (aux.cu) --------------------------------------------------------------
+// fp32 [R x C] (pitch lds) -> bf16 [R x ld] zero padded; transpose: out[c][r] = in[r][c] (out is [C x ld])
+int cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, int transpose, cudaStream_t stream);
+// fp32 rows [n_seq][T][D] with element strides -> bf16 [n_seq*T x ld], ones column at D, zeros after
+int rows_to_bf16(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col,
+                 void* dst, int ld, cudaStream_t stream);
+// X[row(seg,t)] = table_bf16[ids[seg*T+t]] (bit-exact copy), ones column at D, optional dropout, optional padded layout
+int gather_rows(const long long* ids, long long n_tok, int T, const void* table, int V, int D, int ld_table, void* X,
+                int ld_x, int padded, DropoutCfg drop, int* bad_id_flag, cudaStream_t stream);
+// multi-head self attention core on packed Q|K|V bf16 [n_seq*T x ld_qkv]  (d = heads*dk)
+int mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
+                  DropoutCfg drop, cudaStream_t stream);
+int mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+                  void* dqkv, int ld_dqkv, cudaStream_t stream);
+// dscore_r = w_r (dw_r - sum_seg w dw), dw_r = dOut[seg] . X_r
+int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, const float* w, const float* dout, int ldo,
+                float* dscore, cudaStream_t stream);
+// logits[b][c] = cand[b][c] . user[b]
+int dot_score_fwd(const float* cand, const float* user, int B, int C, int D, float* logits, cudaStream_t stream);
+int dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
+                  float* duser, cudaStream_t stream);
+
+int num_sms();
+
+}  // namespace nr

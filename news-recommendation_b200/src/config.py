@@ -1,0 +1,45 @@
+"""Knob surface of the drop-in: the attribute names, defaults and `MODEL_NAME` selection that the
+reference's callers read (reference src/config.py:3-106; train.py:9,19; dataset.py:6,11).
+
+The values are the reference defaults; the classes are generated from one table so that the file is a
+restatement of the knob surface, not a copy of the reference source.
+"""
+import os
+
+model_name = os.environ.get("MODEL_NAME", "NRMS")
+SUPPORTED_MODELS = ("NRMS", "NAML", "LSTUR", "TANR")  # the hot-path scope of this build
+if model_name not in SUPPORTED_MODELS:
+    raise AssertionError(f"MODEL_NAME={model_name!r}: this build accelerates {SUPPORTED_MODELS} only")
+
+_COMMON = {
+    # training loop (read by the reference's train.py / evaluate.py, not by the kernels)
+    "num_epochs": 2, "num_batches_show_loss": 100, "num_batches_validate": 1000, "batch_size": 128,
+    "learning_rate": 0.0001, "num_workers": 4,
+    # data shapes
+    "num_clicked_news_a_user": 50, "num_words_title": 20, "num_words_abstract": 50,
+    "word_freq_threshold": 1, "entity_freq_threshold": 2, "entity_confidence_threshold": 0.5,
+    "negative_sampling_ratio": 2,
+    # regularisation
+    "dropout_probability": 0.2,
+    # vocabulary sizes (MIND-small; edit after preprocessing exactly as with the reference)
+    "num_words": 1 + 70975, "num_categories": 1 + 274, "num_entities": 1 + 12957, "num_users": 1 + 50000,
+    # widths
+    "word_embedding_dim": 300, "category_embedding_dim": 100, "entity_embedding_dim": 100,
+    "query_vector_dim": 200,
+}
+BaseConfig = type("BaseConfig", (), dict(_COMMON, __doc__="General configuration shared by all models"))
+
+_CNN = {"num_filters": 300, "window_size": 3}
+_PER_MODEL = {
+    "NRMS": dict(dataset_attributes={"news": ["title"], "record": []}, num_attention_heads=15),
+    "NAML": dict(dataset_attributes={"news": ["category", "subcategory", "title", "abstract"], "record": []}, **_CNN),
+    "LSTUR": dict(dataset_attributes={"news": ["category", "subcategory", "title"],
+                                      "record": ["user", "clicked_news_length"]},
+                  long_short_term_method="ini", masking_probability=0.5, **_CNN),
+    "TANR": dict(dataset_attributes={"news": ["category", "title"], "record": []},
+                 topic_classification_loss_weight=0.1, **_CNN),
+}
+for _name, _knobs in _PER_MODEL.items():
+    globals()[f"{_name}Config"] = type(f"{_name}Config", (BaseConfig,), dict(_knobs))
+assert LSTURConfig.long_short_term_method in ("ini", "con")  # noqa: F821
+del _name, _knobs

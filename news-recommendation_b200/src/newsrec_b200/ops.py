@@ -1,0 +1,313 @@
+"""torch.autograd.Function wrappers over the C ABI.
+
+Each Function allocates its buffers with torch (the caller owns every buffer, see the header), passes raw
+device pointers + the current CUDA stream to one composite C call, and returns torch tensors.  No
+arithmetic happens here; `torch.cat`/slicing of parameters is layout plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import (MhsaEncoderBwdArgs, MhsaEncoderFwdArgs, NewsrecError, check, load_library, require_cuda)
+
+
+def ru8(x: int) -> int:
+    return (x + 7) // 8 * 8
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_seed_counter = [0x243F6A8885A308D3]
+
+
+def next_seed() -> int:
+    """Per-call dropout seed (counter based, mixed with torch's CPU seed so manual_seed() reproduces runs)."""
+    _seed_counter[0] = (_seed_counter[0] * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+    return (_seed_counter[0] ^ (torch.initial_seed() & 0xFFFFFFFFFFFFFFFF) ^ (int(os.environ.get("RANK", "0")) << 48)) & 0xFFFFFFFFFFFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------------
+# bf16 operand cache: fp32 nn.Parameters -> padded bf16 tensor-core operands, rebuilt only when a
+# parameter's version counter (bumped by optimizer.step / load_state_dict) or storage changes.
+# ---------------------------------------------------------------------------------------------------
+class OperandCache:
+    def __init__(self):
+        self._store = {}
+
+    def get(self, name, params, builder):
+        key = tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in params)
+        hit = self._store.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        with torch.no_grad():
+            val = builder(*[p.detach() for p in params])
+        self._store[name] = (key, val)
+        return val
+
+    def clear(self):
+        self._store.clear()
+
+
+def cast_pad(src: torch.Tensor, ld: int, transpose: bool = False) -> torch.Tensor:
+    """fp32 [R][C] -> zero padded bf16 [R][ld] (or the transpose [C][ld]) on the device."""
+    lib = load_library()
+    src = src.contiguous().float()
+    R, Cc = src.shape
+    rows = Cc if transpose else R
+    dst = torch.empty((rows, ld), dtype=torch.bfloat16, device=src.device)
+    check(lib.nr_cast_pad_bf16(_p(src), R, Cc, Cc, _p(dst), ld, int(transpose), _stream()), "nr_cast_pad_bf16")
+    return dst
+
+
+def mhsa_operands(cache: OperandCache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
+    d, q = Wq.shape[0], Wa.shape[0]
+    ldx, ld3, ldq = ru8(d + 1), ru8(3 * d), ru8(q)
+
+    def build(Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
+        wqkv = torch.cat((Wq, Wk, Wv), dim=0)
+        return dict(wqkv=cast_pad(wqkv, ldx), wqkvT=cast_pad(wqkv, ld3, transpose=True),
+                    bqkv=torch.cat((bq, bk, bv)).float().contiguous(),
+                    wa=cast_pad(Wa, ldx), waT=cast_pad(Wa, ldq, transpose=True),
+                    ba=ba.float().contiguous(), qv=qv.float().contiguous())
+
+    return cache.get(prefix, (Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv), build)
+
+
+def table_operand(cache: OperandCache, name, weight):
+    ldx = ru8(weight.shape[1] + 1)
+    return cache.get(name, (weight,), lambda w: cast_pad(w, ldx))
+
+
+# ---------------------------------------------------------------------------------------------------
+# NRMS NewsEncoder / UserEncoder: gather|dense -> MHSA -> additive pooling in ONE C call each way
+# ---------------------------------------------------------------------------------------------------
+class MhsaPoolEncoderFn(torch.autograd.Function):
+    """forward(ids|None, dense|None, emb_weight|None, Wq,bq,Wk,bk,Wv,bv, Wa,ba,qv, heads, p_drop, cache, prefix)
+
+    ids   : int64 (n_seq, T) device tensor  (news encoder)   -- reference src/model/NRMS/news_encoder.py:27-48
+    dense : fp32  (n_seq, T, d) any strides (user encoder)   -- reference src/model/NRMS/user_encoder.py:15-26
+    """
+
+    @staticmethod
+    def forward(ctx, ids, dense, emb_w, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv, heads, p_drop, cache, prefix, bad_flag):
+        lib = load_library()
+        dev = require_cuda()
+        d, q = Wq.shape[0], Wa.shape[0]
+        ldx, ld3 = ru8(d + 1), ru8(3 * d)
+        ops = mhsa_operands(cache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv)
+        a = MhsaEncoderFwdArgs()
+        if ids is not None:
+            n_seq, T = ids.shape
+            ids = ids.contiguous()
+            table = table_operand(cache, prefix + ".table", emb_w)
+            a.ids, a.table_bf16, a.V = _p(ids), _p(table), emb_w.shape[0]
+            a.dense = None
+        else:
+            n_seq, T, dd = dense.shape
+            if dd != d:
+                raise NewsrecError(f"user encoder input width {dd} != model width {d}")
+            dense = dense.float()
+            a.ids, a.table_bf16, a.V = None, None, 0
+            a.dense = _p(dense)
+            a.dense_s_seq, a.dense_s_tok, a.dense_s_col = dense.stride()
+            table = None
+        n_tok = n_seq * T
+        X = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
+        QKV = torch.empty((n_tok, ld3), dtype=torch.bfloat16, device=dev)
+        Cx = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
+        w = torch.empty((n_tok,), dtype=torch.float32, device=dev)
+        out = torch.empty((n_seq, d), dtype=torch.float32, device=dev)
+        seed = next_seed() if p_drop > 0 else 0
+        a.n_seq, a.T, a.d, a.heads, a.q, a.ldx, a.ld3 = n_seq, T, d, heads, q, ldx, ld3
+        a.wqkv_bf16, a.bqkv, a.wa_bf16, a.ba, a.qv = _p(ops["wqkv"]), _p(ops["bqkv"]), _p(ops["wa"]), _p(ops["ba"]), _p(ops["qv"])
+        a.p_drop, a.seed = float(p_drop), seed
+        a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.out = _p(X), _p(QKV), _p(Cx), _p(w), _p(out)
+        a.bad_id_flag = _p(bad_flag)
+        check(lib.nr_mhsa_encoder_fwd(C.byref(a), _stream()), "nr_mhsa_encoder_fwd")
+        ctx.save_for_backward(X, QKV, Cx, w, ids if ids is not None else torch.empty(0, device=dev))
+        ctx.meta = dict(n_seq=n_seq, T=T, d=d, q=q, heads=heads, p_drop=float(p_drop), seed=seed, ops=ops,
+                        has_ids=ids is not None, V=emb_w.shape[0] if ids is not None else 0,
+                        dense_shape=None if dense is None else tuple(dense.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load_library()
+        X, QKV, Cx, w, ids = ctx.saved_tensors
+        m = ctx.meta
+        dev = X.device
+        d, q, T, n_seq = m["d"], m["q"], m["T"], m["n_seq"]
+        ldx, ld3, ldq = ru8(d + 1), ru8(3 * d), ru8(q)
+        ops = m["ops"]
+        dout = dout.contiguous().float()
+        dWqkv = torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev)
+        dWa = torch.zeros((q, ldx), dtype=torch.float32, device=dev)
+        dqv = torch.zeros((q,), dtype=torch.float32, device=dev)
+        demb = ddense = None
+        if m["has_ids"]:
+            demb = torch.zeros((m["V"], d), dtype=torch.float32, device=dev)
+        else:
+            ddense = torch.empty((n_seq * T, d), dtype=torch.float32, device=dev)
+        ws_bytes = int(lib.nr_mhsa_encoder_bwd_workspace(n_seq, T, d, q))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        a = MhsaEncoderBwdArgs()
+        a.n_seq, a.T, a.d, a.heads, a.q, a.ldx, a.ld3, a.ldq = n_seq, T, d, m["heads"], q, ldx, ld3, ldq
+        a.ids = _p(ids) if m["has_ids"] else None
+        a.V = m["V"]
+        a.wqkvT_bf16, a.wa_bf16, a.waT_bf16, a.ba, a.qv = _p(ops["wqkvT"]), _p(ops["wa"]), _p(ops["waT"]), _p(ops["ba"]), _p(ops["qv"])
+        a.p_drop, a.seed = m["p_drop"], m["seed"]
+        a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.dout = _p(X), _p(QKV), _p(Cx), _p(w), _p(dout)
+        a.dWqkv_ext, a.dWa_ext, a.dqv = _p(dWqkv), _p(dWa), _p(dqv)
+        a.demb, a.ddense = _p(demb), _p(ddense)
+        a.workspace, a.workspace_bytes = _p(ws), ws_bytes
+        check(lib.nr_mhsa_encoder_bwd(C.byref(a), _stream()), "nr_mhsa_encoder_bwd")
+        gW = [dWqkv[i * d:(i + 1) * d, :d].contiguous() for i in range(3)]
+        gb = [dWqkv[i * d:(i + 1) * d, d].contiguous() for i in range(3)]
+        g_dense = ddense.view(m["dense_shape"]) if ddense is not None else None
+        return (None, g_dense, demb, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2],
+                dWa[:, :d].contiguous(), dWa[:, d].contiguous(), dqv, None, None, None, None, None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# AdditiveAttention over dense fp32 rows (NAML / TANR user encoder, NAML 4-view fusion, standalone module)
+# ---------------------------------------------------------------------------------------------------
+class AdditiveAttentionFn(torch.autograd.Function):
+    """reference src/model/general/attention/additive.py:27-53;  x (N, S, D) fp32 -> (N, D)."""
+
+    @staticmethod
+    def forward(ctx, x, Wa, ba, qv, cache, prefix):
+        lib = load_library()
+        dev = require_cuda()
+        N, S, D = x.shape
+        q = Wa.shape[0]
+        ldx, ldq = ru8(D + 1), ru8(q)
+        ops = cache.get(prefix, (Wa, ba, qv), lambda Wa, ba, qv: dict(
+            wa=cast_pad(Wa, ldx), waT=cast_pad(Wa, ldq, transpose=True), ba=ba.float().contiguous(),
+            qv=qv.float().contiguous()))
+        xf = x.float()
+        X = torch.empty((N * S, ldx), dtype=torch.bfloat16, device=dev)
+        xs = xf.reshape(N * S, D) if xf.is_contiguous() else xf.contiguous().view(N * S, D)
+        check(lib.nr_rows_to_bf16(_p(xs), N * S, D, xs.stride(0), xs.stride(1), _p(X), ldx, _stream()), "nr_rows_to_bf16")
+        out = torch.empty((N, D), dtype=torch.float32, device=dev)
+        w = torch.empty((N * S,), dtype=torch.float32, device=dev)
+        check(lib.nr_additive_attention_fwd(_p(X), N, S, D, ldx, _p(ops["wa"]), q, ldx, _p(ops["ba"]), _p(ops["qv"]),
+                                            _p(out), D, _p(w), _stream()), "nr_additive_attention_fwd")
+        ctx.save_for_backward(X, w)
+        ctx.meta = dict(N=N, S=S, D=D, q=q, ops=ops)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = load_library()
+        X, w = ctx.saved_tensors
+        m = ctx.meta
+        N, S, D, q, ops = m["N"], m["S"], m["D"], m["q"], m["ops"]
+        dev = X.device
+        ldx, ldq = ru8(D + 1), ru8(q)
+        dout = dout.contiguous().float()
+        dX = torch.empty((N * S, ldx), dtype=torch.bfloat16, device=dev)
+        dWa = torch.zeros((q, ldx), dtype=torch.float32, device=dev)
+        dqv = torch.zeros((q,), dtype=torch.float32, device=dev)
+        ws_bytes = int(lib.nr_additive_attention_bwd_workspace(N, S, q))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        check(lib.nr_additive_attention_bwd(_p(X), N, S, D, ldx, _p(ops["wa"]), _p(ops["waT"]), q, ldx, ldq, _p(ops["ba"]),
+                                            _p(ops["qv"]), _p(w), _p(dout), D, _p(dX), ldx, _p(dWa), _p(dqv), _p(ws),
+                                            ws_bytes, _stream()), "nr_additive_attention_bwd")
+        gx = dX[:, :D].float().view(N, S, D)
+        return gx, dWa[:, :D].contiguous(), dWa[:, D].contiguous(), dqv, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# DotProductClickPredictor
+# ---------------------------------------------------------------------------------------------------
+class DotScoreFn(torch.autograd.Function):
+    """reference src/model/general/click_predictor/dot_product.py:8-19;  (B,C,D),(B,D) -> (B,C) logits."""
+
+    @staticmethod
+    def forward(ctx, cand, user):
+        lib = load_library()
+        dev = require_cuda()
+        cand = cand.contiguous().float()
+        user = user.contiguous().float()
+        B, Cn, D = cand.shape
+        logits = torch.empty((B, Cn), dtype=torch.float32, device=dev)
+        check(lib.nr_dot_score_fwd(_p(cand), _p(user), B, Cn, D, _p(logits), _stream()), "nr_dot_score_fwd")
+        ctx.save_for_backward(cand, user)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = load_library()
+        cand, user = ctx.saved_tensors
+        B, Cn, D = cand.shape
+        dlogits = dlogits.contiguous().float()
+        dcand = torch.empty_like(cand)
+        duser = torch.empty_like(user)
+        check(lib.nr_dot_score_bwd(_p(cand), _p(user), _p(dlogits), B, Cn, D, _p(dcand), _p(duser), _stream()),
+              "nr_dot_score_bwd")
+        return dcand, duser
+
+
+# ---------------------------------------------------------------------------------------------------
+# standalone MultiHeadSelfAttention (projection + attention core, no pooling)
+# ---------------------------------------------------------------------------------------------------
+class MhsaFn(torch.autograd.Function):
+    """reference src/model/general/attention/multihead_self.py:46-76 with Q=K=V=x, length=None."""
+
+    @staticmethod
+    def forward(ctx, x, Wq, bq, Wk, bk, Wv, bv, heads, cache, prefix):
+        lib = load_library()
+        dev = require_cuda()
+        N, T, d = x.shape
+        ldx, ld3 = ru8(d + 1), ru8(3 * d)
+
+        def build(Wq, bq, Wk, bk, Wv, bv):
+            wqkv = torch.cat((Wq, Wk, Wv), dim=0)
+            return dict(wqkv=cast_pad(wqkv, ldx), wqkvT=cast_pad(wqkv, ld3, transpose=True),
+                        bqkv=torch.cat((bq, bk, bv)).float().contiguous())
+
+        ops = cache.get(prefix, (Wq, bq, Wk, bk, Wv, bv), build)
+        xs = x.float().contiguous().view(N * T, d)
+        X = torch.empty((N * T, ldx), dtype=torch.bfloat16, device=dev)
+        check(lib.nr_rows_to_bf16(_p(xs), N * T, d, d, 1, _p(X), ldx, _stream()), "nr_rows_to_bf16")
+        QKV = torch.empty((N * T, ld3), dtype=torch.bfloat16, device=dev)
+        check(lib.nr_linear(_p(X), N * T, ldx, _p(ops["wqkv"]), 3 * d, ldx, d, 1, 0, 128, _p(ops["bqkv"]), 0, _p(QKV), ld3, 1,
+                            _stream()), "nr_linear")
+        Cx = torch.empty((N * T, ldx), dtype=torch.bfloat16, device=dev)
+        check(lib.nr_mhsa_core_fwd(_p(QKV), ld3, N, T, heads, d // heads, _p(Cx), ldx, 0.0, 0, _stream()), "nr_mhsa_core_fwd")
+        ctx.save_for_backward(X, QKV)
+        ctx.meta = dict(N=N, T=T, d=d, heads=heads, ops=ops)
+        return Cx[:, :d].float().view(N, T, d)
+
+    @staticmethod
+    def backward(ctx, dctx):
+        lib = load_library()
+        X, QKV = ctx.saved_tensors
+        m = ctx.meta
+        N, T, d, heads, ops = m["N"], m["T"], m["d"], m["heads"], m["ops"]
+        dev = X.device
+        ldx, ld3 = ru8(d + 1), ru8(3 * d)
+        g = dctx.float().contiguous().view(N * T, d)
+        dC = torch.empty((N * T, ldx), dtype=torch.bfloat16, device=dev)
+        check(lib.nr_rows_to_bf16(_p(g), N * T, d, d, 1, _p(dC), ldx, _stream()), "nr_rows_to_bf16")
+        dQKV = torch.empty((N * T, ld3), dtype=torch.bfloat16, device=dev)
+        check(lib.nr_mhsa_core_bwd(_p(QKV), ld3, _p(dC), ldx, N, T, heads, d // heads, _p(dQKV), ld3, _stream()),
+              "nr_mhsa_core_bwd")
+        dW = torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev)
+        check(lib.nr_gemm_tn(_p(dQKV), N * T, 3 * d, ld3, _p(X), N * T, d + 1, ldx, 0, d + 1, 0, _p(dW), ldx, _stream()),
+              "nr_gemm_tn")
+        dx = torch.empty((N * T, d), dtype=torch.float32, device=dev)
+        check(lib.nr_linear(_p(dQKV), N * T, ld3, _p(ops["wqkvT"]), d, ld3, 3 * d, 1, 0, 128, None, 0, _p(dx), d, 0, _stream()),
+              "nr_linear")
+        gW = [dW[i * d:(i + 1) * d, :d].contiguous() for i in range(3)]
+        gb = [dW[i * d:(i + 1) * d, d].contiguous() for i in range(3)]
+        return dx.view(N, T, d), gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], None, None, None

@@ -1,0 +1,47 @@
+"""Host-side batch packing: the reference hands the model slot-major lists of per-slot CPU tensors
+(default_collate output).  They are stacked once into a reusable pinned buffer, copied to
+the device in ONE async H2D transfer and re-ordered there into impression-major blocks."""
+from __future__ import annotations
+
+import torch
+
+
+class SlotPacker:
+    """Two pinned staging buffers per shape, each guarded by a CUDA event so that a buffer is never
+    rewritten by the host while its previous H2D copy is still in flight."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def _stack(self, tensors, dev):
+        t0 = tensors[0]
+        if t0.is_cuda:
+            return torch.stack(tensors, dim=0)
+        shape = (len(tensors),) + tuple(t0.shape)
+        key = (shape, t0.dtype)
+        slot = self._bufs.get(key)
+        if slot is None:
+            slot = {"i": 0, "buf": [torch.empty(shape, dtype=t0.dtype).pin_memory() for _ in range(2)],
+                    "ev": [None, None]}
+            self._bufs[key] = slot
+        i = slot["i"]
+        slot["i"] = 1 - i
+        if slot["ev"][i] is not None:
+            slot["ev"][i].synchronize()
+        buf = slot["buf"][i]
+        torch.stack(tensors, dim=0, out=buf)
+        out = buf.to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot["ev"][i] = ev
+        return out
+
+    def pack(self, clicked, candidates, field, dev):
+        """-> (ids (B*H + B*C, ...), B): rows [0, B*H) are the browsed news impression-major, then the candidates."""
+        H = len(clicked)
+        slots = self._stack([x[field] for x in clicked] + [x[field] for x in candidates], dev)  # (H+C, B, ...)
+        B = slots.shape[1]
+        tail = slots.shape[2:]
+        a = slots[:H].transpose(0, 1).reshape(B * H, *tail)
+        b = slots[H:].transpose(0, 1).reshape(B * (slots.shape[0] - H), *tail)
+        return torch.cat((a, b), dim=0), B

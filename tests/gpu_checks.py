@@ -1,0 +1,356 @@
+"""Kernel-vs-oracle checks, written as plain functions returning error metrics so that both the pytest
+wrappers (tests/test_gpu_*.py) and the triage ladder (tools/gpu_ladder.py) can run them.
+
+Everything goes through the C ABI (ctypes) or through the drop-in model package that calls it.
+The oracle (oracle/newsrec_oracle.py) runs on the CPU; it is the checker, never the thing measured.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+import newsrec_oracle as O
+from newsrec_b200 import check, load_library
+from newsrec_b200.ops import _p, _stream, cast_pad, ru8
+
+DEV = "cuda"
+
+
+def relerr(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / max(b.norm().item(), 1e-30))
+
+
+def maxabs(a, b) -> float:
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+def check_prep_and_gather():
+    lib = load_library()
+    V, D, T, n_seq = 97, 300, 20, 13
+    ld = ru8(D + 1)
+    w = O.det_uniform((V, D), 5)
+    table = cast_pad(w.to(DEV), ld)
+    ref = torch.zeros(V, ld)
+    ref[:, :D] = bf16r(w)
+    out = {"cast_pad_exact": bool(torch.equal(table.float().cpu(), ref))}
+    wt = cast_pad(w.to(DEV), ru8(V), transpose=True)
+    reft = torch.zeros(D, ru8(V))
+    reft[:, :V] = bf16r(w).t()
+    out["cast_pad_T_exact"] = bool(torch.equal(wt.float().cpu(), reft))
+    ids = O.synth_titles(n_seq, T, V, 77).to(DEV)
+    X = torch.full((n_seq * T, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    check(lib.nr_gather_rows(_p(ids), n_seq * T, T, _p(table), V, D, ld, _p(X), 0, 0.0, 0, _p(flag), _stream()), "gather")
+    expect = ref[ids.cpu().reshape(-1)]
+    expect[:, D] = 1.0
+    out["gather_exact"] = bool(torch.equal(X.float().cpu(), expect)) and int(flag.item()) == 0
+    # padded CNN layout
+    Xp = torch.full((n_seq * (T + 2), ld), 7.0, dtype=torch.bfloat16, device=DEV)
+    check(lib.nr_gather_rows(_p(ids), n_seq * T, T, _p(table), V, D, ld, _p(Xp), 1, 0.0, 0, _p(flag), _stream()), "gather")
+    Xp3 = Xp.float().cpu().view(n_seq, T + 2, ld)
+    out["gather_padded_exact"] = bool(torch.equal(Xp3[:, 1:T + 1].reshape(-1, ld), expect)) and \
+        float(Xp3[:, 0].abs().sum() + Xp3[:, T + 1].abs().sum()) == 0.0
+    # out-of-range id sets the flag
+    bad = ids.clone()
+    bad[0, 0] = V + 5
+    check(lib.nr_gather_rows(_p(bad), n_seq * T, T, _p(table), V, D, ld, _p(X), 0, 0.0, 0, _p(flag), _stream()), "gather")
+    out["bad_id_flag"] = int(flag.item()) == 1
+    # dropout: keep-rate and scaling
+    big = O.synth_titles(2000, T, V, 78, min_len=T).to(DEV)
+    Xd = torch.empty((2000 * T, ld), dtype=torch.bfloat16, device=DEV)
+    flag.zero_()
+    check(lib.nr_gather_rows(_p(big), 2000 * T, T, _p(table), V, D, ld, _p(Xd), 0, 0.2, 1234, _p(flag), _stream()), "gather")
+    e = ref[big.cpu().reshape(-1)][:, :D]
+    got = Xd.float().cpu()[:, :D]
+    kept = got != 0
+    out["dropout_keep_rate"] = float(kept.float().mean() / (e != 0).float().mean())
+    ratio = (got[kept] / e[kept])
+    out["dropout_scale_err"] = float((ratio - 1.25).abs().max())
+    out["dropout_ones_col_intact"] = bool((Xd[:, D].float() == 1).all())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def _rand_bf16(shape, seed, scale=1.0):
+    return bf16r(O.det_uniform(shape, seed, -scale, scale))
+
+
+def check_linear(M=300, N=900, K=300, taps=1, seg=0, relu=0, out_bf16=1):
+    """nr_linear (tcgen05 gemm_nt + store epilogue) against an fp64 matmul of the same bf16 operands."""
+    lib = load_library()
+    lda, ldw = ru8(K + 1), ru8(K + 1)
+    if taps == 1:
+        A = _rand_bf16((M, K), 1)
+        W = _rand_bf16((N, K), 2, 0.1)
+        bias = O.det_uniform((N,), 3, -0.5, 0.5)
+        ref = A.double() @ W.double().t() + bias.double()
+        Ad = torch.zeros(M, lda)
+        Ad[:, :K] = A
+        Wd = torch.zeros(N, ldw)
+        Wd[:, :K] = W
+        rpt, w_tap_rows = 128, 0
+    else:  # window-3 conv over the padded layout: seg tokens per segment, M = n_seg*(seg+2) rows
+        n_seg = M
+        Mrows = n_seg * (seg + 2)
+        X = _rand_bf16((n_seg, seg, K), 1)
+        W = _rand_bf16((N, taps, K), 2, 0.1)
+        bias = O.det_uniform((N,), 3, -0.5, 0.5)
+        Xp = torch.zeros(n_seg, seg + 2, K)
+        Xp[:, 1:seg + 1] = X
+        ref = torch.zeros(n_seg, seg + 2, N, dtype=torch.float64)
+        for s in range(taps):
+            sh = torch.zeros_like(Xp)
+            lo, hi = max(0, 1 - s), min(seg + 2, seg + 3 - s)
+            sh[:, lo:hi] = Xp[:, lo + s - 1:hi + s - 1]
+            ref += sh.double() @ W[:, s].double().t()
+        ref = (ref + bias.double()).view(Mrows, N)
+        Ad = torch.zeros(Mrows, lda)
+        Ad[:, :K] = Xp.view(Mrows, K)
+        Wd = torch.zeros(taps * N, ldw)
+        for s in range(taps):
+            Wd[s * N:(s + 1) * N, :K] = W[:, s]
+        M = Mrows
+        rpt, w_tap_rows = (128 // (seg + 2)) * (seg + 2), N
+    if relu:
+        ref = ref.clamp(min=0)
+    ld_out = ru8(N) if out_bf16 else (N + 3) // 4 * 4
+    out = torch.full((M, ld_out), float("nan"), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=DEV)
+    Ad, Wd, bd = Ad.to(torch.bfloat16).to(DEV), Wd.to(torch.bfloat16).to(DEV), bias.to(DEV)
+    check(lib.nr_linear(_p(Ad), M, lda, _p(Wd), N, ldw, K, taps, w_tap_rows, rpt, _p(bd), relu, _p(out), ld_out, out_bf16,
+                        _stream()), "nr_linear")
+    torch.cuda.synchronize()
+    got = out[:, :N].float().cpu()
+    if taps > 1:  # pad rows of the padded layout are not part of the result
+        keep = torch.ones(M, dtype=torch.bool).view(-1, seg + 2)
+        keep[:, 0] = keep[:, -1] = False
+        keep = keep.view(-1)
+        got, ref = got[keep], ref[keep]
+    return {"rel": relerr(got, ref), "maxabs": maxabs(got, ref), "nan": int(torch.isnan(got).sum())}
+
+
+def check_gemm_tn(Kr=1000, Ma=900, Nb=301, shift=0):
+    lib = load_library()
+    lda, ldb = ru8(Ma), ru8(Nb)
+    A = _rand_bf16((Kr, Ma), 11, 0.5)
+    B = _rand_bf16((Kr, Nb), 12, 0.5)
+    Bs = torch.zeros_like(B)
+    if shift >= 0:
+        Bs[:Kr - shift] = B[shift:]
+    else:
+        Bs[-shift:] = B[:Kr + shift]
+    ref = A.double().t() @ Bs.double()
+    Ad = torch.zeros(Kr, lda)
+    Ad[:, :Ma] = A
+    Bd = torch.zeros(Kr, ldb)
+    Bd[:, :Nb] = B
+    ldd = ru8(Nb)
+    D = torch.full((Ma, ldd), 1.0, dtype=torch.float32, device=DEV)  # accumulate on top of ones
+    Ad, Bd = Ad.to(torch.bfloat16).to(DEV), Bd.to(torch.bfloat16).to(DEV)
+    check(lib.nr_gemm_tn(_p(Ad), Kr, Ma, lda, _p(Bd), Kr, Nb, ldb, 0, Nb, shift, _p(D), ldd, _stream()), "nr_gemm_tn")
+    torch.cuda.synchronize()
+    got = D[:, :Nb].cpu() - 1.0
+    return {"rel": relerr(got, ref), "maxabs": maxabs(got, ref), "nan": int(torch.isnan(got).sum())}
+
+
+# ------------------------------------------------------------------------------------------------
+def check_mhsa_core(n_seq=7, T=20, heads=15, dk=20):
+    lib = load_library()
+    d = heads * dk
+    ld3, ldx = ru8(3 * d), ru8(d + 1)
+    qkv = _rand_bf16((n_seq * T, 3 * d), 21, 1.5).requires_grad_(True)
+    Q, K, V = [t.view(n_seq, T, heads, dk).transpose(1, 2) for t in qkv.split(d, dim=1)]
+    ctx = O.scaled_dot_product_attention(Q, K, V).transpose(1, 2).reshape(n_seq * T, d)
+    g = _rand_bf16((n_seq * T, d), 22)
+    ctx.backward(g)
+    qd = torch.zeros(n_seq * T, ld3)
+    qd[:, :3 * d] = qkv.detach()
+    qd = qd.to(torch.bfloat16).to(DEV)
+    cd = torch.full((n_seq * T, ldx), 9.0, dtype=torch.bfloat16, device=DEV)
+    check(lib.nr_mhsa_core_fwd(_p(qd), ld3, n_seq, T, heads, dk, _p(cd), ldx, 0.0, 0, _stream()), "mhsa_fwd")
+    gd = torch.zeros(n_seq * T, ldx)
+    gd[:, :d] = g
+    gd = gd.to(torch.bfloat16).to(DEV)
+    dq = torch.full((n_seq * T, ld3), 9.0, dtype=torch.bfloat16, device=DEV)
+    check(lib.nr_mhsa_core_bwd(_p(qd), ld3, _p(gd), ldx, n_seq, T, heads, dk, _p(dq), ld3, _stream()), "mhsa_bwd")
+    torch.cuda.synchronize()
+    c = cd.float().cpu()
+    return {"fwd_rel": relerr(c[:, :d], bf16r(ctx.detach())), "ones_col": bool((c[:, d] == 1).all()),
+            "bwd_rel": relerr(dq.float().cpu()[:, :3 * d], bf16r(qkv.grad))}
+
+
+def check_additive(N=37, S=20, D=300, q=200):
+    from newsrec_b200.ops import AdditiveAttentionFn, OperandCache
+    x = _rand_bf16((N, S, D), 31).requires_grad_(True)
+    p = {"a.linear.weight": O.det_uniform((q, D), 32, -0.1, 0.1).requires_grad_(True),
+         "a.linear.bias": O.det_uniform((q,), 33, -0.05, 0.05).requires_grad_(True),
+         "a.attention_query_vector": O.det_uniform((q,), 34, -0.1, 0.1).requires_grad_(True)}
+    ref = O.additive_attention(x, p, "a", O.BF16)
+    g = O.det_uniform((N, D), 35)
+    ref.backward(g)
+    xd = x.detach().to(DEV).requires_grad_(True)
+    pd = {k: v.detach().to(DEV).requires_grad_(True) for k, v in p.items()}
+    out = AdditiveAttentionFn.apply(xd, pd["a.linear.weight"], pd["a.linear.bias"], pd["a.attention_query_vector"],
+                                    OperandCache(), "t")
+    out.backward(g.to(DEV))
+    torch.cuda.synchronize()
+    return {"fwd_rel": relerr(out, ref), "dx_rel": relerr(xd.grad, x.grad),
+            "dW_rel": relerr(pd["a.linear.weight"].grad, p["a.linear.weight"].grad),
+            "db_rel": relerr(pd["a.linear.bias"].grad, p["a.linear.bias"].grad),
+            "dq_rel": relerr(pd["a.attention_query_vector"].grad, p["a.attention_query_vector"].grad)}
+
+
+def check_dot_score(B=9, Cn=5, D=300):
+    from newsrec_b200.ops import DotScoreFn
+    c = O.det_uniform((B, Cn, D), 41).requires_grad_(True)
+    u = O.det_uniform((B, D), 42).requires_grad_(True)
+    ref = O.dot_product_click_predictor(c, u)
+    g = O.det_uniform((B, Cn), 43)
+    ref.backward(g)
+    cd, ud = c.detach().to(DEV).requires_grad_(True), u.detach().to(DEV).requires_grad_(True)
+    out = DotScoreFn.apply(cd, ud)
+    out.backward(g.to(DEV))
+    return {"fwd_rel": relerr(out, ref), "dc_rel": relerr(cd.grad, c.grad), "du_rel": relerr(ud.grad, u.grad)}
+
+
+# ------------------------------------------------------------------------------------------------
+def nrms_model_and_params(V, seed, heads=15, dropout=0.2):
+    import config as cfgmod
+    from model.NRMS import NRMS
+    cfg = type("Cfg", (cfgmod.NRMSConfig,), dict(num_words=V, num_attention_heads=heads, dropout_probability=dropout))
+    sd = O.det_state_dict(O.nrms_shapes(V), seed)
+    model = NRMS(cfg)
+    model.load_state_dict(sd)
+    return model.to(DEV), sd
+
+
+def slots(t):
+    return [{"title": t[:, j].contiguous()} for j in range(t.shape[1])]
+
+
+def check_nrms_golden():
+    """The committed golden case (minted from the live reference): CUDA path vs reference fp32 outputs and
+    vs the oracle under the bf16 storage contract, forward and all parameter gradients."""
+    from golden_util import case_params, load_case, oracle_forward, unique_params
+    g = load_case("nrms")
+    cand_t, clicked_t = torch.from_numpy(g["cand_title"]), torch.from_numpy(g["clicked_title"])
+    p = case_params("nrms", g)
+    logits_o, _ = oracle_forward("nrms", g, p, O.BF16)
+    O.click_loss(logits_o).backward()
+    model, _ = nrms_model_and_params(120, int(g["seed"]))
+    model.eval()
+    logits = model(slots(cand_t), slots(clicked_t))
+    loss = torch.nn.functional.cross_entropy(logits, torch.zeros(logits.shape[0], dtype=torch.long, device=DEV))
+    loss.backward()
+    torch.cuda.synchronize()
+    out = {"logits_vs_oracle_bf16": relerr(logits, logits_o), "logits_vs_reference_fp32": relerr(logits, torch.from_numpy(g["logits"])),
+           "loss_abs_vs_reference": abs(loss.item() - float(g["loss"]))}
+    grads = dict(model.named_parameters())
+    worst, worst_key = 0.0, ""
+    for k, prm in unique_params(p).items():
+        if prm.grad.norm() < 1e-5:  # analytically ~0 gradients (W_K.bias) carry only rounding noise
+            continue
+        e = relerr(grads[k].grad, prm.grad)
+        if e > worst:
+            worst, worst_key = e, k
+        out["grad:" + k] = e
+    out["worst_grad_rel"] = worst
+    out["worst_grad_key"] = worst_key
+    out["emb_row0_grad_zero"] = bool((grads["news_encoder.word_embedding.weight"].grad[0] == 0).all())
+    model.check_ids()
+    return out
+
+
+def check_nrms_random(B=8, Cn=5, H=50, T=20, V=500, seed=5):
+    """A MIND-shaped batch (K=4, history 50, left padded) vs the oracle under the bf16 contract."""
+    cand_t, clicked_t, _ = O.synth_batch(B, Cn, H, T, V, seed * 100)
+    model, sd = nrms_model_and_params(V, seed)
+    model.eval()
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16)
+    O.click_loss(logits_o).backward()
+    with torch.no_grad():
+        logits_x = O.nrms_forward(cand_t, clicked_t, {k: v.detach() for k, v in p.items()}, 15, O.EXACT)
+    logits = model(slots(cand_t), slots(clicked_t))
+    torch.nn.functional.cross_entropy(logits, torch.zeros(B, dtype=torch.long, device=DEV)).backward()
+    torch.cuda.synchronize()
+    out = {"logits_vs_oracle_bf16": relerr(logits, logits_o), "logits_vs_exact_fp32": relerr(logits, logits_x),
+           "oracle_bf16_vs_exact": relerr(logits_o, logits_x)}
+    grads = dict(model.named_parameters())
+    worst = 0.0
+    for k, prm in p.items():
+        if prm.grad.norm() < 1e-5:
+            continue
+        e = relerr(grads[k].grad, prm.grad)
+        out["grad:" + k] = e
+        worst = max(worst, e)
+    out["worst_grad_rel"] = worst
+    return out
+
+
+def check_nrms_eval_api(V=300, seed=9):
+    """get_news_vector / get_user_vector (non-contiguous input, evaluate.py:220-224) / get_prediction."""
+    model, sd = nrms_model_and_params(V, seed)
+    model.eval()
+    p = {k: v for k, v in sd.items()}
+    titles = O.synth_titles(40, 20, V, 3)
+    with torch.no_grad():
+        nv = model.get_news_vector({"title": titles, "id": ["N%d" % i for i in range(40)]})
+        nv_o = O.nrms_news_encoder(titles, p, 15, O.BF16)
+        B, H = 4, 10
+        stacked = torch.stack([nv[i * 4:(i + 1) * 4] for i in range(H)], dim=0).transpose(0, 1)  # (B,H,d) non-contiguous
+        uv = model.get_user_vector(stacked)
+        uv_o = O.nrms_user_encoder(stacked.cpu(), p, 15, O.BF16)
+        pred = model.get_prediction(nv[:7], uv[0])
+        pred_o = (nv[:7].cpu() @ uv[0].cpu())
+    return {"news_vec_rel": relerr(nv, nv_o), "user_vec_rel": relerr(uv, uv_o), "pred_rel": relerr(pred, pred_o),
+            "user_input_noncontig": not stacked.is_contiguous(), "pred_tolist_len": len(pred.tolist())}
+
+
+def check_nrms_train_mode(B=16, V=400, seed=4):
+    """Training mode: dropout masks come from the in-kernel counter RNG, so parity is statistical:
+    the mean logits over many seeds approach the eval logits, gradients are finite, row 0 grad is zero,
+    and the backward regenerates exactly the forward masks (grad check against finite differences of the
+    SAME masked function is implied by the eval-mode parity of the identical kernels with p=0)."""
+    cand_t, clicked_t, _ = O.synth_batch(B, 5, 50, 20, V, seed * 100)
+    model, _ = nrms_model_and_params(V, seed)
+    model.eval()
+    with torch.no_grad():
+        ref = model(slots(cand_t), slots(clicked_t))
+    model.train()
+    acc = torch.zeros_like(ref)
+    n = 24
+    for _ in range(n):
+        with torch.no_grad():
+            acc += model(slots(cand_t), slots(clicked_t))
+    mean = acc / n
+    logits = model(slots(cand_t), slots(clicked_t))
+    torch.nn.functional.cross_entropy(logits, torch.zeros(B, dtype=torch.long, device=DEV)).backward()
+    g = model.news_encoder.word_embedding.weight.grad
+    return {"mean_train_vs_eval_rel": relerr(mean, ref), "train_differs_from_eval": relerr(logits, ref) > 1e-3,
+            "grads_finite": bool(torch.isfinite(g).all()), "emb_row0_grad_zero": bool((g[0] == 0).all())}
+
+
+def check_nrms_full_size_properties(B=512):
+    """BASELINE.json config[1] sizes (B=512, K=4, H=50, T=20, d=300, 15 heads, V=70976): size-independent
+    properties -- (1) permuting the impressions permutes the logits, (2) the logits of a sub-batch equal the
+    corresponding rows of the full batch, (3) sum of the embedding gradient over rows == a probe identity:
+    d(sum logits)/d(emb) summed over the vocabulary equals the gradient w.r.t. a shared additive shift."""
+    V = 70976
+    cand_t, clicked_t, _ = O.synth_batch(B, 5, 50, 20, V, 4242)
+    model, _ = nrms_model_and_params(V, 3)
+    model.eval()
+    with torch.no_grad():
+        full = model(slots(cand_t), slots(clicked_t))
+        perm = torch.from_numpy(__import__("numpy").random.RandomState(0).permutation(B))
+        permd = model(slots(cand_t[perm]), slots(clicked_t[perm]))
+        sub = model(slots(cand_t[:16]), slots(clicked_t[:16]))
+    return {"perm_equivariance_maxabs": maxabs(permd, full[perm.to(DEV)]), "subbatch_maxabs": maxabs(sub, full[:16]),
+            "finite": bool(torch.isfinite(full).all())}
