@@ -32,6 +32,15 @@ const char* nr_last_error(void);            /* message of the last failing call 
 int nr_device_error(int out4[4]);           /* watchdog record {code, block, thread, aux}; code 0 = none */
 long long nr_launch_count(void);            /* kernels this library has launched so far */
 int nr_num_sms(void);
+/* TRIAGE ONLY (tests): route the GEMMs through a plain SIMT accumulate + the same epilogue functors, to
+ * tell a tcgen05/TMA pipeline bug from an epilogue bug.  Never enabled by the product path. */
+void nr_debug_set_simt_gemm(int on);
+/* Live per-kernel timing for bench.py: CUDA events on the launching stream around every kernel of this
+ * library.  nr_profile_report writes JSON {"<context>/<op>[shape]": [launches, total_ms], ...}, returns its
+ * length (or -1 if cap is too small) and clears the records.  Off by default. */
+void nr_profile_enable(int on);
+void nr_profile_context(const char* ctx);
+int nr_profile_report(char* buf, int cap);
 
 /* ---- operand preparation ------------------------------------------------------------------------- */
 /* fp32 [R][C] (pitch lds) -> zero padded bf16 [R][ld]; transpose!=0: dst is [C][ld] with dst[c][r]=src[r][c] */

@@ -8,6 +8,7 @@
 namespace nr {
 const char* last_error();
 int read_device_error(int* out4);
+void set_debug_simt_gemm(int on);
 extern int g_launches;
 }  // namespace nr
 
@@ -24,6 +25,10 @@ const char* nr_last_error(void) { return last_error(); }
 int nr_device_error(int out4[4]) { return read_device_error(out4); }
 long long nr_launch_count(void) { return g_launches; }
 int nr_num_sms(void) { return num_sms(); }
+void nr_debug_set_simt_gemm(int on) { set_debug_simt_gemm(on); }
+void nr_profile_enable(int on) { prof_enable(on); }
+void nr_profile_context(const char* ctx) { prof_context(ctx ? ctx : ""); }
+int nr_profile_report(char* buf, int cap) { return prof_report(buf, cap); }
 
 int nr_cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, int transpose, void* stream) {
     NR_REQUIRE(src && dst && R >= 0 && C >= 0 && ld % 8 == 0 && ld >= (transpose ? R : C),
@@ -130,6 +135,7 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
     if (a->n_seq == 0) return 0;
     const int M = static_cast<int>(a->n_seq * a->T);
     const cudaStream_t st = S(stream);
+    prof_context(a->ids != nullptr ? "news.fwd" : "user.fwd");
     if (a->ids != nullptr) {
         NR_REQUIRE(a->table_bf16 && a->bad_id_flag && a->V >= 1, "nr_mhsa_encoder_fwd: table / bad_id_flag missing");
         NR_PROPAGATE(gather_rows(a->ids, M, a->T, a->table_bf16, a->V, a->d, a->ldx, a->X_bf16, a->ldx, 0,
@@ -183,6 +189,7 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     ws += align256(rows * a->ldx * 2);
     void* dQKV = ws;
 
+    prof_context(a->ids != nullptr ? "news.bwd" : "user.bwd");
     // --- additive pooling backward ---
     NR_PROPAGATE(pool_dscore(a->C_bf16, a->ldx, a->d, a->n_seq, a->T, a->w, a->dout, a->d, dscore, st));
     NR_PROPAGATE(gemm_additive_dpre(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, dscore, dpre, a->ldq,

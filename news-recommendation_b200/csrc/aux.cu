@@ -35,6 +35,7 @@ int cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, in
     const long long total = static_cast<long long>(transpose ? C : R) * ld;
     if (total == 0) return 0;
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    ProfScope ps("cast_pad", R, C, ld, stream);
     cast_pad_kernel<<<blocks, 256, 0, stream>>>(src, R, C, lds, static_cast<__nv_bfloat16*>(dst), ld, transpose);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
@@ -63,6 +64,7 @@ int rows_to_bf16(const float* src, long long n_seq, int T, int D, long long s_se
     if (n == 0) return 0;
     NR_REQUIRE(ld >= D + 1, "rows_to_bf16: pitch %d too small for D=%d plus the ones column", ld, D);
     const int blocks = static_cast<int>(std::min<long long>((n * ld + 255) / 256, 148 * 16));
+    ProfScope ps("rows_to_bf16", static_cast<int>(n), D, ld, stream);
     rows_to_bf16_kernel<<<blocks, 256, 0, stream>>>(src, n, T, D, s_seq, s_tok, s_col, static_cast<__nv_bfloat16*>(dst),
                                                     ld);
     ++g_launches;
@@ -131,6 +133,7 @@ int gather_rows(const long long* ids, long long n_tok, int T, const void* table,
     if (n_tok == 0) return 0;
     NR_REQUIRE(ld_table == ld_x && ld_x % 8 == 0 && ld_x >= D + 1, "gather_rows: pitch %d/%d for D=%d", ld_table, ld_x, D);
     const int blocks = static_cast<int>(std::min<long long>((n_tok + 7) / 8, 148 * 8));
+    ProfScope ps("gather_rows", static_cast<int>(n_tok), D, ld_x, stream);
     gather_rows_kernel<<<blocks, 256, 0, stream>>>(ids, n_tok, T, static_cast<const uint4*>(table), V, D, ld_x,
                                                    static_cast<uint4*>(X), padded, drop.p, drop.seed, bad_id_flag);
     ++g_launches;
@@ -329,6 +332,7 @@ static int mhsa_launch(bool bwd, const void* qkv, int ld_qkv, const void* dctx, 
     const int groups = ceil_div(heads, hpb);
     const long long blocks = n_seq * groups;
     NR_REQUIRE(blocks < (1ll << 31), "mhsa: too many (sequence, head-group) blocks");
+    ProfScope ps(bwd ? "mhsa_core_bwd" : "mhsa_core_fwd", static_cast<int>(n_seq), T, heads * DK, stream);
     if (!bwd) {
         const size_t smem = sizeof(float) * 2 * hpb * T * DK;
         mhsa_fwd_kernel<DK><<<static_cast<unsigned>(blocks), 64, smem, stream>>>(
@@ -409,6 +413,7 @@ int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, con
     if (n_seg == 0) return 0;
     NR_REQUIRE(seg_len <= 128 && D % 2 == 0, "pool_dscore: seg_len=%d D=%d", seg_len, D);
     const int blocks = static_cast<int>(std::min<long long>(n_seg, 148 * 16));
+    ProfScope ps("pool_dscore", static_cast<int>(n_seg), seg_len, D, stream);
     pool_dscore_kernel<<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(X), lda, D, n_seg, seg_len, w, dout,
                                                    ldo, dscore);
     ++g_launches;
@@ -449,6 +454,7 @@ __global__ void dot_bwd_kernel(const float* __restrict__ cand, const float* __re
 }
 int dot_score_fwd(const float* cand, const float* user, int B, int C, int D, float* logits, cudaStream_t stream) {
     if (B * C == 0) return 0;
+    ProfScope ps("dot_fwd", B, C, D, stream);
     dot_fwd_kernel<<<ceil_div(B * C * 32, 256), 256, 0, stream>>>(cand, user, B, C, D, logits);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
@@ -457,6 +463,7 @@ int dot_score_fwd(const float* cand, const float* user, int B, int C, int D, flo
 int dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
                   float* duser, cudaStream_t stream) {
     if (B == 0) return 0;
+    ProfScope ps("dot_bwd", B, C, D, stream);
     dot_bwd_kernel<<<B, 128, 0, stream>>>(cand, user, dlogits, B, C, D, dcand, duser);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());

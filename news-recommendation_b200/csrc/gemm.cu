@@ -4,7 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 
 #define NR_OWNS_WATCHDOG 1
 #include "nr_epilogues.cuh"
@@ -29,6 +32,69 @@ int read_device_error(int* out4) {
     return (int)cudaMemcpyFromSymbol(out4, g_dev_error, sizeof(int) * 4);
 }
 
+// ------------------------------------------------------------------------------------------------
+// live per-kernel timing
+// ------------------------------------------------------------------------------------------------
+struct ProfRec {
+    std::string name;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::string g_prof_ctx;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) {
+        e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+void prof_enable(int on) { g_prof_on = on != 0; }
+void prof_context(const char* ctx) { if (g_prof_on) g_prof_ctx = ctx; }
+ProfScope::ProfScope(const char* op, int a, int b, int c, cudaStream_t s) : idx(-1), stream(s) {
+    if (!g_prof_on) return;
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%s/%s[%d,%d,%d]", g_prof_ctx.c_str(), op, a, b, c);
+    ProfRec r{buf, prof_event(), prof_event()};
+    cudaEventRecord(r.a, s);
+    idx = static_cast<int>(g_prof.size());
+    g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
+}
+int prof_report(char* buf, int cap) {
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto& e = agg[r.name];
+            e.first += 1;
+            e.second += ms;
+        }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\": [%d, %.6f]", first ? "" : ", ", kv.first.c_str(), kv.second.first,
+                 kv.second.second);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    if (static_cast<int>(out.size()) + 1 > cap) return -1;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return static_cast<int>(out.size());
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -40,14 +106,15 @@ int num_sms() {
     return n;
 }
 
+static int g_debug_simt = -1;
 bool debug_simt_gemm() {
-    static int v = -1;
-    if (v < 0) {
+    if (g_debug_simt < 0) {
         const char* e = getenv("NEWSREC_DEBUG_SIMT_GEMM");
-        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+        g_debug_simt = (e != nullptr && e[0] == '1') ? 1 : 0;
     }
-    return v == 1;
+    return g_debug_simt == 1;
 }
+void set_debug_simt_gemm(int on) { g_debug_simt = on ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // TMA descriptor encoding via the driver entry point (resolved at run time: the library must load
@@ -93,7 +160,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
 // gemm_nt planning
 // ------------------------------------------------------------------------------------------------
 int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B, int N, int ldb, int K, int taps,
-                 int b_tap_rows, int rows_per_tile, int sms) {
+                 int b_tap_rows, int rows_per_tile, int sms, int max_slices) {
     NR_REQUIRE(M >= 0 && N >= 1 && K >= 1 && taps >= 1 && rows_per_tile >= 1 && rows_per_tile <= kTileM,
                "plan_gemm_nt: bad shape M=%d N=%d K=%d taps=%d rpt=%d", M, N, K, taps, rows_per_tile);
     NR_REQUIRE(sms > 0, "no CUDA device (SM count unknown)");
@@ -116,6 +183,8 @@ int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B,
         if (p.n_box > 256) continue;
         const long bbytes = static_cast<long>(taps) * p.k_chunks * p.n_box * 128;
         if (bbytes + 4L * kAStageBytes + fixed <= kSmemLimit) break;
+        // epilogues that reduce over the whole output row need ONE slice: accept a shallower A ring instead
+        if (slices == max_slices && bbytes + 2L * kAStageBytes + fixed <= kSmemLimit) break;
     }
     p.n_slices = ceil_div(N, p.n_stride);
     const long bbytes = static_cast<long>(taps) * p.k_chunks * p.n_box * 128;
@@ -293,6 +362,7 @@ int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, in
     p.b_row_shift = b_row_shift;
     p.D = D;
     p.ldd = ldd;
+    ProfScope ps("gemm_tn", Kr, Ma, Nb, stream);
     if (debug_simt_gemm()) {
         dim3 g(ceil_div(Nb, 64), Ma);
         gemm_tn_simt_kernel<<<g, 64, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda,
@@ -347,7 +417,7 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
                int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream) {
     if (M == 0) return 0;
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms()));
+    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0));
     NR_REQUIRE(out_bf16 ? (ld_out % 8 == 0) : (ld_out % 4 == 0), "gemm_store: output pitch %d breaks vector stores", ld_out);
     EpiStore e;
     e.out = out;
@@ -362,6 +432,7 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
     e.ones_col = ones_col;
     e.ones_cols_zero_upto = ones_zero_upto;
     g_launches += debug_simt_gemm() ? 2 : 1;
+    ProfScope ps("gemm_store", M, N, K * taps, stream);
     return launch_gemm_nt(plan, e, A, lda, W, ldw, stream);
 }
 
@@ -372,7 +443,7 @@ int gemm_additive_pool(const void* X, int M, int lda, int D, const void* Wa, int
     NR_REQUIRE(q <= 256 && (D % 2) == 0 && (ldo % 2) == 0, "additive_pool: q=%d D=%d ldo=%d unsupported", q, D, ldo);
     const int rpt = (kTileM / seg_len) * seg_len;
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, rpt, num_sms()));
+    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, rpt, num_sms(), 1));
     NR_REQUIRE(plan.p.n_slices == 1, "additive_pool: the query dimension must fit one weight slice (q=%d D=%d)", q, D);
     EpiPool e;
     e.bias = ba;
@@ -387,6 +458,7 @@ int gemm_additive_pool(const void* X, int M, int lda, int D, const void* Wa, int
     e.ldo = ldo;
     e.w_out = w_out;
     g_launches += debug_simt_gemm() ? 2 : 1;
+    ProfScope ps("gemm_additive_pool", M, q, D, stream);
     return launch_gemm_nt(plan, e, X, lda, Wa, ldw, stream);
 }
 
@@ -396,7 +468,7 @@ int gemm_additive_dpre(const void* X, int M, int lda, int D, const void* Wa, int
     if (M == 0) return 0;
     NR_REQUIRE(q <= 256 && ld_dpre % 8 == 0 && ld_dpre >= round_up(q, 8), "additive_dpre: q=%d ld=%d", q, ld_dpre);
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, kTileM, num_sms()));
+    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, kTileM, num_sms(), 1));
     NR_REQUIRE(plan.p.n_slices == 1, "additive_dpre: q=%d D=%d does not fit one weight slice", q, D);
     EpiDPre e;
     e.bias = ba;
@@ -406,6 +478,7 @@ int gemm_additive_dpre(const void* X, int M, int lda, int D, const void* Wa, int
     e.ld = ld_dpre;
     e.dqv = dqv;
     g_launches += debug_simt_gemm() ? 2 : 1;
+    ProfScope ps("gemm_additive_dpre", M, q, D, stream);
     return launch_gemm_nt(plan, e, X, lda, Wa, ldw, stream);
 }
 
@@ -414,7 +487,7 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
                      DropoutCfg drop, const void* relu_src, int relu_ld, cudaStream_t stream) {
     if (M == 0) return 0;
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, dpre, M, ld_dpre, WaT, D, ldwT, q, 1, 0, kTileM, num_sms()));
+    NR_PROPAGATE(plan_gemm_nt(&plan, dpre, M, ld_dpre, WaT, D, ldwT, q, 1, 0, kTileM, num_sms(), 0));
     NR_REQUIRE(ld_dx % 8 == 0, "pool_dinput: ld_dx=%d", ld_dx);
     EpiDPoolIn e;
     e.w = w;
@@ -430,6 +503,7 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
     e.relu_src = static_cast<const __nv_bfloat16*>(relu_src);
     e.relu_ld = relu_ld;
     g_launches += debug_simt_gemm() ? 2 : 1;
+    ProfScope ps("gemm_pool_dinput", M, D, q, stream);
     return launch_gemm_nt(plan, e, dpre, ld_dpre, WaT, ldwT, stream);
 }
 
@@ -439,7 +513,7 @@ int gemm_scatter_emb(const void* A, int M, int lda, const void* W, int N, int ld
     if (M == 0) return 0;
     NR_REQUIRE(N == D && D % 4 == 0, "scatter_emb: N=%d D=%d", N, D);
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms()));
+    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0));
     EpiScatter e;
     e.ids = ids;
     e.demb = demb;
@@ -448,6 +522,7 @@ int gemm_scatter_emb(const void* A, int M, int lda, const void* W, int N, int ld
     e.drop = to_drop(drop);
     e.drop_ld = drop_ld;
     g_launches += debug_simt_gemm() ? 2 : 1;
+    ProfScope ps("gemm_scatter_emb", M, N, K * taps, stream);
     return launch_gemm_nt(plan, e, A, lda, W, ldw, stream);
 }
 

@@ -274,7 +274,7 @@ struct GemmNTPlan {
 };
 // Fills slices/boxes/stages and encodes the tensor maps.  A: [M rows][K] pitch lda; B: [taps*b_tap_rows][K] pitch ldb.
 int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B, int N, int ldb, int K, int taps,
-                 int b_tap_rows, int rows_per_tile, int num_sms);
+                 int b_tap_rows, int rows_per_tile, int num_sms, int max_slices);
 bool debug_simt_gemm();
 
 template <class Epi>

@@ -69,4 +69,16 @@ int dot_score_bwd(const float* cand, const float* user, const float* dlogits, in
 
 int num_sms();
 
+// ---- live per-kernel timing (bench.py): CUDA events on the launching stream around every kernel ------
+// Off by default.  A ProfScope brackets one kernel launch; names are "<context>/<op>[shape]".
+void prof_enable(int on);
+void prof_context(const char* ctx);  // prefix set by the composites ("news.fwd", "user.bwd", ...)
+int prof_report(char* buf, int cap); // JSON {"name": [launches, total_ms], ...}; clears the records
+struct ProfScope {
+    ProfScope(const char* op, int a, int b, int c, cudaStream_t s);
+    ~ProfScope();
+    int idx;
+    cudaStream_t stream;
+};
+
 }  // namespace nr

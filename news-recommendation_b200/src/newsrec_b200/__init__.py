@@ -48,6 +48,10 @@ SIGNATURES = {
     "nr_device_error": (_i, [C.POINTER(_i * 4)]),
     "nr_launch_count": (_ll, []),
     "nr_num_sms": (_i, []),
+    "nr_debug_set_simt_gemm": (None, [_i]),
+    "nr_profile_enable": (None, [_i]),
+    "nr_profile_context": (None, [C.c_char_p]),
+    "nr_profile_report": (_i, [C.c_char_p, _i]),
     "nr_cast_pad_bf16": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "nr_rows_to_bf16": (_i, [_vp, _ll, _i, _ll, _ll, _vp, _i, _vp]),
     "nr_gather_rows": (_i, [_vp, _ll, _i, _vp, _i, _i, _i, _vp, _i, _f, _ull, _vp, _vp]),
@@ -106,6 +110,16 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise NewsrecError("newsrec_b200 needs a CUDA (sm_100a) device: the hot path has no CPU fallback")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def profile_report() -> dict:
+    """Drain the live per-kernel timing records: {name: (launches, total_ms)}."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    n = load_library().nr_profile_report(buf, len(buf))
+    if n < 0:
+        raise NewsrecError("profile report does not fit the buffer")
+    return {k: tuple(v) for k, v in json.loads(buf.value.decode()).items()}
 
 
 def launch_count() -> int:

@@ -485,3 +485,46 @@ def synth_batch(B, C, H, T, V, seed, with_hist_pad=True):
     keep = torch.arange(H).unsqueeze(0) >= (H - hist_len).unsqueeze(1)
     clicked = clicked * keep.unsqueeze(-1)
     return cand, clicked, hist_len
+
+
+# --------------------------------------------------------------------------- #
+# CPU baseline: the reference's NRMS training step, restated with the reference's OWN call structure
+# (one news_encoder call per slot, dropout active in train mode, dense Embedding gradient), so that
+# timing it is timing what the reference does on the host cores.  Used by bench.py (cpu_baseline /
+# --impl reference) only.
+# --------------------------------------------------------------------------- #
+class ReferenceStructuredNRMS(torch.nn.Module):
+    """src/model/NRMS/__init__.py:7-48 + news_encoder.py:27-48 + user_encoder.py:15-26, slot by slot."""
+
+    def __init__(self, V, d=300, heads=15, q=200, p_drop=0.2, seed=0):
+        super().__init__()
+        self.heads, self.p_drop = heads, p_drop
+        sd = det_state_dict(nrms_shapes(V, d, q), seed)
+        self.params = torch.nn.ParameterDict({k.replace(".", "/"): torch.nn.Parameter(v) for k, v in sd.items()})
+
+    def _p(self):
+        return {k.replace("/", "."): v for k, v in self.params.items()}
+
+    def news_encoder(self, title, p):
+        # news_encoder.py:38-47 (dropout after the embedding and after the self-attention)
+        x = F.dropout(embedding(title, p["news_encoder.word_embedding.weight"]), p=self.p_drop, training=self.training)
+        x = multihead_self_attention(x, p, "news_encoder.multihead_self_attention", self.heads)
+        x = F.dropout(x, p=self.p_drop, training=self.training)
+        return additive_attention(x, p, "news_encoder.additive_attention")
+
+    def forward(self, candidate_news, clicked_news):
+        p = self._p()
+        cand = torch.stack([self.news_encoder(x["title"], p) for x in candidate_news], dim=1)   # __init__.py:38-39
+        clicked = torch.stack([self.news_encoder(x["title"], p) for x in clicked_news], dim=1)  # __init__.py:41-42
+        user = nrms_user_encoder(clicked, p, self.heads)
+        return dot_product_click_predictor(cand, user)
+
+
+def reference_cpu_step(model, candidate_news, clicked_news):
+    """zero_grad -> forward -> CrossEntropy(label 0) -> backward  (src/train.py:202-231, optimizer excluded:
+    the metric is forward+backward)."""
+    for prm in model.parameters():
+        prm.grad = None
+    loss = click_loss(model(candidate_news, clicked_news))
+    loss.backward()
+    return float(loss.detach())

@@ -354,3 +354,113 @@ def check_nrms_full_size_properties(B=512):
         sub = model(slots(cand_t[:16]), slots(clicked_t[:16]))
     return {"perm_equivariance_maxabs": maxabs(permd, full[perm.to(DEV)]), "subbatch_maxabs": maxabs(sub, full[:16]),
             "finite": bool(torch.isfinite(full).all())}
+
+
+# ------------------------------------------------------------------------------------------------
+def check_backend_agreement(M=8800, N=900, K=300):
+    """tcgen05 accumulators vs the SIMT triage backend on identical operands (fp32 output): locates
+    pipeline bugs (which tile / row / column disagrees) that bf16 output rounding would hide."""
+    lib = load_library()
+    lda = ldw = ru8(K + 1)
+    A = torch.zeros(M, lda)
+    A[:, :K] = _rand_bf16((M, K), 1)
+    W = torch.zeros(N, ldw)
+    W[:, :K] = _rand_bf16((N, K), 2, 0.1)
+    bias = O.det_uniform((N,), 3, -0.5, 0.5).to(DEV)
+    ref = (A[:, :K].double() @ W[:, :K].double().t() + bias.cpu().double())
+    Ad, Wd = A.to(torch.bfloat16).to(DEV), W.to(torch.bfloat16).to(DEV)
+    ld_out = (N + 3) // 4 * 4
+    outs = []
+    for simt in (0, 1, 0):
+        lib.nr_debug_set_simt_gemm(simt)
+        out = torch.full((M, ld_out), float("nan"), dtype=torch.float32, device=DEV)
+        check(lib.nr_linear(_p(Ad), M, lda, _p(Wd), N, ldw, K, 1, 0, 128, _p(bias), 0, _p(out), ld_out, 0, _stream()), "nr_linear")
+        torch.cuda.synchronize()
+        outs.append(out[:, :N].cpu().double())
+    lib.nr_debug_set_simt_gemm(0)
+    t, s, t2 = outs
+    diff = (t - s).abs()
+    bad = (diff > 1e-4).nonzero()
+    res = {"tc_vs_ref_rel": relerr(t, ref), "simt_vs_ref_rel": relerr(s, ref), "tc_vs_simt_maxabs": float(diff.max()),
+           "tc_rerun_maxabs": float((t - t2).abs().max()), "n_bad": int(bad.shape[0])}
+    if bad.shape[0]:
+        rows, cols = bad[:, 0], bad[:, 1]
+        res["bad_rows_sample"] = rows[:12].tolist()
+        res["bad_cols_sample"] = cols[:12].tolist()
+        res["bad_tiles"] = sorted(set((rows // 128).tolist()))[:40]
+        res["bad_col_range"] = [int(cols.min()), int(cols.max())]
+        res["bad_row_in_tile_range"] = [int((rows % 128).min()), int((rows % 128).max())]
+    return res
+
+
+def _encoder_fwd_raw(ids, dense, sd, prefix, heads, V):
+    """Direct nr_mhsa_encoder_fwd call returning every intermediate buffer (for differential triage)."""
+    from newsrec_b200 import MhsaEncoderFwdArgs
+    lib = load_library()
+    d, q = 300, 200
+    ldx, ld3 = ru8(d + 1), ru8(3 * d)
+    g = lambda k: sd[f"{prefix}.{k}"].to(DEV)
+    wqkv = torch.cat([g(f"multihead_self_attention.W_{n}.weight") for n in "QKV"], 0)
+    ops = dict(wqkv=cast_pad(wqkv, ldx), bqkv=torch.cat([g(f"multihead_self_attention.W_{n}.bias") for n in "QKV"]).contiguous(),
+               wa=cast_pad(g("additive_attention.linear.weight"), ldx), ba=g("additive_attention.linear.bias").contiguous(),
+               qv=g("additive_attention.attention_query_vector").contiguous())
+    a = MhsaEncoderFwdArgs()
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    if ids is not None:
+        n_seq, T = ids.shape
+        table = cast_pad(sd["news_encoder.word_embedding.weight"].to(DEV), ldx)
+        a.ids, a.table_bf16, a.V = _p(ids), _p(table), V
+    else:
+        n_seq, T, _ = dense.shape
+        a.dense = _p(dense)
+        a.dense_s_seq, a.dense_s_tok, a.dense_s_col = dense.stride()
+    n_tok = n_seq * T
+    bufs = dict(X=torch.zeros((n_tok, ldx), dtype=torch.bfloat16, device=DEV), QKV=torch.zeros((n_tok, ld3), dtype=torch.bfloat16, device=DEV),
+                C=torch.zeros((n_tok, ldx), dtype=torch.bfloat16, device=DEV), w=torch.zeros((n_tok,), device=DEV),
+                out=torch.zeros((n_seq, d), device=DEV))
+    a.n_seq, a.T, a.d, a.heads, a.q, a.ldx, a.ld3 = n_seq, T, d, heads, q, ldx, ld3
+    a.wqkv_bf16, a.bqkv, a.wa_bf16, a.ba, a.qv = _p(ops["wqkv"]), _p(ops["bqkv"]), _p(ops["wa"]), _p(ops["ba"]), _p(ops["qv"])
+    a.p_drop, a.seed = 0.0, 0
+    a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.out = _p(bufs["X"]), _p(bufs["QKV"]), _p(bufs["C"]), _p(bufs["w"]), _p(bufs["out"])
+    a.bad_id_flag = _p(flag)
+    check(lib.nr_mhsa_encoder_fwd(C.byref(a), _stream()), "nr_mhsa_encoder_fwd")
+    torch.cuda.synchronize()
+    return {k: v.float().cpu() for k, v in bufs.items()}
+
+
+def check_encoder_backend_diff(B=8, V=500, seed=5):
+    """Every intermediate of the news and user encoders, tcgen05 vs SIMT triage backend, same inputs."""
+    lib = load_library()
+    cand_t, clicked_t, _ = O.synth_batch(B, 5, 50, 20, V, seed * 100)
+    sd = O.det_state_dict(O.nrms_shapes(V), seed)
+    ids = torch.cat((clicked_t.reshape(-1, 20), cand_t.reshape(-1, 20)), 0).to(DEV)
+    res = {}
+    runs = {}
+    for name, simt in (("tc", 0), ("simt", 1)):
+        lib.nr_debug_set_simt_gemm(simt)
+        news = _encoder_fwd_raw(ids, None, sd, "news_encoder", 15, V)
+        dense = news["out"][:B * 50].view(B, 50, 300).to(DEV).contiguous()
+        user = _encoder_fwd_raw(None, dense, sd, "user_encoder", 15, V)
+        runs[name] = (news, user)
+    lib.nr_debug_set_simt_gemm(0)
+    for lvl, i in (("news", 0), ("user", 1)):
+        for k in ("X", "QKV", "C", "w", "out"):
+            a, b = runs["tc"][i][k], runs["simt"][i][k]
+            d = (a - b).abs()
+            res[f"{lvl}.{k}.maxabs"] = float(d.max())
+            res[f"{lvl}.{k}.n_diff"] = int((d > 0).sum())
+            res[f"{lvl}.{k}.rel"] = relerr(a, b)
+            if k in ("w", "out") and d.max() > 0:
+                idx = d.reshape(d.shape[0], -1).max(dim=1).values.topk(min(5, d.shape[0]))
+                res[f"{lvl}.{k}.worst_rows"] = idx.indices.tolist()
+                res[f"{lvl}.{k}.worst_vals"] = [float(v) for v in idx.values]
+    # and against the oracle
+    p = {k: v for k, v in sd.items()}
+    with torch.no_grad():
+        nv_o = O.nrms_news_encoder(ids.cpu(), p, 15, O.BF16)
+    res["news.out.tc_vs_oracle"] = relerr(runs["tc"][0]["out"], nv_o)
+    res["news.out.simt_vs_oracle"] = relerr(runs["simt"][0]["out"], nv_o)
+    dn = (runs["tc"][0]["out"] - nv_o).abs().max(dim=1).values
+    res["news.out.tc_vs_oracle_worst_rows"] = dn.topk(5).indices.tolist()
+    res["news.out.tc_vs_oracle_worst_vals"] = [float(v) for v in dn.topk(5).values]
+    return res

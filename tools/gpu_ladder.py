@@ -39,6 +39,9 @@ CHECKS = {
     "additive": ("check_additive", {}),
     "additive_s50": ("check_additive", dict(N=9, S=50)),
     "additive_s4_f400": ("check_additive", dict(N=50, S=4, D=400)),
+    "backend_agreement": ("check_backend_agreement", {}),
+    "backend_agreement_1tile": ("check_backend_agreement", dict(M=4000)),
+    "encoder_backend_diff": ("check_encoder_backend_diff", {}),
     "dot_score": ("check_dot_score", {}),
     "nrms_golden": ("check_nrms_golden", {}),
     "nrms_random": ("check_nrms_random", {}),
