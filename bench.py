@@ -136,12 +136,36 @@ def kernel_work(name):
     return 0.0, 0.0
 
 
+def usable_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (os.cpu_count()
+    reports the whole machine inside a container; oversubscribing OpenMP threads stalls the CPU arm)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except (OSError, ValueError):
+            pass
+    return min(n, 64)
+
+
+def log(msg):
+    print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+
 def run_reference(args):
-    """The reference's own CPU path (oracle port with the reference's per-slot call structure), all host threads."""
+    """The reference's own CPU path (oracle port with the reference's per-slot call structure), all usable host threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import newsrec_oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
+    log(f"reference arm: {cores} threads, batch {args.ref_batch}, {args.warmup}+{args.steps} steps")
     B = args.ref_batch
     model = O.ReferenceStructuredNRMS(V_WORDS, D_MODEL, HEADS, Q_DIM, 0.2, 0)
     model.train()
@@ -234,14 +258,17 @@ def main():
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item()), newsrec_b200.launch_count() - l0
 
+    log(f"rank {rank}/{world}: model + data ready; timing device-resident steps")
     # ---- device-resident inputs: `value` ----
     lib.nr_profile_enable(1)
     with ClockSampler(local) as clk:
         ms_total, launches = timed(dev_batches, read_loss=False)
     prof = newsrec_b200.profile_report()
     lib.nr_profile_enable(0)
+    log(f"device-resident: {ms_total / args.steps:.3f} ms/step; timing end-to-end steps")
     # ---- end to end through the public API with HOST buffers (H2D of ids + D2H of the loss inside) ----
     ms_e2e, _ = timed(host_batches, read_loss=True)
+    log(f"end-to-end: {ms_e2e / args.steps:.3f} ms/step")
 
     if rank != 0:
         return

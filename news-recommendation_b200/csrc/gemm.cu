@@ -54,8 +54,21 @@ static cudaEvent_t prof_event() {
     return e;
 }
 void prof_enable(int on) { g_prof_on = on != 0; }
-void prof_context(const char* ctx) { if (g_prof_on) g_prof_ctx = ctx; }
+void prof_context(const char* ctx) { g_prof_ctx = ctx; }
+// NEWSREC_TRACE=1: print every launch and synchronise after it (pin-points a stuck or faulting kernel).
+static int trace_on() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NEWSREC_TRACE");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
 ProfScope::ProfScope(const char* op, int a, int b, int c, cudaStream_t s) : idx(-1), stream(s) {
+    if (trace_on()) {
+        fprintf(stderr, "[nr] launch %s/%s[%d,%d,%d]\n", g_prof_ctx.c_str(), op, a, b, c);
+        fflush(stderr);
+    }
     if (!g_prof_on) return;
     char buf[160];
     snprintf(buf, sizeof(buf), "%s/%s[%d,%d,%d]", g_prof_ctx.c_str(), op, a, b, c);
@@ -66,6 +79,11 @@ ProfScope::ProfScope(const char* op, int a, int b, int c, cudaStream_t s) : idx(
 }
 ProfScope::~ProfScope() {
     if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
+    if (trace_on()) {
+        const cudaError_t e = cudaStreamSynchronize(stream);
+        fprintf(stderr, "[nr]   -> %s\n", cudaGetErrorString(e));
+        fflush(stderr);
+    }
 }
 int prof_report(char* buf, int cap) {
     std::map<std::string, std::pair<int, double>> agg;
