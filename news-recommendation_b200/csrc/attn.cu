@@ -1,0 +1,598 @@
+// Multi-head self-attention core (reference src/model/general/attention/multihead_self.py:15-23) on the
+// legacy tensor path (mma.sync m16n8k16 bf16 + ldmatrix): the per-(sequence, head) products are 20x20x20 /
+// 50x50x20 -- 3 % of the model's FLOPs and far too small for a 128-row tcgen05 tile -- so one WARP owns one
+// head, all operands live in shared-memory tiles and nothing but Q|K|V (+dCtx) is read from HBM.
+//
+//   forward : S = QK^T/sqrt(dk);  A = exp(S)/(sum exp(S) + 1e-8)  [stable form];  ctx = A V
+//   backward: dA = dCtx V^T;  dS = A (dA - sum A dA)/sqrt(dk);  dQ = dS K;  dK = dS^T Q;  dV = A^T dCtx
+//
+// bf16 storage contract (mirrored by the oracle): A and dS are rounded to bf16 as tensor-core operands,
+// all softmax arithmetic is fp32.
+#include <algorithm>
+
+#include "nr_common.cuh"
+#include "nr_ops.h"
+
+namespace nr {
+
+extern int g_launches;
+
+namespace {
+
+constexpr int kPitch = 40;  // bf16 elements per tile row (80 B: 16-byte aligned, ldmatrix conflict-free)
+
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint32_t* b) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// A fragment (16 x 16) of a row-major [row][k] tile:           rows row0.., k columns k0..
+__device__ __forceinline__ void load_a(uint32_t* a, const __nv_bfloat16* tile, int pitch, int row0, int k0, int lane) {
+    ldsm_x4(a, tile + (row0 + (lane & 15)) * pitch + k0 + ((lane >> 4) << 3));
+}
+// A fragment of A = M^T where M is stored row-major [k][m]:      m rows m0.., k columns k0..
+__device__ __forceinline__ void load_a_t(uint32_t* a, const __nv_bfloat16* tile, int pitch, int m0, int k0, int lane) {
+    ldsm_x4_t(a, tile + (k0 + (lane & 7) + ((lane >> 4) << 3)) * pitch + m0 + (((lane >> 3) & 1) << 3));
+}
+// B fragment (k16 x n8) with B[k][n] = tile[n][k] (tile row-major [n][k]):   n rows n0.., k columns k0..
+__device__ __forceinline__ void load_b(uint32_t* b, const __nv_bfloat16* tile, int pitch, int n0, int k0, int lane) {
+    ldsm_x2(b, tile + (n0 + (lane & 7)) * pitch + k0 + (((lane >> 3) & 1) << 3));
+}
+// B fragment with B[k][n] = tile[k][n] (tile row-major [k][n]):                k rows k0.., n columns n0..
+__device__ __forceinline__ void load_b_t(uint32_t* b, const __nv_bfloat16* tile, int pitch, int k0, int n0, int lane) {
+    ldsm_x2_t(b, tile + (k0 + (lane & 7) + (((lane >> 3) & 1) << 3)) * pitch + n0);
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ float drop_mult(uint64_t seed, uint32_t thresh, float scale, long long row, int ld, int col) {
+    const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row) * ld + col) >> 2);
+    return (((bits >> (16 * (col & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
+}
+
+// Row-block softmax on the S fragments of one 16-row m-tile.  s[nt][4] holds (row g: c0,c1 ; row g+8: c2,c3)
+// for key columns nt*8 + 2t, +1.  Input scores are pre-scaled into the log2 domain.  Returns P in place.
+template <int NTJ>
+__device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NTJ; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const bool ok = nt * 8 + 2 * t4 + e < T;
+            s[nt][e] = ok ? s[nt][e] : -INFINITY;
+            s[nt][2 + e] = ok ? s[nt][2 + e] : -INFINITY;
+            m0 = fmaxf(m0, s[nt][e]);
+            m1 = fmaxf(m1, s[nt][2 + e]);
+        }
+    }
+    m0 = quad_max(m0);
+    m1 = quad_max(m1);
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NTJ; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            s[nt][e] = exp2f(s[nt][e] - m0);
+            s[nt][2 + e] = exp2f(s[nt][2 + e] - m1);
+            l0 += s[nt][e];
+            l1 += s[nt][2 + e];
+        }
+    }
+    l0 = quad_sum(l0);
+    l1 = quad_sum(l1);
+    const float i0 = 1.f / (l0 + 1e-8f * exp2f(-m0));  // == exp(S)/(sum exp(S) + 1e-8) of the reference
+    const float i1 = 1.f / (l1 + 1e-8f * exp2f(-m1));
+#pragma unroll
+    for (int nt = 0; nt < NTJ; ++nt) {
+        s[nt][0] *= i0;
+        s[nt][1] *= i0;
+        s[nt][2] *= i1;
+        s[nt][3] *= i1;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Warp-private task pipeline.  A task is one (sequence, head); a warp walks tasks gw, gw+W, gw+2W, ... and keeps
+// kStages of them in flight with cp.async (8-byte pieces when d_k % 4 == 0, 4-byte when even, else plain
+// 2-byte copies), so that ~40-60 KB per SM are always outstanding -- the first (CTA-staged, synchronous)
+// version of this kernel was latency bound at ~270 GB/s.
+// Tile = [TP rows][kPitch] bf16, valid region [T][dk]; everything outside stays zero for the whole kernel.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// global rows [T][dk] at g (pitch ld, elements)  ->  tile rows.  piece = bytes per copy (8 / 4 / 2).
+__device__ __forceinline__ void tile_load(__nv_bfloat16* tile, const __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane) {
+    const int epp = piece >> 1;        // elements per piece
+    const int ppr = dk / epp;          // pieces per row
+    const float inv = 1.0f / static_cast<float>(ppr);
+    const int n = T * ppr;
+    for (int i = lane; i < n; i += 32) {
+        const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
+        const int c = (i - r * ppr) * epp;
+        __nv_bfloat16* dst = tile + r * kPitch + c;
+        const __nv_bfloat16* src = g + static_cast<size_t>(r) * ld + c;
+        if (piece == 8) cp_async8(dst, src);
+        else if (piece == 4) cp_async4(dst, src);
+        else *dst = *src;
+    }
+}
+__device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane) {
+    const int epp = piece >> 1;
+    const int ppr = dk / epp;
+    const float inv = 1.0f / static_cast<float>(ppr);
+    const int n = T * ppr;
+    for (int i = lane; i < n; i += 32) {
+        const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
+        const int c = (i - r * ppr) * epp;
+        const __nv_bfloat16* src = tile + r * kPitch + c;
+        __nv_bfloat16* dst = g + static_cast<size_t>(r) * ld + c;
+        if (piece == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+        else if (piece == 4) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+        else *dst = *src;
+    }
+}
+// context tile -> global with the dropout mask applied on the fly (one counter hash per 4 aligned columns)
+__device__ __forceinline__ void tile_store_dropout(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane,
+                                                   long long row0, int col0, uint64_t seed, uint32_t thresh, float scale) {
+    const int epp = piece >> 1;
+    const int ppr = dk / epp;
+    const float inv = 1.0f / static_cast<float>(ppr);
+    const int n = T * ppr;
+    for (int i = lane; i < n; i += 32) {
+        const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
+        const int c = (i - r * ppr) * epp;
+        const __nv_bfloat16* src = tile + r * kPitch + c;
+        __nv_bfloat16* dst = g + static_cast<size_t>(r) * ld + c;
+        const int gc = col0 + c;
+        const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row0 + r) * ld + gc) >> 2);
+        if (piece == 8) {
+            const uint2 u = *reinterpret_cast<const uint2*>(src);
+            float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+            a.x *= ((bits & 0xffffu) >= thresh) ? scale : 0.f;
+            a.y *= (((bits >> 16) & 0xffffu) >= thresh) ? scale : 0.f;
+            b.x *= (((bits >> 32) & 0xffffu) >= thresh) ? scale : 0.f;
+            b.y *= (((bits >> 48) & 0xffffu) >= thresh) ? scale : 0.f;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y));
+        } else if (piece == 4) {
+            float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(src));
+            a.x *= (((bits >> (16 * (gc & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
+            a.y *= (((bits >> (16 * ((gc + 1) & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(a.x, a.y);
+        } else {
+            const float m = (((bits >> (16 * (gc & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
+            *dst = __float2bfloat16_rn(__bfloat162float(*src) * m);
+        }
+    }
+}
+__host__ __device__ inline int piece_bytes(int dk, int ld_a, int ld_b, int d) {
+    if ((dk % 4) == 0 && (ld_a % 4) == 0 && (ld_b % 4) == 0 && (d % 4) == 0) return 8;
+    if ((dk % 2) == 0 && (ld_a % 2) == 0 && (ld_b % 2) == 0 && (d % 2) == 0) return 4;
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int TP, int KSD, int NTD, int STG, int WPS>
+__global__ void __launch_bounds__(WPS * 32) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
+                                                                  int T, int heads, int dk, __nv_bfloat16* __restrict__ ctx,
+                                                                  int ld_ctx, float p, uint64_t seed) {
+    constexpr int NTJ = TP / 8, MT = TP / 16;
+    // A tile holds exactly T rows (pitch kPitch).  Fragment loads of rows >= T run into the neighbouring tile or the
+    // zeroed slack behind the last one: finite bytes that only ever meet zero probabilities / unused output rows.
+    const int TILE = T * kPitch;
+    extern __shared__ __align__(16) __nv_bfloat16 sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int d = heads * dk;
+    for (int i = tid; i < (WPS * STG * 3 * TILE + (TP - T) * kPitch) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    __syncthreads();
+    __nv_bfloat16* wbase = sm + warp * STG * 3 * TILE;
+    const float sc = rsqrtf(static_cast<float>(dk)) * 1.4426950408889634f;
+    const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    const float dscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    const int ntj = (T + 7) >> 3;
+    const int piece = piece_bytes(dk, ld, ld_ctx, d);
+    const long long n_tasks = n_seq * heads;
+    const long long W = static_cast<long long>(gridDim.x) * WPS;
+    const long long gw = static_cast<long long>(blockIdx.x) * WPS + warp;
+
+    auto prefetch = [&](long long task, int stage) {
+        if (task < n_tasks) {
+            const long long seq = task / heads;
+            const int h = static_cast<int>(task - seq * heads);
+            const __nv_bfloat16* src = qkv + seq * T * static_cast<long long>(ld) + h * dk;
+            __nv_bfloat16* t0 = wbase + stage * 3 * TILE;
+            tile_load(t0, src, ld, T, dk, piece, lane);
+            tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
+            tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
+        }
+        cp_commit();
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < STG - 1; ++s0) prefetch(gw + s0 * W, s0);
+
+    int stage = 0;
+    for (long long task = gw; task < n_tasks; task += W) {
+        cp_wait<STG - 2>();
+        __syncwarp();
+        // the stage consumed in the previous iteration is free again: refill it before computing this task
+        prefetch(task + (STG - 1) * W, (stage + STG - 1) % STG);
+        const long long seq = task / heads;
+        const int h = static_cast<int>(task - seq * heads);
+        __nv_bfloat16* q = wbase + stage * 3 * TILE;
+        const __nv_bfloat16* k = q + TILE;
+        const __nv_bfloat16* v = q + 2 * TILE;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            if (mt * 16 >= T) break;
+            float s[NTJ][4];
+#pragma unroll
+            for (int nt = 0; nt < NTJ; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KSD; ++ks) {
+                uint32_t a[4];
+                load_a(a, q, kPitch, mt * 16, ks * 16, lane);
+#pragma unroll
+                for (int nt = 0; nt < NTJ; ++nt) {
+                    if (nt >= ntj) break;
+                    uint32_t b[2];
+                    load_b(b, k, kPitch, nt * 8, ks * 16, lane);
+                    mma_bf16(s[nt], a, b);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTJ; ++nt) {
+                s[nt][0] *= sc; s[nt][1] *= sc; s[nt][2] *= sc; s[nt][3] *= sc;
+            }
+            softmax_rows<NTJ>(s, T, t4);
+            float o[NTD][4];
+#pragma unroll
+            for (int nd = 0; nd < NTD; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+            for (int kj = 0; kj < MT; ++kj) {
+                if (kj * 16 >= T) break;
+                uint32_t a[4];
+                a[0] = pack_bf16x2(s[2 * kj][0], s[2 * kj][1]);
+                a[1] = pack_bf16x2(s[2 * kj][2], s[2 * kj][3]);
+                a[2] = pack_bf16x2(s[2 * kj + 1][0], s[2 * kj + 1][1]);
+                a[3] = pack_bf16x2(s[2 * kj + 1][2], s[2 * kj + 1][3]);
+#pragma unroll
+                for (int nd = 0; nd < NTD; ++nd) {
+                    uint32_t b[2];
+                    load_b_t(b, v, kPitch, kj * 16, nd * 8, lane);
+                    mma_bf16(o[nd], a, b);
+                }
+            }
+            // context rows replace this m-tile's (now dead) Q rows; only the valid [T][dk] region is touched
+            __syncwarp();
+#pragma unroll
+            for (int nd = 0; nd < NTD; ++nd) {
+                const int col = nd * 8 + 2 * t4;
+                if (col >= dk) continue;
+                const bool pair = col + 1 < dk;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int r = mt * 16 + g + hf * 8;
+                    if (r >= T) continue;
+                    const float v0 = o[nd][2 * hf], v1 = pair ? o[nd][2 * hf + 1] : 0.f;
+                    *reinterpret_cast<uint32_t*>(q + r * kPitch + col) = pack_bf16x2(v0, v1);
+                }
+            }
+        }
+        __syncwarp();
+        __nv_bfloat16* out = ctx + seq * T * static_cast<long long>(ld_ctx);
+        if (p > 0.f) tile_store_dropout(q, out + h * dk, ld_ctx, T, dk, piece, lane, seq * T, h * dk, seed, thresh, dscale);
+        else tile_store(q, out + h * dk, ld_ctx, T, dk, piece, lane);
+        if (h == 0) {  // ones column + zero tail of the padded context rows
+            for (int i = lane; i < T * (ld_ctx - d); i += 32) {
+                const int r = i / (ld_ctx - d), c = i - r * (ld_ctx - d);
+                out[static_cast<size_t>(r) * ld_ctx + d + c] = __float2bfloat16_rn(c == 0 ? 1.0f : 0.f);
+            }
+        }
+        __syncwarp();
+        stage = (stage + 1) % STG;
+    }
+    cp_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int TP, int KSD, int NTD, int STG, int WPS>
+__global__ void __launch_bounds__(WPS * 32) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
+                                                                  const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
+                                                                  long long n_seq, int T, int heads, int dk,
+                                                                  __nv_bfloat16* __restrict__ dqkv, int ld_d) {
+    constexpr int NTJ = TP / 8, MT = TP / 16, SP = TP + 8;
+    const int TILE = T * kPitch;  // packed rows, see the forward kernel
+    extern __shared__ __align__(16) __nv_bfloat16 sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int d = heads * dk;
+    const int PER_WARP = STG * 4 * TILE + 2 * TP * SP;  // the P/dS scratch behind a warp's tiles doubles as read slack
+    for (int i = tid; i < WPS * PER_WARP / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    __syncthreads();
+    __nv_bfloat16* wbase = sm + warp * PER_WARP;
+    __nv_bfloat16* ps = wbase + STG * 4 * TILE;  // [TP][SP] probabilities (bf16)
+    __nv_bfloat16* ds = ps + TP * SP;                // [TP][SP] score gradients (bf16)
+    const float rs = rsqrtf(static_cast<float>(dk));
+    const float sc = rs * 1.4426950408889634f;
+    const int ntj = (T + 7) >> 3;
+    const int piece = piece_bytes(dk, ld, ld_dctx, d) == 8 && (ld_d % 4) == 0 ? 8 : (piece_bytes(dk, ld, ld_dctx, d) >= 4 && (ld_d % 2) == 0 ? 4 : 2);
+    const long long n_tasks = n_seq * heads;
+    const long long W = static_cast<long long>(gridDim.x) * WPS;
+    const long long gw = static_cast<long long>(blockIdx.x) * WPS + warp;
+
+    auto prefetch = [&](long long task, int stage) {
+        if (task < n_tasks) {
+            const long long seq = task / heads;
+            const int h = static_cast<int>(task - seq * heads);
+            const __nv_bfloat16* src = qkv + seq * T * static_cast<long long>(ld) + h * dk;
+            __nv_bfloat16* t0 = wbase + stage * 4 * TILE;
+            tile_load(t0, src, ld, T, dk, piece, lane);
+            tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
+            tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
+            tile_load(t0 + 3 * TILE, dctx + seq * T * static_cast<long long>(ld_dctx) + h * dk, ld_dctx, T, dk, piece, lane);
+        }
+        cp_commit();
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < STG - 1; ++s0) prefetch(gw + s0 * W, s0);
+
+    int stage = 0;
+    for (long long task = gw; task < n_tasks; task += W) {
+        cp_wait<STG - 2>();
+        __syncwarp();
+        // the stage consumed in the previous iteration is free again: refill it before computing this task
+        prefetch(task + (STG - 1) * W, (stage + STG - 1) % STG);
+        const long long seq = task / heads;
+        const int h = static_cast<int>(task - seq * heads);
+        const __nv_bfloat16* q = wbase + stage * 4 * TILE;
+        __nv_bfloat16* k = wbase + stage * 4 * TILE + TILE;
+        __nv_bfloat16* v = k + TILE;
+        const __nv_bfloat16* gg = v + TILE;
+        __nv_bfloat16* gout = dqkv + seq * T * static_cast<long long>(ld_d);
+        // ---- phase A (row blocks i): P, dS -> smem (bf16); dQ straight to global ----
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            if (mt * 16 >= T) continue;
+            float dq[NTD][4];
+#pragma unroll
+            for (int nd = 0; nd < NTD; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
+            float s[NTJ][4], dp[NTJ][4];
+#pragma unroll
+            for (int nt = 0; nt < NTJ; ++nt) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+                dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KSD; ++ks) {
+                uint32_t aq[4], ag[4];
+                load_a(aq, q, kPitch, mt * 16, ks * 16, lane);
+                load_a(ag, gg, kPitch, mt * 16, ks * 16, lane);
+#pragma unroll
+                for (int nt = 0; nt < NTJ; ++nt) {
+                    if (nt >= ntj) break;
+                    uint32_t bk[2], bv[2];
+                    load_b(bk, k, kPitch, nt * 8, ks * 16, lane);
+                    load_b(bv, v, kPitch, nt * 8, ks * 16, lane);
+                    mma_bf16(s[nt], aq, bk);    // S  = Q K^T
+                    mma_bf16(dp[nt], ag, bv);   // dA = dCtx V^T
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NTJ; ++nt) {
+                s[nt][0] *= sc; s[nt][1] *= sc; s[nt][2] *= sc; s[nt][3] *= sc;
+            }
+            softmax_rows<NTJ>(s, T, t4);
+            float del0 = 0.f, del1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NTJ; ++nt) {
+                del0 += s[nt][0] * dp[nt][0] + s[nt][1] * dp[nt][1];
+                del1 += s[nt][2] * dp[nt][2] + s[nt][3] * dp[nt][3];
+            }
+            del0 = quad_sum(del0);
+            del1 = quad_sum(del1);
+            const bool r0ok = mt * 16 + g < T, r1ok = mt * 16 + g + 8 < T;
+#pragma unroll
+            for (int nt = 0; nt < NTJ; ++nt) {
+                // rows >= T carry garbage (zero Q rows give a uniform softmax): force them to zero, they are
+                // k-indices of the phase-B products
+                const float p0 = r0ok ? s[nt][0] : 0.f, p1 = r0ok ? s[nt][1] : 0.f;
+                const float p2 = r1ok ? s[nt][2] : 0.f, p3 = r1ok ? s[nt][3] : 0.f;
+                dp[nt][0] = p0 * (dp[nt][0] - del0) * rs;
+                dp[nt][1] = p1 * (dp[nt][1] - del0) * rs;
+                dp[nt][2] = p2 * (dp[nt][2] - del1) * rs;
+                dp[nt][3] = p3 * (dp[nt][3] - del1) * rs;
+                const int col = nt * 8 + 2 * t4;
+                *reinterpret_cast<uint32_t*>(ps + (mt * 16 + g) * SP + col) = pack_bf16x2(p0, p1);
+                *reinterpret_cast<uint32_t*>(ps + (mt * 16 + g + 8) * SP + col) = pack_bf16x2(p2, p3);
+                *reinterpret_cast<uint32_t*>(ds + (mt * 16 + g) * SP + col) = pack_bf16x2(dp[nt][0], dp[nt][1]);
+                *reinterpret_cast<uint32_t*>(ds + (mt * 16 + g + 8) * SP + col) = pack_bf16x2(dp[nt][2], dp[nt][3]);
+            }
+            // dQ = dS K   (A = dS fragments straight from registers, B[k=j][n=d] = K[j][d])
+#pragma unroll
+            for (int kj = 0; kj < MT; ++kj) {
+                if (kj * 16 >= T) break;
+                uint32_t a[4];
+                a[0] = pack_bf16x2(dp[2 * kj][0], dp[2 * kj][1]);
+                a[1] = pack_bf16x2(dp[2 * kj][2], dp[2 * kj][3]);
+                a[2] = pack_bf16x2(dp[2 * kj + 1][0], dp[2 * kj + 1][1]);
+                a[3] = pack_bf16x2(dp[2 * kj + 1][2], dp[2 * kj + 1][3]);
+#pragma unroll
+                for (int nd = 0; nd < NTD; ++nd) {
+                    uint32_t b[2];
+                    load_b_t(b, k, kPitch, kj * 16, nd * 8, lane);
+                    mma_bf16(dq[nd], a, b);
+                }
+            }
+#pragma unroll
+            for (int nd = 0; nd < NTD; ++nd) {
+                const int col = nd * 8 + 2 * t4;
+                if (col >= dk) continue;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int r = mt * 16 + g + hf * 8;
+                    if (r >= T) continue;
+                    __nv_bfloat16* o = gout + static_cast<size_t>(r) * ld_d + h * dk + col;
+                    if (col + 1 < dk && piece >= 4) {
+                        *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(dq[nd][2 * hf], dq[nd][2 * hf + 1]);
+                    } else {
+                        o[0] = __float2bfloat16_rn(dq[nd][2 * hf]);
+                        if (col + 1 < dk) o[1] = __float2bfloat16_rn(dq[nd][2 * hf + 1]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- phase B (row blocks j): dK = dS^T Q, dV = P^T dCtx ----
+        // (K and V tiles are dead after phase A: each row block's result goes straight into them)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            if (mt * 16 >= T) continue;
+            float dkk[NTD][4], dvv[NTD][4];
+#pragma unroll
+            for (int nd = 0; nd < NTD; ++nd) {
+                dkk[nd][0] = dkk[nd][1] = dkk[nd][2] = dkk[nd][3] = 0.f;
+                dvv[nd][0] = dvv[nd][1] = dvv[nd][2] = dvv[nd][3] = 0.f;
+            }
+#pragma unroll
+            for (int ki = 0; ki < MT; ++ki) {
+                if (ki * 16 >= T) break;
+                uint32_t ad[4], ap[4];
+                load_a_t(ad, ds, SP, mt * 16, ki * 16, lane);
+                load_a_t(ap, ps, SP, mt * 16, ki * 16, lane);
+#pragma unroll
+                for (int nd = 0; nd < NTD; ++nd) {
+                    uint32_t bq[2], bg[2];
+                    load_b_t(bq, q, kPitch, ki * 16, nd * 8, lane);
+                    load_b_t(bg, gg, kPitch, ki * 16, nd * 8, lane);
+                    mma_bf16(dkk[nd], ad, bq);
+                    mma_bf16(dvv[nd], ap, bg);
+                }
+            }
+#pragma unroll
+            for (int nd = 0; nd < NTD; ++nd) {
+                const int col = nd * 8 + 2 * t4;
+                if (col >= dk) continue;
+                const bool pair = col + 1 < dk;  // odd d_k: keep the zero padding column intact
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int r = mt * 16 + g + hf * 8;
+                    if (r >= T) continue;
+                    *reinterpret_cast<uint32_t*>(k + r * kPitch + col) = pack_bf16x2(dkk[nd][2 * hf], pair ? dkk[nd][2 * hf + 1] : 0.f);
+                    *reinterpret_cast<uint32_t*>(v + r * kPitch + col) = pack_bf16x2(dvv[nd][2 * hf], pair ? dvv[nd][2 * hf + 1] : 0.f);
+                }
+            }
+        }
+        __syncwarp();
+        tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, lane);
+        tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, lane);
+        __syncwarp();
+        stage = (stage + 1) % STG;
+    }
+    cp_wait<0>();
+}
+
+template <int TP, int KSD, int NTD, int STG, int WPS>
+int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+               void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
+    const long long tasks = n_seq * heads;
+    const size_t tile = sizeof(__nv_bfloat16) * T * kPitch;
+    const size_t smem_f = WPS * STG * 3 * tile + sizeof(__nv_bfloat16) * (TP - T) * kPitch;
+    const size_t smem_b = WPS * (STG * 4 * tile + sizeof(__nv_bfloat16) * 2 * TP * (TP + 8));
+    const size_t smem = bwd ? smem_b : smem_f;
+    NR_REQUIRE(smem <= 227 * 1024, "mhsa: tile set of %zu bytes exceeds shared memory", smem);
+    const int per_sm = std::max<int>(1, std::min<size_t>(6, (224 * 1024) / (smem + 1024)));
+    const int grid = static_cast<int>(std::min<long long>(ceil_div(static_cast<int>(std::min<long long>(tasks, 1 << 30)), WPS),
+                                                          static_cast<long long>(num_sms()) * per_sm));
+    if (!bwd) {
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
+                                                                             heads, dk, static_cast<__nv_bfloat16*>(out), ld_out, drop.p,
+                                                                             drop.seed);
+    } else {
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
+                                                                             static_cast<const __nv_bfloat16*>(dctx), ld_dctx, n_seq, T,
+                                                                             heads, dk, static_cast<__nv_bfloat16*>(out), ld_out);
+    }
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+template <int TP, int KSD, int NTD>
+int launch_mma(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+               void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
+    // 64-row tiles (history-level attention) are 4x larger: the backward keeps a shallower ring on fewer warps
+    if (TP > 32 && bwd)
+        return launch_mma_cfg<TP, KSD, NTD, 2, 3>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    return launch_mma_cfg<TP, KSD, NTD, 2, 4>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+}
+
+template <int TP>
+int dispatch_dk(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
+    if (dk <= 16) return launch_mma<TP, 1, 2>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    if (dk <= 24) return launch_mma<TP, 2, 3>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    return launch_mma<TP, 2, 4>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+}
+
+}  // namespace
+
+int mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx, DropoutCfg drop,
+                  cudaStream_t stream) {
+    if (n_seq == 0) return 0;
+    NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
+    NR_REQUIRE(dk >= 2 && dk <= 32, "mhsa: head size d_k=%d not in [2,32]", dk);
+    NR_REQUIRE(ld_ctx >= heads * dk + 1, "mhsa: context pitch %d has no room for the ones column", ld_ctx);
+    ProfScope ps("mhsa_core_fwd", static_cast<int>(n_seq), T, heads * dk, stream);
+    if (T <= 32) return dispatch_dk<32>(false, qkv, ld_qkv, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
+    return dispatch_dk<64>(false, qkv, ld_qkv, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
+}
+
+int mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+                  void* dqkv, int ld_dqkv, cudaStream_t stream) {
+    if (n_seq == 0) return 0;
+    NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
+    NR_REQUIRE(dk >= 2 && dk <= 32, "mhsa: head size d_k=%d not in [2,32]", dk);
+    ProfScope ps("mhsa_core_bwd", static_cast<int>(n_seq), T, heads * dk, stream);
+    const DropoutCfg nodrop{0.f, 0};
+    if (T <= 32) return dispatch_dk<32>(true, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
+    return dispatch_dk<64>(true, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
+}
+
+}  // namespace nr

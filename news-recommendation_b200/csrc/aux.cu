@@ -142,241 +142,6 @@ int gather_rows(const long long* ids, long long n_tok, int T, const void* table,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Self-attention core, one (sequence, head) per thread group, one query row per thread.
-// Reference semantics (multihead_self.py:15-23): A = exp(S) / (sum exp(S) + 1e-8), S = QK^T/sqrt(dk),
-// no mask.  Implemented in the numerically safe equivalent form exp(S-m) / (sum exp(S-m) + 1e-8 e^{-m}).
-// ------------------------------------------------------------------------------------------------
-template <int DK>
-__global__ void __launch_bounds__(64) mhsa_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
-                                                      int T, int heads, __nv_bfloat16* __restrict__ ctx, int ld_ctx,
-                                                      float p, uint64_t seed, int hpb) {
-    extern __shared__ float sm[];  // K[hpb][T][DK], V[hpb][T][DK]
-    const int d = heads * DK;
-    const int groups = (heads + hpb - 1) / hpb;
-    const long long seq = blockIdx.x / groups;
-    const int h0 = (blockIdx.x % groups) * hpb;
-    const int nh = min(hpb, heads - h0);
-    float* Ks = sm;
-    float* Vs = sm + hpb * T * DK;
-    const __nv_bfloat16* base = qkv + seq * T * static_cast<long long>(ld);
-    for (int i = threadIdx.x; i < nh * T * DK; i += blockDim.x) {
-        const int hh = i / (T * DK);
-        const int rem = i - hh * T * DK;
-        const int j = rem / DK, dd = rem - j * DK;
-        const long long off = static_cast<long long>(j) * ld + (h0 + hh) * DK + dd;
-        Ks[i] = __bfloat162float(base[off + d]);
-        Vs[i] = __bfloat162float(base[off + 2 * d]);
-    }
-    __syncthreads();
-    const int hh = threadIdx.x / T;
-    const int i = threadIdx.x - hh * T;
-    if (hh >= nh) return;
-    const int h = h0 + hh;
-    float q[DK];
-    const float scale = rsqrtf(static_cast<float>(DK)) * 1.4426950408889634f;  // fold log2(e): exp(x) = exp2(x*log2e)
-#pragma unroll
-    for (int dd = 0; dd < DK; ++dd) q[dd] = __bfloat162float(base[static_cast<long long>(i) * ld + h * DK + dd]) * scale;
-    float m = -INFINITY, l = 0.f, acc[DK];
-#pragma unroll
-    for (int dd = 0; dd < DK; ++dd) acc[dd] = 0.f;
-    const float* kh = Ks + hh * T * DK;
-    const float* vh = Vs + hh * T * DK;
-    for (int j = 0; j < T; ++j) {
-        float s = 0.f;
-#pragma unroll
-        for (int dd = 0; dd < DK; ++dd) s = fmaf(q[dd], kh[j * DK + dd], s);
-        const float mn = fmaxf(m, s);
-        const float corr = exp2f(m - mn);
-        const float pj = exp2f(s - mn);
-        l = l * corr + pj;
-#pragma unroll
-        for (int dd = 0; dd < DK; ++dd) acc[dd] = fmaf(pj, vh[j * DK + dd], acc[dd] * corr);
-        m = mn;
-    }
-    const float inv = 1.f / (l + 1e-8f * exp2f(-m));
-    const long long row = seq * T + i;
-    __nv_bfloat16* o = ctx + row * ld_ctx + h * DK;
-    const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-    const float dscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-#pragma unroll
-    for (int dd = 0; dd < DK; ++dd) {
-        float v = acc[dd] * inv;
-        if (p > 0.f) v *= drop_mult(seed, thresh, dscale, row, ld_ctx, h * DK + dd);
-        o[dd] = __float2bfloat16_rn(v);
-    }
-    if (h == 0) {  // ones column + zero tail of the padded row
-        __nv_bfloat16* r = ctx + row * ld_ctx;
-        r[d] = __float2bfloat16_rn(1.0f);
-        for (int c = d + 1; c < ld_ctx; ++c) r[c] = __float2bfloat16_rn(0.f);
-    }
-}
-
-template <int DK>
-__global__ void __launch_bounds__(64) mhsa_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
-                                                      const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
-                                                      long long n_seq, int T, int heads,
-                                                      __nv_bfloat16* __restrict__ dqkv, int ld_d, int hpb) {
-    extern __shared__ float sm[];
-    const int d = heads * DK;
-    const int groups = (heads + hpb - 1) / hpb;
-    const long long seq = blockIdx.x / groups;
-    const int h0 = (blockIdx.x % groups) * hpb;
-    const int nh = min(hpb, heads - h0);
-    const int TD = T * DK, TT = T * T;
-    float* Qs = sm;                  // [hpb][T][DK]
-    float* Ks = Qs + hpb * TD;
-    float* Vs = Ks + hpb * TD;
-    float* Gs = Vs + hpb * TD;       // dCtx
-    float* Ps = Gs + hpb * TD;       // [hpb][T][T]  P
-    float* Ss = Ps + hpb * TT;       // [hpb][T][T]  dS (scaled)
-    const __nv_bfloat16* base = qkv + seq * T * static_cast<long long>(ld);
-    const __nv_bfloat16* gbase = dctx + seq * T * static_cast<long long>(ld_dctx);
-    for (int i = threadIdx.x; i < nh * TD; i += blockDim.x) {
-        const int hh = i / TD;
-        const int rem = i - hh * TD;
-        const int j = rem / DK, dd = rem - j * DK;
-        const int col = (h0 + hh) * DK + dd;
-        const long long off = static_cast<long long>(j) * ld + col;
-        Qs[i] = __bfloat162float(base[off]);
-        Ks[i] = __bfloat162float(base[off + d]);
-        Vs[i] = __bfloat162float(base[off + 2 * d]);
-        Gs[i] = __bfloat162float(gbase[static_cast<long long>(j) * ld_dctx + col]);
-    }
-    __syncthreads();
-    const int hh = threadIdx.x / T;
-    const int i = threadIdx.x - hh * T;
-    const bool active = hh < nh;
-    const int h = h0 + hh;
-    const float rs = rsqrtf(static_cast<float>(DK));
-    const float* qh = Qs + hh * TD;
-    const float* kh = Ks + hh * TD;
-    const float* vh = Vs + hh * TD;
-    const float* gh = Gs + hh * TD;
-    float* ph = Ps + hh * TT;
-    float* sh = Ss + hh * TT;
-    if (active) {
-        // phase A (row i): scores, softmax-with-epsilon, dP, delta, dS, dQ
-        float q[DK], g[DK];
-#pragma unroll
-        for (int dd = 0; dd < DK; ++dd) {
-            q[dd] = qh[i * DK + dd] * (rs * 1.4426950408889634f);
-            g[dd] = gh[i * DK + dd];
-        }
-        float m = -INFINITY;
-        for (int j = 0; j < T; ++j) {
-            float s = 0.f;
-#pragma unroll
-            for (int dd = 0; dd < DK; ++dd) s = fmaf(q[dd], kh[j * DK + dd], s);
-            ph[i * T + j] = s;
-            m = fmaxf(m, s);
-        }
-        float l = 0.f;
-        for (int j = 0; j < T; ++j) {
-            const float e = exp2f(ph[i * T + j] - m);
-            ph[i * T + j] = e;
-            l += e;
-        }
-        const float inv = 1.f / (l + 1e-8f * exp2f(-m));
-        float delta = 0.f;
-        for (int j = 0; j < T; ++j) {
-            const float pij = ph[i * T + j] * inv;
-            float dp = 0.f;
-#pragma unroll
-            for (int dd = 0; dd < DK; ++dd) dp = fmaf(g[dd], vh[j * DK + dd], dp);
-            ph[i * T + j] = pij;
-            sh[i * T + j] = dp;
-            delta = fmaf(pij, dp, delta);
-        }
-        float dq[DK];
-#pragma unroll
-        for (int dd = 0; dd < DK; ++dd) dq[dd] = 0.f;
-        for (int j = 0; j < T; ++j) {
-            const float ds = ph[i * T + j] * (sh[i * T + j] - delta) * rs;
-            sh[i * T + j] = ds;
-#pragma unroll
-            for (int dd = 0; dd < DK; ++dd) dq[dd] = fmaf(ds, kh[j * DK + dd], dq[dd]);
-        }
-        __nv_bfloat16* o = dqkv + (seq * T + i) * static_cast<long long>(ld_d) + h * DK;
-#pragma unroll
-        for (int dd = 0; dd < DK; ++dd) o[dd] = __float2bfloat16_rn(dq[dd]);
-    }
-    __syncthreads();
-    if (active) {
-        // phase B (column j = i): dK_j = sum_i dS_ij Q_i ; dV_j = sum_i P_ij dCtx_i
-        const int j = i;
-        float dk[DK], dv[DK];
-#pragma unroll
-        for (int dd = 0; dd < DK; ++dd) { dk[dd] = 0.f; dv[dd] = 0.f; }
-        for (int r = 0; r < T; ++r) {
-            const float ds = sh[r * T + j];
-            const float pp = ph[r * T + j];
-#pragma unroll
-            for (int dd = 0; dd < DK; ++dd) {
-                dk[dd] = fmaf(ds, qh[r * DK + dd], dk[dd]);
-                dv[dd] = fmaf(pp, gh[r * DK + dd], dv[dd]);
-            }
-        }
-        __nv_bfloat16* o = dqkv + (seq * T + j) * static_cast<long long>(ld_d) + h * DK;
-#pragma unroll
-        for (int dd = 0; dd < DK; ++dd) {
-            o[d + dd] = __float2bfloat16_rn(dk[dd]);
-            o[2 * d + dd] = __float2bfloat16_rn(dv[dd]);
-        }
-    }
-}
-
-template <int DK>
-static int mhsa_launch(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T,
-                       int heads, void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
-    const int hpb = std::max(1, 64 / T);
-    const int groups = ceil_div(heads, hpb);
-    const long long blocks = n_seq * groups;
-    NR_REQUIRE(blocks < (1ll << 31), "mhsa: too many (sequence, head-group) blocks");
-    ProfScope ps(bwd ? "mhsa_core_bwd" : "mhsa_core_fwd", static_cast<int>(n_seq), T, heads * DK, stream);
-    if (!bwd) {
-        const size_t smem = sizeof(float) * 2 * hpb * T * DK;
-        mhsa_fwd_kernel<DK><<<static_cast<unsigned>(blocks), 64, smem, stream>>>(
-            static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T, heads, static_cast<__nv_bfloat16*>(out), ld_out,
-            drop.p, drop.seed, hpb);
-    } else {
-        const size_t smem = sizeof(float) * (4 * hpb * T * DK + 2 * hpb * T * T);
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        mhsa_bwd_kernel<DK><<<static_cast<unsigned>(blocks), 64, smem, stream>>>(
-            static_cast<const __nv_bfloat16*>(qkv), ld_qkv, static_cast<const __nv_bfloat16*>(dctx), ld_dctx, n_seq, T,
-            heads, static_cast<__nv_bfloat16*>(out), ld_out, hpb);
-    }
-    ++g_launches;
-    NR_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}
-
-#define NR_DK_DISPATCH(dk, ...)                                                        \
-    switch (dk) {                                                                      \
-        case 10: return mhsa_launch<10>(__VA_ARGS__);                                  \
-        case 12: return mhsa_launch<12>(__VA_ARGS__);                                  \
-        case 15: return mhsa_launch<15>(__VA_ARGS__);                                  \
-        case 20: return mhsa_launch<20>(__VA_ARGS__);                                  \
-        case 25: return mhsa_launch<25>(__VA_ARGS__);                                  \
-        case 30: return mhsa_launch<30>(__VA_ARGS__);                                  \
-        default: set_error("mhsa: unsupported head size d_k=%d (supported: 10,12,15,20,25,30)", dk); return -1; \
-    }
-
-int mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
-                  DropoutCfg drop, cudaStream_t stream) {
-    if (n_seq == 0) return 0;
-    NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
-    NR_REQUIRE(ld_ctx >= heads * dk + 1, "mhsa: context pitch %d has no room for the ones column", ld_ctx);
-    NR_DK_DISPATCH(dk, false, qkv, ld_qkv, nullptr, 0, n_seq, T, heads, ctx, ld_ctx, drop, stream);
-}
-int mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
-                  void* dqkv, int ld_dqkv, cudaStream_t stream) {
-    if (n_seq == 0) return 0;
-    NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
-    DropoutCfg nodrop{0.f, 0};
-    NR_DK_DISPATCH(dk, true, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dqkv, ld_dqkv, nodrop, stream);
-}
-
-// ------------------------------------------------------------------------------------------------
 // pooling backward, scalar part: dw_r = dOut[seg] . X_r ; dscore_r = w_r (dw_r - sum_seg w dw)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pool_dscore_kernel(const __nv_bfloat16* __restrict__ X, int lda, int D,

@@ -520,6 +520,9 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
     e.drop = to_drop(drop);
     e.relu_src = static_cast<const __nv_bfloat16*>(relu_src);
     e.relu_ld = relu_ld;
+    e.M = M;
+    e.rows_per_tile = kTileM;
+    NR_REQUIRE(seg_len >= 2, "pool_dinput: seg_len=%d (staging buffer holds 80 segments per tile)", seg_len);
     g_launches += debug_simt_gemm() ? 2 : 1;
     ProfScope ps("gemm_pool_dinput", M, D, q, stream);
     return launch_gemm_nt(plan, e, dpre, ld_dpre, WaT, ldwT, stream);

@@ -22,7 +22,7 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                     // bf16 elements per 128-byte swizzle row
 constexpr int kAStageBytes = kTileM * 128;      // 16 KB
 constexpr int kMaxStages = 8;
-constexpr int kEpiScratchBytes = 6144;
+constexpr int kEpiScratchBytes = 10240;
 constexpr int kSmemLimit = 232448;              // 227 KB
 
 struct GemmNTParams {
@@ -186,7 +186,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue warps 0..3 =====================
-        epi.init(threadIdx.x, scratch);
+        epi.init(col0, ncols, threadIdx.x, scratch);
         int it = 0;
         for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128, 1) gemm_nt_simt_epi_kernel(const GemmNTPa
     const int ncols = min(p.n_stride, p.N - col0);
     for (int i = threadIdx.x; i < kEpiScratchBytes / 4; i += 128) scratch[i] = 0.f;
     __syncthreads();
-    epi.init(threadIdx.x, scratch);
+    epi.init(col0, ncols, threadIdx.x, scratch);
     for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step) {
         EpiCtx c;
         c.tile = tile;

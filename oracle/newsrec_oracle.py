@@ -99,16 +99,23 @@ BF16 = Contract(True)
 # --------------------------------------------------------------------------- #
 # shared modules  (reference: src/model/general/**)
 # --------------------------------------------------------------------------- #
-def scaled_dot_product_attention(Q, K, V):
+def scaled_dot_product_attention(Q, K, V, c: "Contract" = None):
     """src/model/general/attention/multihead_self.py:15-23.
 
     scores = exp(QK^T/sqrt(d_k)) WITHOUT max-subtraction; attn = scores/(sum+1e-8);
     no mask (no caller passes `length`).
+    Contract: the attention probabilities enter the A.V product as bf16 tensor-core operands, and the
+    gradient w.r.t. the scaled scores is rounded to bf16 (operand of the dQ / dK products); the softmax
+    arithmetic itself is fp32.
     """
     d_k = Q.shape[-1]
-    scores = torch.matmul(Q, K.transpose(-1, -2)) / math.sqrt(d_k)
-    scores = torch.exp(scores)
+    raw = torch.matmul(Q, K.transpose(-1, -2))
+    if c is not None:
+        raw = c.grad(raw)  # the kernels round dS/sqrt(d_k), i.e. the gradient w.r.t. the UNscaled product
+    scores = torch.exp(raw / math.sqrt(d_k))
     attn = scores / (torch.sum(scores, dim=-1, keepdim=True) + 1e-8)
+    if c is not None:
+        attn = c.operand(attn)
     return torch.matmul(attn, V)
 
 
@@ -129,7 +136,7 @@ def multihead_self_attention(x, p, prefix, heads, c: Contract = EXACT):
     def split(t):  # (N,T,d) -> (N,h,T,d_k)   (:53-58)
         return t.view(N, T, heads, d_k).transpose(1, 2)
 
-    ctx = scaled_dot_product_attention(split(proj("Q")), split(proj("K")), split(proj("V")))
+    ctx = scaled_dot_product_attention(split(proj("Q")), split(proj("K")), split(proj("V")), c)
     ctx = ctx.transpose(1, 2).contiguous().view(N, T, d)  # (:74-76)
     return c.act(ctx)
 

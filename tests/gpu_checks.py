@@ -167,7 +167,7 @@ def check_mhsa_core(n_seq=7, T=20, heads=15, dk=20):
     ld3, ldx = ru8(3 * d), ru8(d + 1)
     qkv = _rand_bf16((n_seq * T, 3 * d), 21, 1.5).requires_grad_(True)
     Q, K, V = [t.view(n_seq, T, heads, dk).transpose(1, 2) for t in qkv.split(d, dim=1)]
-    ctx = O.scaled_dot_product_attention(Q, K, V).transpose(1, 2).reshape(n_seq * T, d)
+    ctx = O.scaled_dot_product_attention(Q, K, V, O.BF16).transpose(1, 2).reshape(n_seq * T, d)
     g = _rand_bf16((n_seq * T, d), 22)
     ctx.backward(g)
     qd = torch.zeros(n_seq * T, ld3)

@@ -36,6 +36,11 @@ CHECKS = {
     "gemm_tn_shift_neg": ("check_gemm_tn", dict(Kr=900, Ma=400, Nb=301, shift=-1)),
     "mhsa_core_t20": ("check_mhsa_core", dict(n_seq=7, T=20)),
     "mhsa_core_t50": ("check_mhsa_core", dict(n_seq=3, T=50)),
+    "mhsa_core_many": ("check_mhsa_core", dict(n_seq=2000, T=20)),
+    "mhsa_core_t16_dk10": ("check_mhsa_core", dict(n_seq=5, T=16, heads=30, dk=10)),
+    "mhsa_core_t33_dk15": ("check_mhsa_core", dict(n_seq=5, T=33, heads=20, dk=15)),
+    "mhsa_core_t64_dk30": ("check_mhsa_core", dict(n_seq=4, T=64, heads=10, dk=30)),
+    "mhsa_core_t7_dk25": ("check_mhsa_core", dict(n_seq=9, T=7, heads=12, dk=25)),
     "additive": ("check_additive", {}),
     "additive_s50": ("check_additive", dict(N=9, S=50)),
     "additive_s4_f400": ("check_additive", dict(N=50, S=4, D=400)),
