@@ -152,6 +152,82 @@ typedef struct {
 long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q);
 int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream);
 
+/* ---- reference: title / abstract CNN encoder ------------------------------------------------------------
+ *   NAML  TextEncoder      src/model/NAML/news_encoder.py:21-37
+ *   LSTUR title branch     src/model/LSTUR/news_encoder.py:56-72
+ *   TANR  NewsEncoder      src/model/TANR/news_encoder.py:40-52
+ * embedding -> dropout -> Conv2d(1, F, (3, d), padding (1, 0)) -> ReLU -> dropout -> additive pooling.
+ * The conv is three row-shifted tcgen05 GEMM taps over a zero-padded layout (T+2 rows per segment). */
+typedef struct {
+    long long n_seq;
+    int T, d, F, q, ldx, ldf;       /* ldx = round_up(d+1, 8), ldf = round_up(F+1, 8)                       */
+    const long long* ids;           /* [n_seq*T]                                                          */
+    const void* table_bf16;         /* [V][ldx]                                                           */
+    int V;
+    const void* wconv_bf16;         /* [3*F][ldx]; rows s*F..(s+1)*F hold tap s = weight[:, 0, s, :]        */
+    const float* bconv;             /* [F]                                                                */
+    const void* wa_bf16;            /* [q][ldf]                                                           */
+    const float* ba;
+    const float* qv;
+    float p_drop;
+    unsigned long long seed;
+    void* Xp_bf16;                  /* [n_seq*(T+2)][ldx]  gathered rows, zero-padded layout (saved)        */
+    void* Y_bf16;                   /* [n_seq*T][ldf]      relu(conv) rows (saved)                          */
+    float* w;                       /* [n_seq*T]                                                          */
+    float* out;                     /* [n_seq][F]                                                         */
+    int* bad_id_flag;
+} nr_cnn_encoder_fwd_args;
+int nr_cnn_encoder_fwd(const nr_cnn_encoder_fwd_args* a, void* stream);
+
+typedef struct {
+    long long n_seq;
+    int T, d, F, q, ldx, ldf, ldq;
+    const long long* ids;
+    int V;
+    const void* wconvT_bf16;        /* [3*d][ldf]; rows s*d..(s+1)*d hold (weight[:, 0, 2-s, :])^T          */
+    const void* wa_bf16;            /* [q][ldf]                                                           */
+    const void* waT_bf16;           /* [F][ldq]                                                           */
+    const float* ba;
+    const float* qv;
+    float p_drop;
+    unsigned long long seed;
+    const void* Xp_bf16;
+    const void* Y_bf16;
+    const float* w;
+    const float* dout;              /* [n_seq][F]                                                         */
+    float* dWconv_ext;              /* [3][F][ldx] (+=); column d of tap 1 is d(bias)                       */
+    float* dWa_ext;                 /* [q][ldf] (+=); column F is d(bias)                                   */
+    float* dqv;                     /* [q] (+=)                                                           */
+    float* demb;                    /* [V][d] (+=)                                                        */
+    void* workspace;
+    long long workspace_bytes;
+} nr_cnn_encoder_bwd_args;
+long long nr_cnn_encoder_bwd_workspace(long long n_seq, int T, int F, int q);
+int nr_cnn_encoder_bwd(const nr_cnn_encoder_bwd_args* a, void* stream);
+
+/* ---- generic Linear over dense fp32 rows (TANR topic predictor src/model/TANR/__init__.py:58-61, GRU
+ * projections).  fwd: X_bf16 = bf16(x | 1) (saved), out = act(X W^T + b).  bwd: dW_ext[N][ldx] += dY^T [X|1]
+ * (column K = d(bias)), dx = dY W (optional).  relu_out masks dy with (relu_out > 0). */
+int nr_linear_rows_fwd(const float* x, long long n, int K, long long s_row, long long s_col, void* X_bf16, int ldx,
+                       const void* W_bf16, int N, int ldw, const float* bias, int relu, float* out, int ld_out,
+                       void* stream);
+int nr_linear_rows_bwd(const float* dy, const float* relu_out, long long n, int N, int ld_dy, void* dY_bf16, int ldn,
+                       const void* X_bf16, int K, int ldx, const void* WT_bf16, int ldwT, float* dW_ext, float* dx,
+                       int ld_dx, void* stream);
+
+/* ---- fp32 embedding lookups (LSTUR category / user embeddings, src/model/LSTUR/news_encoder.py:47-53) ---- */
+int nr_embedding_f32_fwd(const long long* ids, long long n, const float* table, int V, int D, float* out,
+                         int* bad_id_flag, void* stream);
+int nr_embedding_f32_bwd(const long long* ids, long long n, const float* dout, int D, float* dtable, void* stream);
+
+/* ---- reference: NAML ElementEncoder  relu(Linear(embedding(id)))  (src/model/NAML/news_encoder.py:40-47) --- */
+int nr_element_encoder_fwd(const long long* ids, long long n, const void* table_bf16, int V, int E, int lde,
+                           void* E_bf16, const void* W_bf16, int F, const float* bias, float* out, int* bad_id_flag,
+                           void* stream);
+int nr_element_encoder_bwd(const long long* ids, long long n, const float* dout, const float* out, int F, void* dY_bf16,
+                           int ldf, const void* E_bf16, int E, int lde, const void* WT_bf16, float* dW_ext,
+                           float* dtable, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

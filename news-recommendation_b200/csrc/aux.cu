@@ -187,6 +187,82 @@ int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// ReLU backward + cast:  dst = dy * (relu_out > 0)  -> zero padded bf16 rows
+// ------------------------------------------------------------------------------------------------
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ ro, long long n, int N, int ld_dy,
+                                __nv_bfloat16* __restrict__ dst, int ldn) {
+    const long long total = n * ldn;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / ldn;
+        const int c = static_cast<int>(i - r * ldn);
+        float v = 0.f;
+        if (c < N) {
+            v = dy[r * ld_dy + c];
+            if (ro != nullptr && !(ro[r * ld_dy + c] > 0.f)) v = 0.f;
+        }
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+int relu_bwd_to_bf16(const float* dy, const float* relu_out, long long n, int N, int ld_dy, void* dst, int ldn, cudaStream_t stream) {
+    if (n == 0) return 0;
+    ProfScope ps("relu_bwd_to_bf16", static_cast<int>(n), N, ldn, stream);
+    const int blocks = static_cast<int>(std::min<long long>((n * ldn + 255) / 256, 148 * 16));
+    relu_bwd_kernel<<<blocks, 256, 0, stream>>>(dy, relu_out, n, N, ld_dy, static_cast<__nv_bfloat16*>(dst), ldn);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 embedding rows (category / user tables): gather forward, red.add scatter backward
+// ------------------------------------------------------------------------------------------------
+__global__ void emb_f32_fwd_kernel(const long long* __restrict__ ids, long long n, const float* __restrict__ table, int V, int D,
+                                   float* __restrict__ out, int* bad_flag) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long i = w0; i < n; i += nw) {
+        long long id = ids[i];
+        if (id < 0 || id >= V) {
+            if (lane == 0) atomicExch(bad_flag, 1);
+            id = 0;
+        }
+        for (int c = lane; c < D; c += 32) out[i * D + c] = table[id * D + c];
+    }
+}
+__global__ void emb_f32_bwd_kernel(const long long* __restrict__ ids, long long n, const float* __restrict__ dout, int D,
+                                   float* __restrict__ dtable) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long i = w0; i < n; i += nw) {
+        const long long id = ids[i];
+        if (id == 0) continue;  // padding_idx
+        for (int c = lane; c < D; c += 32) red_add_f32(dtable + id * D + c, dout[i * D + c]);
+    }
+}
+int embedding_f32_fwd(const long long* ids, long long n, const float* table, int V, int D, float* out, int* bad_id_flag,
+                      cudaStream_t stream) {
+    if (n == 0) return 0;
+    ProfScope ps("embedding_f32_fwd", static_cast<int>(n), D, V, stream);
+    const int blocks = static_cast<int>(std::min<long long>((n + 7) / 8, 148 * 8));
+    emb_f32_fwd_kernel<<<blocks, 256, 0, stream>>>(ids, n, table, V, D, out, bad_id_flag);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int embedding_f32_bwd(const long long* ids, long long n, const float* dout, int D, float* dtable, cudaStream_t stream) {
+    if (n == 0) return 0;
+    ProfScope ps("embedding_f32_bwd", static_cast<int>(n), D, 0, stream);
+    const int blocks = static_cast<int>(std::min<long long>((n + 7) / 8, 148 * 8));
+    emb_f32_bwd_kernel<<<blocks, 256, 0, stream>>>(ids, n, dout, D, dtable);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // dot-product click predictor (reference dot_product.py:8-19): one warp per (impression, candidate)
 // ------------------------------------------------------------------------------------------------
 __global__ void dot_fwd_kernel(const float* __restrict__ cand, const float* __restrict__ user, int B, int C, int D,

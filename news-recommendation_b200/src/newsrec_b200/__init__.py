@@ -40,6 +40,30 @@ class MhsaEncoderBwdArgs(C.Structure):
     ]
 
 
+class CnnEncoderFwdArgs(C.Structure):
+    """nr_cnn_encoder_fwd_args (include/newsrec_b200.h)."""
+    _fields_ = [
+        ("n_seq", _ll), ("T", _i), ("d", _i), ("F", _i), ("q", _i), ("ldx", _i), ("ldf", _i),
+        ("ids", _vp), ("table_bf16", _vp), ("V", _i),
+        ("wconv_bf16", _vp), ("bconv", _vp), ("wa_bf16", _vp), ("ba", _vp), ("qv", _vp),
+        ("p_drop", _f), ("seed", _ull),
+        ("Xp_bf16", _vp), ("Y_bf16", _vp), ("w", _vp), ("out", _vp), ("bad_id_flag", _vp),
+    ]
+
+
+class CnnEncoderBwdArgs(C.Structure):
+    """nr_cnn_encoder_bwd_args (include/newsrec_b200.h)."""
+    _fields_ = [
+        ("n_seq", _ll), ("T", _i), ("d", _i), ("F", _i), ("q", _i), ("ldx", _i), ("ldf", _i), ("ldq", _i),
+        ("ids", _vp), ("V", _i),
+        ("wconvT_bf16", _vp), ("wa_bf16", _vp), ("waT_bf16", _vp), ("ba", _vp), ("qv", _vp),
+        ("p_drop", _f), ("seed", _ull),
+        ("Xp_bf16", _vp), ("Y_bf16", _vp), ("w", _vp), ("dout", _vp),
+        ("dWconv_ext", _vp), ("dWa_ext", _vp), ("dqv", _vp), ("demb", _vp),
+        ("workspace", _vp), ("workspace_bytes", _ll),
+    ]
+
+
 # name -> (restype, argtypes).  Must list EVERY symbol include/newsrec_b200.h declares
 # (tests/test_abi_symbols.py cross-checks this table against the header and the built .so).
 SIGNATURES = {
@@ -68,6 +92,15 @@ SIGNATURES = {
     "nr_mhsa_encoder_fwd": (_i, [C.POINTER(MhsaEncoderFwdArgs), _vp]),
     "nr_mhsa_encoder_bwd_workspace": (_ll, [_ll, _i, _i, _i]),
     "nr_mhsa_encoder_bwd": (_i, [C.POINTER(MhsaEncoderBwdArgs), _vp]),
+    "nr_cnn_encoder_fwd": (_i, [C.POINTER(CnnEncoderFwdArgs), _vp]),
+    "nr_cnn_encoder_bwd_workspace": (_ll, [_ll, _i, _i, _i]),
+    "nr_cnn_encoder_bwd": (_i, [C.POINTER(CnnEncoderBwdArgs), _vp]),
+    "nr_linear_rows_fwd": (_i, [_vp, _ll, _i, _ll, _ll, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "nr_linear_rows_bwd": (_i, [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
+    "nr_embedding_f32_fwd": (_i, [_vp, _ll, _vp, _i, _i, _vp, _vp, _vp]),
+    "nr_embedding_f32_bwd": (_i, [_vp, _ll, _vp, _i, _vp, _vp]),
+    "nr_element_encoder_fwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "nr_element_encoder_bwd": (_i, [_vp, _ll, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -218,7 +218,7 @@ def naml_element_encoder(ids, p, prefix, c: Contract = EXACT):
     """src/model/NAML/news_encoder.py:46-47: relu(linear(embedding(id)))."""
     e = F.embedding(ids, c.operand(p[f"{prefix}.embedding.weight"]), padding_idx=0)
     w = c.operand(p[f"{prefix}.linear.weight"])
-    return F.relu(F.linear(e, w) + p[f"{prefix}.linear.bias"])
+    return F.relu(c.grad(F.linear(e, w) + p[f"{prefix}.linear.bias"]))  # kernel stores d(pre-activation) in bf16
 
 
 NAML_VIEW_ORDER = ("title", "abstract", "category", "subcategory")
@@ -273,7 +273,7 @@ def tanr_forward(cand, clicked, p, c: Contract = EXACT):
     logits = dot_product_click_predictor(cv, user)
     # :58-67  topic head over all B*(C+H) news vectors, class 0 has weight 0
     allv = torch.cat((cv, hv), dim=1).reshape(-1, cv.shape[-1])
-    y_pred = F.linear(c.act(allv), c.operand(p["topic_predictor.weight"])) + p["topic_predictor.bias"]
+    y_pred = c.grad(F.linear(c.operand(allv), c.operand(p["topic_predictor.weight"])) + p["topic_predictor.bias"])
     y = torch.cat((cand["category"], clicked["category"]), dim=1).flatten()
     class_weight = torch.ones(y_pred.shape[1], dtype=y_pred.dtype)
     class_weight[0] = 0

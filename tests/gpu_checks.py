@@ -464,3 +464,93 @@ def check_encoder_backend_diff(B=8, V=500, seed=5):
     res["news.out.tc_vs_oracle_worst_rows"] = dn.topk(5).indices.tolist()
     res["news.out.tc_vs_oracle_worst_vals"] = [float(v) for v in dn.topk(5).values]
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+def build_model(case, V=120, ncat=15, nusers=40, H=6, dropout=0.2):
+    """Drop-in model + deterministic state_dict for a golden case name (see oracle/make_golden.py)."""
+    import importlib
+    import config as cfgmod
+    from golden_util import case_shapes
+    name = {"nrms": "NRMS", "naml": "NAML", "naml_f400": "NAML", "tanr": "TANR", "lstur_ini": "LSTUR", "lstur_con": "LSTUR"}[case]
+    over = dict(num_words=V, num_categories=ncat, num_users=nusers, num_clicked_news_a_user=H, dropout_probability=dropout)
+    if case == "naml_f400":
+        over["num_filters"] = 400
+    if case.startswith("lstur"):
+        over["long_short_term_method"] = case.split("_")[1]
+    cfg = type("Cfg", (getattr(cfgmod, name + "Config"),), over)
+    Model = getattr(importlib.import_module("model." + name), name)
+    return Model(cfg).to(DEV), cfg
+
+
+def golden_inputs(case, g):
+    """Reference-style slot lists for a golden case."""
+    t = lambda k: torch.from_numpy(g[k])
+    keys = {"title": "title", "abstract": "abstract", "category": "category", "subcategory": "subcategory"}
+    def mk(prefix):
+        n = g[prefix + "_title"].shape[1]
+        out = []
+        for j in range(n):
+            dct = {}
+            for k in keys:
+                if f"{prefix}_{k}" in g:
+                    dct[k] = t(f"{prefix}_{k}")[:, j].contiguous()
+            out.append(dct)
+        return out
+    return mk("cand"), mk("clicked")
+
+
+def check_golden(case):
+    """A committed golden case (minted from the live reference): CUDA drop-in vs the reference's fp32 outputs, vs the
+    oracle under the bf16 storage contract, and -- per gradient -- against the exact fp32 oracle next to the error the
+    bf16 contract itself has (kernel_err <= ~1.5 x contract_err is the pass criterion)."""
+    from golden_util import case_params, load_case, oracle_forward, unique_params
+    g = load_case(case)
+    p_b = case_params(case, g)
+    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16)
+    (O.click_loss(logits_b) + (0.1 * topic_b if topic_b is not None else 0.0)).backward()
+    p_x = case_params(case, g)
+    logits_x, topic_x = oracle_forward(case, g, p_x, O.EXACT)
+    (O.click_loss(logits_x) + (0.1 * topic_x if topic_x is not None else 0.0)).backward()
+    model, _ = build_model(case)
+    sd = O.tie_shared(O.det_state_dict(__import__("golden_util").case_shapes(case), int(g["seed"])))
+    model.load_state_dict(sd)
+    model.eval()
+    cand, clicked = golden_inputs(case, g)
+    if case.startswith("lstur"):
+        out = model(torch.from_numpy(g["user"]), torch.from_numpy(g["clicked_news_length"]).clone(), cand, clicked)
+    else:
+        out = model(cand, clicked)
+    logits, topic = (out if isinstance(out, tuple) else (out, None))
+    loss = torch.nn.functional.cross_entropy(logits, torch.zeros(logits.shape[0], dtype=torch.long, device=DEV))
+    (loss + (0.1 * topic if topic is not None else 0.0)).backward()
+    torch.cuda.synchronize()
+    res = {"logits_vs_oracle_bf16": relerr(logits, logits_b), "logits_vs_reference_fp32": relerr(logits, torch.from_numpy(g["logits"])),
+           "oracle_bf16_vs_reference_fp32": relerr(logits_b, torch.from_numpy(g["logits"])),
+           "loss_abs_vs_reference": abs(loss.item() - float(g["loss"]))}
+    if topic is not None:
+        res["topic_loss_rel_vs_reference"] = abs(topic.item() - float(g["topic_loss"])) / abs(float(g["topic_loss"]))
+    grads = dict(model.named_parameters())
+    worst_ratio, worst_key, worst_vs_b = 0.0, "", 0.0
+    gscale = max(float(v.grad.norm()) for v in unique_params(p_x).values())
+    for k, prm in unique_params(p_x).items():
+        gk = grads[k].grad
+        if gk is None:
+            res["missing_grad:" + k] = True
+            continue
+        if prm.grad.norm() < 1e-4 * gscale:  # analytically ~0 gradients (W_K.bias): rounding noise only
+            continue
+        e_kernel = relerr(gk, prm.grad)
+        e_contract = relerr(unique_params(p_b)[k].grad, prm.grad)
+        e_vs_b = relerr(gk, unique_params(p_b)[k].grad)
+        res["grad:" + k] = [e_kernel, e_contract, e_vs_b]
+        ratio = e_kernel / max(e_contract, 2e-3)
+        if ratio > worst_ratio:
+            worst_ratio, worst_key = ratio, k
+        worst_vs_b = max(worst_vs_b, e_vs_b)
+    res["worst_grad_ratio_kernel_over_contract"] = worst_ratio
+    res["worst_grad_key"] = worst_key
+    res["worst_grad_vs_oracle_bf16"] = worst_vs_b
+    w = grads.get("news_encoder.word_embedding.weight", grads.get("news_encoder.text_encoders.title.word_embedding.weight"))
+    res["emb_row0_grad_zero"] = bool((w.grad[0] == 0).all())
+    return res

@@ -49,6 +49,12 @@ CHECKS = {
     "encoder_backend_diff": ("check_encoder_backend_diff", {}),
     "dot_score": ("check_dot_score", {}),
     "nrms_golden": ("check_nrms_golden", {}),
+    "golden_nrms": ("check_golden", dict(case="nrms")),
+    "golden_naml": ("check_golden", dict(case="naml")),
+    "golden_naml_f400": ("check_golden", dict(case="naml_f400")),
+    "golden_tanr": ("check_golden", dict(case="tanr")),
+    "golden_lstur_ini": ("check_golden", dict(case="lstur_ini")),
+    "golden_lstur_con": ("check_golden", dict(case="lstur_con")),
     "nrms_random": ("check_nrms_random", {}),
     "nrms_eval_api": ("check_nrms_eval_api", {}),
     "nrms_train_mode": ("check_nrms_train_mode", {}),
