@@ -228,6 +228,51 @@ int nr_element_encoder_bwd(const long long* ids, long long n, const float* dout,
                            int ldf, const void* E_bf16, int E, int lde, const void* WT_bf16, float* dW_ext,
                            float* dtable, void* stream);
 
+/* ---- reference: LSTUR UserEncoder -- pack_padded_sequence + nn.GRU, last hidden state -----------------
+ * (src/model/LSTUR/user_encoder.py:16-45).  Gate order r, z, n; user b consumes the FIRST len[b] positions of
+ * its (left-padded) history (reference quirk kept as-is); len 0 is clamped to 1 (user_encoder.py:27).
+ * ldd = round_up(D+1, 8), ldh = round_up(Hd+1, 8), ldg = round_up(3Hd, 4), ldb = round_up(3Hd+1, 8). */
+typedef struct {
+    int B, S, D, Hd;
+    const float* x;                 /* fp32 [B][S][D] clicked-news vectors with element strides below     */
+    long long x_s_b, x_s_t, x_s_c;
+    const long long* len;           /* [B] int64 (device)                                                */
+    const float* h0;                /* [B][Hd] initial hidden state (user embedding for 'ini', zeros for 'con') */
+    const void* wih_bf16;           /* [3Hd][ldd]                                                        */
+    const void* whh_bf16;           /* [3Hd][ldh]                                                        */
+    const float* bih;
+    const float* bhh;
+    /* saved for backward (caller-allocated) */
+    void* xb;                       /* bf16 [B*S][ldd]                                                   */
+    float* gi;                      /* fp32 [B*S][ldg]   input projections, rows b*S+t                    */
+    float* gh;                      /* fp32 [S][B][ldg]  recurrent projections                            */
+    float* hs;                      /* fp32 [S+1][B][Hd] hidden states                                    */
+    void* hb;                       /* bf16 [S+1][B][ldh]                                                 */
+    float* out;                     /* fp32 [B][Hd] last hidden state                                     */
+} nr_gru_fwd_args;
+int nr_gru_fwd(const nr_gru_fwd_args* a, void* stream);
+
+typedef struct {
+    int B, S, D, Hd;
+    const long long* len;
+    const void* wihT_bf16;          /* [D][ldb]  = W_ih^T                                                */
+    const void* whhT_bf16;          /* [Hd][ldb] = W_hh^T                                                */
+    const void* xb;
+    const float* gi;
+    const float* gh;
+    const float* hs;
+    const void* hb;
+    const float* dout;              /* [B][Hd]                                                           */
+    float* dWih_ext;                /* [3Hd][ldd] (+=), column D  = d(bias_ih)                            */
+    float* dWhh_ext;                /* [3Hd][ldh] (+=), column Hd = d(bias_hh)                            */
+    float* dx;                      /* [B*S][D] (=)                                                      */
+    float* dh0;                     /* [B][Hd] (=)                                                       */
+    void* workspace;
+    long long workspace_bytes;
+} nr_gru_bwd_args;
+long long nr_gru_bwd_workspace(int B, int S, int D, int Hd);
+int nr_gru_bwd(const nr_gru_bwd_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,27 @@ class CnnEncoderBwdArgs(C.Structure):
     ]
 
 
+class GruFwdArgs(C.Structure):
+    """nr_gru_fwd_args (include/newsrec_b200.h)."""
+    _fields_ = [
+        ("B", _i), ("S", _i), ("D", _i), ("Hd", _i),
+        ("x", _vp), ("x_s_b", _ll), ("x_s_t", _ll), ("x_s_c", _ll),
+        ("len", _vp), ("h0", _vp), ("wih_bf16", _vp), ("whh_bf16", _vp), ("bih", _vp), ("bhh", _vp),
+        ("xb", _vp), ("gi", _vp), ("gh", _vp), ("hs", _vp), ("hb", _vp), ("out", _vp),
+    ]
+
+
+class GruBwdArgs(C.Structure):
+    """nr_gru_bwd_args (include/newsrec_b200.h)."""
+    _fields_ = [
+        ("B", _i), ("S", _i), ("D", _i), ("Hd", _i),
+        ("len", _vp), ("wihT_bf16", _vp), ("whhT_bf16", _vp),
+        ("xb", _vp), ("gi", _vp), ("gh", _vp), ("hs", _vp), ("hb", _vp),
+        ("dout", _vp), ("dWih_ext", _vp), ("dWhh_ext", _vp), ("dx", _vp), ("dh0", _vp),
+        ("workspace", _vp), ("workspace_bytes", _ll),
+    ]
+
+
 # name -> (restype, argtypes).  Must list EVERY symbol include/newsrec_b200.h declares
 # (tests/test_abi_symbols.py cross-checks this table against the header and the built .so).
 SIGNATURES = {
@@ -101,6 +122,9 @@ SIGNATURES = {
     "nr_embedding_f32_bwd": (_i, [_vp, _ll, _vp, _i, _vp, _vp]),
     "nr_element_encoder_fwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "nr_element_encoder_bwd": (_i, [_vp, _ll, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "nr_gru_fwd": (_i, [C.POINTER(GruFwdArgs), _vp]),
+    "nr_gru_bwd_workspace": (_ll, [_i, _i, _i, _i]),
+    "nr_gru_bwd": (_i, [C.POINTER(GruBwdArgs), _vp]),
 }
 
 _lib = None

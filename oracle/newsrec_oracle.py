@@ -305,7 +305,7 @@ def gru_last_hidden(x, lengths, h0, p, prefix, c: Contract = EXACT):
     w_hh = c.operand(p[f"{prefix}.weight_hh_l0"])
     b_ih, b_hh = p[f"{prefix}.bias_ih_l0"], p[f"{prefix}.bias_hh_l0"]
     Hd = w_hh.shape[1]
-    gi_all = c.grad(F.linear(c.act(x), w_ih) + b_ih)  # (B,S,3Hd)
+    gi_all = c.grad(F.linear(c.operand(x), w_ih) + b_ih)  # (B,S,3Hd); dX = dGI.W_ih stays fp32
     h = h0
     for t in range(S):
         gh = c.grad(F.linear(c.operand(h) if c.bf16 else h, w_hh) + b_hh)
