@@ -15,8 +15,9 @@ class SlotPacker:
 
     def _stack(self, tensors, dev):
         t0 = tensors[0]
-        if t0.is_cuda:
-            return torch.stack(tensors, dim=0)
+        dev = torch.device(dev)
+        if t0.is_cuda or dev.type != "cuda":
+            return torch.stack(tensors, dim=0).to(dev)
         shape = (len(tensors),) + tuple(t0.shape)
         key = (shape, t0.dtype)
         slot = self._bufs.get(key)

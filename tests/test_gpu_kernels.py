@@ -1,0 +1,68 @@
+"""Kernel-level parity on the B200 (every call goes through the C ABI).  Tolerances are written here:
+  * integer / byte work (gather, padding layout, operand packing): bit exact;
+  * a kernel fed bf16 operands, compared with an fp64 evaluation of the SAME bf16 operands:
+      fp32 outputs <= 1e-5 norm-wise, bf16 outputs <= 3e-3 (one bf16 rounding of the result);
+  * attention / pooling cores against the oracle under the bf16 storage contract: <= 1e-3 norm-wise
+    (the north-star tolerance for activations)."""
+import pytest
+
+import gpu_checks as G
+
+pytestmark = pytest.mark.gpu
+
+
+def test_operand_prep_and_gather_are_bit_exact():
+    r = G.check_prep_and_gather()
+    for k in ("cast_pad_exact", "cast_pad_T_exact", "gather_exact", "gather_padded_exact", "bad_id_flag", "dropout_ones_col_intact"):
+        assert r[k], (k, r)
+    assert abs(r["dropout_keep_rate"] - 0.8) < 0.01, r
+    assert r["dropout_scale_err"] < 0.01, r      # kept values are x/(1-p) up to one bf16 rounding
+
+
+@pytest.mark.parametrize("kw", [dict(M=128, N=64, K=64), dict(M=300, N=900, K=300), dict(M=128 * 9 + 17, N=900, K=300),
+                                dict(M=128 * 600 + 5, N=900, K=300)])
+def test_tcgen05_linear_bf16_out(kw):
+    r = G.check_linear(**kw)
+    assert r["nan"] == 0 and r["rel"] < 3e-3, r
+
+
+def test_tcgen05_linear_fp32_out_k900():
+    r = G.check_linear(M=777, N=300, K=900, out_bf16=0)
+    assert r["nan"] == 0 and r["rel"] < 1e-5, r
+
+
+@pytest.mark.parametrize("kw", [dict(M=37, N=300, K=300, taps=3, seg=20, relu=1), dict(M=11, N=400, K=300, taps=3, seg=50, relu=1)])
+def test_tcgen05_conv3_taps(kw):
+    r = G.check_linear(**kw)
+    assert r["nan"] == 0 and r["rel"] < 3e-3, r
+
+
+@pytest.mark.parametrize("kw", [dict(Kr=64, Ma=128, Nb=64), dict(Kr=1000, Ma=900, Nb=301), dict(Kr=64 * 700 + 13, Ma=200, Nb=301),
+                                dict(Kr=900, Ma=300, Nb=301, shift=1), dict(Kr=900, Ma=400, Nb=301, shift=-1)])
+def test_tcgen05_weight_grad_gemm(kw):
+    r = G.check_gemm_tn(**kw)
+    assert r["nan"] == 0 and r["rel"] < 1e-5, r
+
+
+def test_tcgen05_matches_simt_triage_backend():
+    r = G.check_backend_agreement()
+    assert r["n_bad"] == 0 and r["tc_rerun_maxabs"] == 0.0 and r["tc_vs_ref_rel"] < 1e-5, r
+
+
+@pytest.mark.parametrize("kw", [dict(n_seq=7, T=20), dict(n_seq=3, T=50), dict(n_seq=2000, T=20), dict(n_seq=5, T=16, heads=30, dk=10),
+                                dict(n_seq=5, T=33, heads=20, dk=15), dict(n_seq=4, T=64, heads=10, dk=30), dict(n_seq=9, T=7, heads=12, dk=25)])
+def test_attention_core(kw):
+    r = G.check_mhsa_core(**kw)
+    assert r["ones_col"] and r["fwd_rel"] < 1e-3 and r["bwd_rel"] < 1e-3, r
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(N=9, S=50), dict(N=50, S=4, D=400)])
+def test_additive_attention(kw):
+    r = G.check_additive(**kw)
+    assert r["fwd_rel"] < 1e-5, r
+    assert r["dx_rel"] < 3e-3 and r["dW_rel"] < 1e-3 and r["db_rel"] < 1e-3 and r["dq_rel"] < 1e-4, r
+
+
+def test_dot_product_click_predictor():
+    r = G.check_dot_score()
+    assert r["fwd_rel"] < 1e-6 and r["dc_rel"] < 1e-6 and r["du_rel"] < 1e-6, r
