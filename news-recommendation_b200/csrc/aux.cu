@@ -81,50 +81,51 @@ __device__ __forceinline__ float drop_mult(uint64_t seed, uint32_t thresh, float
     return (((bits >> (16 * (col & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
 }
 
+// one thread = one 16-byte chunk of one token row: consecutive threads copy consecutive chunks (coalesced);
+// dropout draws ONE counter hash per 4 aligned columns (two per chunk)
 __global__ void gather_rows_kernel(const long long* __restrict__ ids, long long n_tok, int T,
                                    const uint4* __restrict__ table, int V, int D, int ld, uint4* __restrict__ X,
                                    int padded, float p, uint64_t seed, int* bad_flag) {
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const int chunks = ld >> 3;  // 16-byte chunks per row
     const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-    for (long long tok = warp0; tok < n_tok; tok += nwarps) {
-        long long id = ids[tok];
+    const long long total = n_tok * chunks;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long tok = i / chunks;
+        const int c = static_cast<int>(i - tok * chunks);
+        long long id = __ldg(ids + tok);
         if (id < 0 || id >= V) {
-            if (lane == 0) atomicExch(bad_flag, 1);
+            if (c == 0) atomicExch(bad_flag, 1);
             id = 0;
         }
         const long long seg = tok / T;
         const int t = static_cast<int>(tok - seg * T);
         const long long xr = padded ? seg * (T + 2) + 1 + t : tok;
-        const uint4* src = table + id * chunks;
-        uint4* dst = X + xr * chunks;
-        for (int c = lane; c < chunks; c += 32) {
-            uint4 u = __ldg(src + c);
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-            const int col = c * 8;
-            if (p > 0.f) {
+        uint4 u = __ldg(table + id * chunks + c);
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        const int col = c * 8;
+        if (p > 0.f) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float2 f = unpack_bf16x2(w[j]);
-                    f.x *= drop_mult(seed, thresh, scale, xr, ld, col + 2 * j);
-                    f.y *= drop_mult(seed, thresh, scale, xr, ld, col + 2 * j + 1);
-                    w[j] = pack_bf16x2(f.x, f.y);
-                }
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(xr) * ld + col + 4 * h) >> 2);
+                float2 f0 = unpack_bf16x2(w[2 * h]), f1 = unpack_bf16x2(w[2 * h + 1]);
+                f0.x *= ((bits & 0xffffu) >= thresh) ? scale : 0.f;
+                f0.y *= (((bits >> 16) & 0xffffu) >= thresh) ? scale : 0.f;
+                f1.x *= (((bits >> 32) & 0xffffu) >= thresh) ? scale : 0.f;
+                f1.y *= (((bits >> 48) & 0xffffu) >= thresh) ? scale : 0.f;
+                w[2 * h] = pack_bf16x2(f0.x, f0.y);
+                w[2 * h + 1] = pack_bf16x2(f1.x, f1.y);
             }
-            if (D >= col && D < col + 8) {  // ones column, zeros behind it
-                __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(w);
-                for (int j = D - col; j < 8; ++j) e[j] = __float2bfloat16_rn(j == D - col ? 1.0f : 0.f);
-            }
-            dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        if (D >= col && D < col + 8) {  // ones column, zeros behind it
+            __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(w);
+            for (int j = D - col; j < 8; ++j) e[j] = __float2bfloat16_rn(j == D - col ? 1.0f : 0.f);
+        }
+        X[xr * chunks + c] = make_uint4(w[0], w[1], w[2], w[3]);
         if (padded) {
-            if (t == 0)
-                for (int c = lane; c < chunks; c += 32) X[(xr - 1) * chunks + c] = make_uint4(0, 0, 0, 0);
-            if (t == T - 1)
-                for (int c = lane; c < chunks; c += 32) X[(xr + 1) * chunks + c] = make_uint4(0, 0, 0, 0);
+            if (t == 0) X[(xr - 1) * chunks + c] = make_uint4(0, 0, 0, 0);
+            if (t == T - 1) X[(xr + 1) * chunks + c] = make_uint4(0, 0, 0, 0);
         }
     }
 }
@@ -150,16 +151,21 @@ __global__ void __launch_bounds__(128) pool_dscore_kernel(const __nv_bfloat16* _
                                                           float* __restrict__ dscore) {
     __shared__ float s_dw[128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = D >> 3;  // whole 16-byte chunks of the row; the tail (D % 8) is handled element-wise
     for (long long seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
         const float* dob = dout + seg * ldo;
         for (int t = warp; t < seg_len; t += 4) {
             const __nv_bfloat16* xr = X + (seg * seg_len + t) * static_cast<long long>(lda);
             float a = 0.f;
-            for (int c = 2 * lane; c < D; c += 64) {
-                const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
-                a = fmaf(f.x, dob[c], a);
-                a = fmaf(f.y, dob[c + 1], a);
+            for (int c = lane; c < chunks; c += 32) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + c);
+                const float4 d0 = *reinterpret_cast<const float4*>(dob + c * 8);
+                const float4 d1 = *reinterpret_cast<const float4*>(dob + c * 8 + 4);
+                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+                a = fmaf(f0.x, d0.x, a); a = fmaf(f0.y, d0.y, a); a = fmaf(f1.x, d0.z, a); a = fmaf(f1.y, d0.w, a);
+                a = fmaf(f2.x, d1.x, a); a = fmaf(f2.y, d1.y, a); a = fmaf(f3.x, d1.z, a); a = fmaf(f3.y, d1.w, a);
             }
+            for (int c = chunks * 8 + lane; c < D; c += 32) a = fmaf(__bfloat162float(xr[c]), dob[c], a);
             a = warp_sum(a);
             if (lane == 0) s_dw[t] = a;
         }
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(128) pool_dscore_kernel(const __nv_bfloat16* _
 int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, const float* w, const float* dout, int ldo,
                 float* dscore, cudaStream_t stream) {
     if (n_seg == 0) return 0;
-    NR_REQUIRE(seg_len <= 128 && D % 2 == 0, "pool_dscore: seg_len=%d D=%d", seg_len, D);
+    NR_REQUIRE(seg_len <= 128 && D % 4 == 0 && ldo % 4 == 0 && lda % 8 == 0, "pool_dscore: seg_len=%d D=%d ldo=%d lda=%d", seg_len, D, ldo, lda);
     const int blocks = static_cast<int>(std::min<long long>(n_seg, 148 * 16));
     ProfScope ps("pool_dscore", static_cast<int>(n_seg), seg_len, D, stream);
     pool_dscore_kernel<<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(X), lda, D, n_seg, seg_len, w, dout,

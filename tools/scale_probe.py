@@ -24,7 +24,7 @@ dev = torch.device("cuda", 0)
 model = NRMS(cfgmod.NRMSConfig).to(dev)
 model.train()
 for B in [int(x) for x in sys.argv[1:]] or [16, 64, 256, 512]:
-    faulthandler.dump_traceback_later(40, exit=True)
+    faulthandler.dump_traceback_later(int(__import__("os").environ.get("PROBE_WATCHDOG", "40")), exit=True)
     cand, clicked = bench.synth_slots(B, 7, device=dev)
     label = torch.zeros(B, dtype=torch.long, device=dev)
     for it in range(2):
