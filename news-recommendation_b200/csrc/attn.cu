@@ -9,6 +9,7 @@
 // bf16 storage contract (mirrored by the oracle): A and dS are rounded to bf16 as tensor-core operands,
 // all softmax arithmetic is fp32.
 #include <algorithm>
+#include <cstdlib>
 
 #include "nr_common.cuh"
 #include "nr_ops.h"
@@ -163,6 +164,78 @@ __device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloa
         else *dst = *src;
     }
 }
+// Per-lane copy plan: the (row, column) of every piece a lane moves is the same for every task, so the
+// offsets are computed ONCE per kernel (ncu: per-piece index arithmetic was 30 % of all instructions).
+constexpr int kMaxP = 4;  // pieces per lane covered by the plan (T * pieces_per_row <= 128); larger tiles use the loops
+struct PieceMap {
+    int n;            // pieces of this lane
+    int src[kMaxP];   // element offset in the global matrix:  r * ld + c
+    int dst[kMaxP];   // element offset in the tile:            r * kPitch + c
+    int row[kMaxP];
+    int col[kMaxP];
+};
+__device__ __forceinline__ bool make_piece_map(PieceMap& m, int T, int dk, int piece, int ld, int lane) {
+    const int epp = piece >> 1, ppr = dk / epp, n = T * ppr;
+    m.n = 0;
+    if (piece < 4 || n > kMaxP * 32) return false;
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k) {
+        const int i = lane + 32 * k;
+        const int r = i / ppr, c = (i - r * ppr) * epp;
+        m.src[k] = r * ld + c;
+        m.dst[k] = r * kPitch + c;
+        m.row[k] = r;
+        m.col[k] = c;
+        if (i < n) m.n = k + 1;
+    }
+    return true;
+}
+__device__ __forceinline__ void tile_load_map(uint32_t tile_saddr, const __nv_bfloat16* g, const PieceMap& m, int piece) {
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k) {
+        if (k < m.n) {
+            if (piece == 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_saddr + 2 * m.dst[k]), "l"(g + m.src[k]) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_saddr + 2 * m.dst[k]), "l"(g + m.src[k]) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void tile_store_map(const __nv_bfloat16* tile, __nv_bfloat16* g, const PieceMap& m, int piece) {
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k) {
+        if (k < m.n) {
+            if (piece == 8) *reinterpret_cast<uint2*>(g + m.src[k]) = *reinterpret_cast<const uint2*>(tile + m.dst[k]);
+            else *reinterpret_cast<uint32_t*>(g + m.src[k]) = *reinterpret_cast<const uint32_t*>(tile + m.dst[k]);
+        }
+    }
+}
+// context tile -> global with dropout (one counter hash per 4 aligned columns), offsets from the plan
+__device__ __forceinline__ void tile_store_dropout_map(const __nv_bfloat16* tile, __nv_bfloat16* g, const PieceMap& m, int piece, int ld,
+                                                       long long row0, int col0, uint64_t seed, uint32_t thresh, float scale) {
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k) {
+        if (k < m.n) {
+            const int gc = col0 + m.col[k];
+            const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row0 + m.row[k]) * ld + gc) >> 2);
+            if (piece == 8) {
+                const uint2 u = *reinterpret_cast<const uint2*>(tile + m.dst[k]);
+                float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+                a.x *= ((bits & 0xffffu) >= thresh) ? scale : 0.f;
+                a.y *= (((bits >> 16) & 0xffffu) >= thresh) ? scale : 0.f;
+                b.x *= (((bits >> 32) & 0xffffu) >= thresh) ? scale : 0.f;
+                b.y *= (((bits >> 48) & 0xffffu) >= thresh) ? scale : 0.f;
+                *reinterpret_cast<uint2*>(g + m.src[k]) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y));
+            } else {
+                float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(tile + m.dst[k]));
+                a.x *= (((bits >> (16 * (gc & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
+                a.y *= (((bits >> (16 * ((gc + 1) & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
+                *reinterpret_cast<uint32_t*>(g + m.src[k]) = pack_bf16x2(a.x, a.y);
+            }
+        }
+    }
+}
+
 // context tile -> global with the dropout mask applied on the fly (one counter hash per 4 aligned columns)
 __device__ __forceinline__ void tile_store_dropout(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane,
                                                    long long row0, int col0, uint64_t seed, uint32_t thresh, float scale) {
@@ -205,8 +278,8 @@ __host__ __device__ inline int piece_bytes(int dk, int ld_a, int ld_b, int d) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int TP, int KSD, int NTD, int STG, int WPS>
-__global__ void __launch_bounds__(WPS * 32) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST>
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
                                                                   int T, int heads, int dk, __nv_bfloat16* __restrict__ ctx,
                                                                   int ld_ctx, float p, uint64_t seed) {
     constexpr int NTJ = TP / 8, MT = TP / 16;
@@ -224,19 +297,33 @@ __global__ void __launch_bounds__(WPS * 32) mhsa_mma_fwd_kernel(const __nv_bfloa
     const float dscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     const int ntj = (T + 7) >> 3;
     const int piece = piece_bytes(dk, ld, ld_ctx, d);
-    const long long n_tasks = n_seq * heads;
-    const long long W = static_cast<long long>(gridDim.x) * WPS;
-    const long long gw = static_cast<long long>(blockIdx.x) * WPS + warp;
+    const int n_tasks = static_cast<int>(n_seq * heads);  // < 2^31, checked by the launcher
+    const int W = gridDim.x * WPS;
+    const int gw = blockIdx.x * WPS + warp;
+    PieceMap lmap, smap;
+    if (FAST) {
+        make_piece_map(lmap, T, dk, piece, ld, lane);
+        make_piece_map(smap, T, dk, piece, ld_ctx, lane);
+    }
+    constexpr bool fast = FAST;
+    const uint32_t wbase_s = smem_u32(wbase);
 
-    auto prefetch = [&](long long task, int stage) {
+    auto prefetch = [&](int task, int stage) {
         if (task < n_tasks) {
-            const long long seq = task / heads;
-            const int h = static_cast<int>(task - seq * heads);
-            const __nv_bfloat16* src = qkv + seq * T * static_cast<long long>(ld) + h * dk;
-            __nv_bfloat16* t0 = wbase + stage * 3 * TILE;
-            tile_load(t0, src, ld, T, dk, piece, lane);
-            tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
-            tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
+            const int seq = task / heads;
+            const int h = task - seq * heads;
+            const __nv_bfloat16* src = qkv + static_cast<long long>(seq) * T * ld + h * dk;
+            if constexpr (fast) {
+                const uint32_t t0s = wbase_s + 2 * stage * 3 * TILE;
+                tile_load_map(t0s, src, lmap, piece);
+                tile_load_map(t0s + 2 * TILE, src + d, lmap, piece);
+                tile_load_map(t0s + 4 * TILE, src + 2 * d, lmap, piece);
+            } else {
+                __nv_bfloat16* t0 = wbase + stage * 3 * TILE;
+                tile_load(t0, src, ld, T, dk, piece, lane);
+                tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
+                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
+            }
         }
         cp_commit();
     };
@@ -244,13 +331,13 @@ __global__ void __launch_bounds__(WPS * 32) mhsa_mma_fwd_kernel(const __nv_bfloa
     for (int s0 = 0; s0 < STG - 1; ++s0) prefetch(gw + s0 * W, s0);
 
     int stage = 0;
-    for (long long task = gw; task < n_tasks; task += W) {
+    for (int task = gw; task < n_tasks; task += W) {
         cp_wait<STG - 2>();
         __syncwarp();
         // the stage consumed in the previous iteration is free again: refill it before computing this task
         prefetch(task + (STG - 1) * W, (stage + STG - 1) % STG);
         const long long seq = task / heads;
-        const int h = static_cast<int>(task - seq * heads);
+        const int h = task - static_cast<int>(seq) * heads;
         __nv_bfloat16* q = wbase + stage * 3 * TILE;
         const __nv_bfloat16* k = q + TILE;
         const __nv_bfloat16* v = q + 2 * TILE;
@@ -313,8 +400,14 @@ __global__ void __launch_bounds__(WPS * 32) mhsa_mma_fwd_kernel(const __nv_bfloa
         }
         __syncwarp();
         __nv_bfloat16* out = ctx + seq * T * static_cast<long long>(ld_ctx);
-        if (p > 0.f) tile_store_dropout(q, out + h * dk, ld_ctx, T, dk, piece, lane, seq * T, h * dk, seed, thresh, dscale);
-        else tile_store(q, out + h * dk, ld_ctx, T, dk, piece, lane);
+        if constexpr (fast) {
+            if (p > 0.f) tile_store_dropout_map(q, out + h * dk, smap, piece, ld_ctx, seq * T, h * dk, seed, thresh, dscale);
+            else tile_store_map(q, out + h * dk, smap, piece);
+        } else if (p > 0.f) {
+            tile_store_dropout(q, out + h * dk, ld_ctx, T, dk, piece, lane, seq * T, h * dk, seed, thresh, dscale);
+        } else {
+            tile_store(q, out + h * dk, ld_ctx, T, dk, piece, lane);
+        }
         if (h == 0) {  // ones column + zero tail of the padded context rows
             for (int i = lane; i < T * (ld_ctx - d); i += 32) {
                 const int r = i / (ld_ctx - d), c = i - r * (ld_ctx - d);
@@ -330,8 +423,8 @@ __global__ void __launch_bounds__(WPS * 32) mhsa_mma_fwd_kernel(const __nv_bfloa
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int TP, int KSD, int NTD, int STG, int WPS>
-__global__ void __launch_bounds__(WPS * 32) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST>
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
                                                                   const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
                                                                   long long n_seq, int T, int heads, int dk,
                                                                   __nv_bfloat16* __restrict__ dqkv, int ld_d) {
@@ -350,20 +443,37 @@ __global__ void __launch_bounds__(WPS * 32) mhsa_mma_bwd_kernel(const __nv_bfloa
     const float sc = rs * 1.4426950408889634f;
     const int ntj = (T + 7) >> 3;
     const int piece = piece_bytes(dk, ld, ld_dctx, d) == 8 && (ld_d % 4) == 0 ? 8 : (piece_bytes(dk, ld, ld_dctx, d) >= 4 && (ld_d % 2) == 0 ? 4 : 2);
-    const long long n_tasks = n_seq * heads;
-    const long long W = static_cast<long long>(gridDim.x) * WPS;
-    const long long gw = static_cast<long long>(blockIdx.x) * WPS + warp;
+    const int n_tasks = static_cast<int>(n_seq * heads);
+    const int W = gridDim.x * WPS;
+    const int gw = blockIdx.x * WPS + warp;
+    PieceMap lmap, gmap, smap;
+    if (FAST) {
+        make_piece_map(lmap, T, dk, piece, ld, lane);
+        make_piece_map(gmap, T, dk, piece, ld_dctx, lane);
+        make_piece_map(smap, T, dk, piece, ld_d, lane);
+    }
+    constexpr bool fast = FAST;
+    const uint32_t wbase_s = smem_u32(wbase);
 
-    auto prefetch = [&](long long task, int stage) {
+    auto prefetch = [&](int task, int stage) {
         if (task < n_tasks) {
-            const long long seq = task / heads;
-            const int h = static_cast<int>(task - seq * heads);
-            const __nv_bfloat16* src = qkv + seq * T * static_cast<long long>(ld) + h * dk;
-            __nv_bfloat16* t0 = wbase + stage * 4 * TILE;
-            tile_load(t0, src, ld, T, dk, piece, lane);
-            tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
-            tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
-            tile_load(t0 + 3 * TILE, dctx + seq * T * static_cast<long long>(ld_dctx) + h * dk, ld_dctx, T, dk, piece, lane);
+            const int seq = task / heads;
+            const int h = task - seq * heads;
+            const __nv_bfloat16* src = qkv + static_cast<long long>(seq) * T * ld + h * dk;
+            const __nv_bfloat16* gsrc = dctx + static_cast<long long>(seq) * T * ld_dctx + h * dk;
+            if constexpr (fast) {
+                const uint32_t t0s = wbase_s + 2 * stage * 4 * TILE;
+                tile_load_map(t0s, src, lmap, piece);
+                tile_load_map(t0s + 2 * TILE, src + d, lmap, piece);
+                tile_load_map(t0s + 4 * TILE, src + 2 * d, lmap, piece);
+                tile_load_map(t0s + 6 * TILE, gsrc, gmap, piece);
+            } else {
+                __nv_bfloat16* t0 = wbase + stage * 4 * TILE;
+                tile_load(t0, src, ld, T, dk, piece, lane);
+                tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
+                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
+                tile_load(t0 + 3 * TILE, gsrc, ld_dctx, T, dk, piece, lane);
+            }
         }
         cp_commit();
     };
@@ -371,13 +481,13 @@ __global__ void __launch_bounds__(WPS * 32) mhsa_mma_bwd_kernel(const __nv_bfloa
     for (int s0 = 0; s0 < STG - 1; ++s0) prefetch(gw + s0 * W, s0);
 
     int stage = 0;
-    for (long long task = gw; task < n_tasks; task += W) {
+    for (int task = gw; task < n_tasks; task += W) {
         cp_wait<STG - 2>();
         __syncwarp();
         // the stage consumed in the previous iteration is free again: refill it before computing this task
         prefetch(task + (STG - 1) * W, (stage + STG - 1) % STG);
         const long long seq = task / heads;
-        const int h = static_cast<int>(task - seq * heads);
+        const int h = task - static_cast<int>(seq) * heads;
         const __nv_bfloat16* q = wbase + stage * 4 * TILE;
         __nv_bfloat16* k = wbase + stage * 4 * TILE + TILE;
         __nv_bfloat16* v = k + TILE;
@@ -517,18 +627,24 @@ __global__ void __launch_bounds__(WPS * 32) mhsa_mma_bwd_kernel(const __nv_bfloa
             }
         }
         __syncwarp();
-        tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, lane);
-        tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, lane);
+        if constexpr (fast) {
+            tile_store_map(k, gout + d + h * dk, smap, piece);
+            tile_store_map(v, gout + 2 * d + h * dk, smap, piece);
+        } else {
+            tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, lane);
+            tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, lane);
+        }
         __syncwarp();
         stage = (stage + 1) % STG;
     }
     cp_wait<0>();
 }
 
-template <int TP, int KSD, int NTD, int STG, int WPS>
-int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST>
+int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     const long long tasks = n_seq * heads;
+    NR_REQUIRE(tasks < (1ll << 31), "mhsa: too many (sequence, head) tasks");
     const size_t tile = sizeof(__nv_bfloat16) * T * kPitch;
     const size_t smem_f = WPS * STG * 3 * tile + sizeof(__nv_bfloat16) * (TP - T) * kPitch;
     const size_t smem_b = WPS * (STG * 4 * tile + sizeof(__nv_bfloat16) * 2 * TP * (TP + 8));
@@ -538,13 +654,13 @@ int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int 
     const int grid = static_cast<int>(std::min<long long>(ceil_div(static_cast<int>(std::min<long long>(tasks, 1 << 30)), WPS),
                                                           static_cast<long long>(num_sms()) * per_sm));
     if (!bwd) {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out, drop.p,
                                                                              drop.seed);
     } else {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
                                                                              static_cast<const __nv_bfloat16*>(dctx), ld_dctx, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out);
     }
@@ -553,6 +669,20 @@ int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int 
     return 0;
 }
 
+
+// the per-lane copy plan covers tiles of up to 128 pieces of >= 4 bytes; anything else takes the generic loops
+template <int TP, int KSD, int NTD, int STG, int WPS>
+int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+                   void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
+    const int d = heads * dk;
+    int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, d);
+    if (bwd) piece = (piece == 8 && (ld_out % 4) == 0) ? 8 : ((piece >= 4 && (ld_out % 2) == 0) ? 4 : 2);
+    static const bool force_loops = getenv("NEWSREC_ATTN_LOOPS") != nullptr;  // tuning switch (tools/kbench.py)
+    const bool fast = !force_loops && piece >= 4 && T * (dk / (piece / 2)) <= kMaxP * 32;
+    if (fast)
+        return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, false>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+}
 
 template <int TP, int KSD, int NTD>
 int launch_mma(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
