@@ -98,7 +98,7 @@ typedef struct {
     int heads;                /* num_attention_heads, d % heads == 0                                */
     int q;                    /* query_vector_dim                                                   */
     int ldx;                  /* pitch of X / C / weight operands: multiple of 8, >= d+1            */
-    int ld3;                  /* pitch of QKV: multiple of 8, >= 3d                                 */
+    int ld3;                  /* pitch of QKV: round_up(3d, 16) (32-byte rows for STG.256 epilogues) */
     /* input: ids+table (news encoder) or dense (user encoder) */
     const long long* ids;     /* [n_seq*T] or NULL                                                  */
     const void* table_bf16;   /* [V][ldx]                                                           */
@@ -125,7 +125,7 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream);
 
 typedef struct {
     long long n_seq;
-    int T, d, heads, q, ldx, ld3, ldq;   /* ldq: pitch of dPre / WaT, multiple of 8, >= q               */
+    int T, d, heads, q, ldx, ld3, ldq;   /* ldq: pitch of dPre / WaT = round_up(q, 16)                   */
     const long long* ids;                /* NULL for the dense (user) variant                            */
     int V;
     const void* wqkvT_bf16;              /* [d][ld3]  = (W_Q|W_K|W_V)^T                                  */

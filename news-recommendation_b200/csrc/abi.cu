@@ -79,7 +79,7 @@ int nr_additive_attention_fwd(const void* X, long long n_seg, int seg_len, int D
 static inline long long align256(long long x) { return (x + 255) & ~255ll; }
 long long nr_additive_attention_bwd_workspace(long long n_seg, int seg_len, int q) {
     const long long rows = n_seg * seg_len;
-    return align256(rows * 4) + align256(rows * ((q + 7) & ~7) * 2) + 256;
+    return align256(rows * 4) + align256(rows * ((q + 15) & ~15) * 2) + 256;
 }
 int nr_additive_attention_bwd(const void* X, long long n_seg, int seg_len, int D, int ldx, const void* Wa,
                               const void* WaT, int q, int ldw, int ldwT, const float* ba, const float* qv, const float* w,
@@ -92,7 +92,7 @@ int nr_additive_attention_bwd(const void* X, long long n_seg, int seg_len, int D
     const long long rows = n_seg * seg_len;
     NR_REQUIRE(rows < (1ll << 31), "nr_additive_attention_bwd: too many rows");
     const int M = static_cast<int>(rows);
-    const int ldq = (q + 7) & ~7;
+    const int ldq = (q + 15) & ~15;
     char* ws = static_cast<char*>(workspace);
     float* dscore = reinterpret_cast<float*>(ws);
     void* dpre = ws + align256(rows * 4);
@@ -159,7 +159,7 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
 
 long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q) {
     const long long rows = n_seq * T;
-    const long long ldx = (d + 1 + 7) & ~7, ld3 = (3 * d + 7) & ~7, ldq = (q + 7) & ~7;
+    const long long ldx = (d + 1 + 7) & ~7, ld3 = (3 * d + 15) & ~15, ldq = (q + 15) & ~15;
     return align256(rows * 4) + align256(rows * ldq * 2) + align256(rows * ldx * 2) + align256(rows * ld3 * 2) + 256;
 }
 
@@ -167,8 +167,8 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     NR_REQUIRE(a != nullptr, "nr_mhsa_encoder_bwd: null args");
     NR_PROPAGATE(check_mhsa_shape(a->n_seq, a->T, a->d, a->heads, a->q, a->ldx, a->ld3));
     NR_REQUIRE(a->ldq % 8 == 0 && a->ldq >= a->q, "nr_mhsa_encoder_bwd: ldq=%d", a->ldq);
-    NR_REQUIRE(a->ldx == ((a->d + 8) & ~7) && a->ld3 == ((3 * a->d + 7) & ~7) && a->ldq == ((a->q + 7) & ~7),
-               "nr_mhsa_encoder_bwd: pitches must be the canonical round-up-to-8 values");
+    NR_REQUIRE(a->ldx == ((a->d + 8) & ~7) && a->ld3 == ((3 * a->d + 15) & ~15) && a->ldq == ((a->q + 15) & ~15),
+               "nr_mhsa_encoder_bwd: pitches must be canonical: ldx=round_up(d+1,8), ld3=round_up(3d,16), ldq=round_up(q,16)");
     NR_REQUIRE(a->wqkvT_bf16 && a->wa_bf16 && a->waT_bf16 && a->ba && a->qv && a->X_bf16 && a->QKV_bf16 && a->C_bf16 &&
                    a->w && a->dout && a->dWqkv_ext && a->dWa_ext && a->dqv && a->workspace,
                "nr_mhsa_encoder_bwd: null operand");

@@ -13,6 +13,7 @@ static const RowMapCfg kIdentity = {0, 0, 0, 0, 0};
 static const DropoutCfg kNoDrop = {0.f, 0};
 static inline long long align256(long long x) { return (x + 255) & ~255ll; }
 static inline int ru8(int x) { return (x + 7) & ~7; }
+static inline int ru16(int x) { return (x + 15) & ~15; }
 
 static int check_cnn_shape(long long n_seq, int T, int d, int F, int q, int ldx, int ldf) {
     NR_REQUIRE(n_seq >= 0 && T >= 1 && T <= 126 && d >= 8 && F >= 8 && q >= 1 && q <= 256,
@@ -53,13 +54,13 @@ int nr_cnn_encoder_fwd(const nr_cnn_encoder_fwd_args* a, void* stream) {
 
 long long nr_cnn_encoder_bwd_workspace(long long n_seq, int T, int F, int q) {
     const long long rows = n_seq * T, rows_p = n_seq * (T + 2);
-    return align256(rows * 4) + align256(rows * ru8(q) * 2) + align256(rows_p * ru8(F + 1) * 2) + 256;
+    return align256(rows * 4) + align256(rows * ru16(q) * 2) + align256(rows_p * ru8(F + 1) * 2) + 256;
 }
 
 int nr_cnn_encoder_bwd(const nr_cnn_encoder_bwd_args* a, void* stream) {
     NR_REQUIRE(a != nullptr, "nr_cnn_encoder_bwd: null args");
     NR_PROPAGATE(check_cnn_shape(a->n_seq, a->T, a->d, a->F, a->q, a->ldx, a->ldf));
-    NR_REQUIRE(a->ldq == ru8(a->q), "nr_cnn_encoder_bwd: ldq=%d", a->ldq);
+    NR_REQUIRE(a->ldq == ru16(a->q), "nr_cnn_encoder_bwd: ldq=%d (must be round_up(q, 16))", a->ldq);
     NR_REQUIRE(a->ids && a->wconvT_bf16 && a->wa_bf16 && a->waT_bf16 && a->ba && a->qv && a->Xp_bf16 && a->Y_bf16 && a->w &&
                    a->dout && a->dWconv_ext && a->dWa_ext && a->dqv && a->demb && a->workspace, "nr_cnn_encoder_bwd: null operand");
     NR_REQUIRE(a->workspace_bytes >= nr_cnn_encoder_bwd_workspace(a->n_seq, a->T, a->F, a->q), "nr_cnn_encoder_bwd: workspace too small");

@@ -196,7 +196,7 @@ int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B,
     int slices = 1;
     for (;; ++slices) {
         NR_REQUIRE(slices <= 64, "plan_gemm_nt: cannot fit weight slice (N=%d K=%d taps=%d)", N, K, taps);
-        p.n_stride = round_up(ceil_div(N, slices), 8);
+        p.n_stride = round_up(ceil_div(N, slices), 16);  // 32-byte aligned slice starts (STG.256 epilogues)
         p.n_box = round_up(std::min(p.n_stride, N), 16);
         if (p.n_box > 256) continue;
         const long bbytes = static_cast<long>(taps) * p.k_chunks * p.n_box * 128;
@@ -243,7 +243,7 @@ __global__ void gemm_nt_simt_acc_kernel(const __nv_bfloat16* A, int lda, const _
 // ------------------------------------------------------------------------------------------------
 // gemm_tn kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTNParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -411,7 +411,7 @@ int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, in
         attr_set = true;
     }
     const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + 512;
-    gemm_tn_kernel<<<p.m_tiles * k_slices, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+    gemm_tn_kernel<<<p.m_tiles * k_slices, kTnThreads, smem, stream>>>(tmA, tmB, p);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -522,7 +522,7 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
     e.relu_ld = relu_ld;
     e.M = M;
     e.rows_per_tile = kTileM;
-    NR_REQUIRE(seg_len >= 2, "pool_dinput: seg_len=%d (staging buffer holds 80 segments per tile)", seg_len);
+    NR_REQUIRE(seg_len >= 4, "pool_dinput: seg_len=%d (each column half stages up to 40 segments per tile)", seg_len);
     g_launches += debug_simt_gemm() ? 2 : 1;
     ProfScope ps("gemm_pool_dinput", M, D, q, stream);
     return launch_gemm_nt(plan, e, dpre, ld_dpre, WaT, ldwT, stream);

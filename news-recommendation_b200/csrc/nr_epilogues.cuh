@@ -1,8 +1,11 @@
-// Fused epilogue functors for gemm_nt.  Each epilogue thread owns one accumulator row (= TMEM lane)
-// and walks its columns in chunks of 32 fp32 values.  Contract for every functor:
-//   * all 128 threads call acc.load32() the same number of times (tcgen05.ld is warp-collective)
-//   * every thread calls acc.release() exactly once per tile, after its last load32
-//   * init()/finish() bracket the CTA's whole tile loop (all 128 epilogue threads call them)
+// Fused epilogue functors for gemm_nt.  256 epilogue threads: thread (quarter, lane) owns accumulator row
+// r = 32*quarter + lane (= TMEM lane) and the two warps of a quarter ("halves") split the row's 32-column chunks
+// [ch0, ch1).  Contract for every functor:
+//   * a thread calls acc.load32() exactly once per chunk of ITS range (tcgen05.ld is warp-collective and the
+//     range is warp-uniform), and acc.release() exactly once per tile after its last load (also when the range is empty)
+//   * init()/finish() bracket the CTA's whole tile loop (all 256 epilogue threads call them)
+//   * per-slice vectors (bias, query vector, dOut rows) are staged in shared memory: with ~220 KB of smem carved out
+//     the L1 holds next to nothing and per-element global loads made the epilogue 10x the MMA time (ncu, profiles/)
 #pragma once
 #include "nr_gemm.cuh"
 
@@ -43,8 +46,29 @@ struct Dropout {
     }
 };
 
+// 16 bf16 = one full 32-byte sector per thread (STG.256, sm_100): halves the L2 write requests of the row-per-thread
+// epilogues compared with two half-sector 16-byte stores.  Needs a 32-byte aligned destination.
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* o, const float* y) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(pack_bf16x2(y[0], y[1])),
+                 "r"(pack_bf16x2(y[2], y[3])), "r"(pack_bf16x2(y[4], y[5])), "r"(pack_bf16x2(y[6], y[7])),
+                 "r"(pack_bf16x2(y[8], y[9])), "r"(pack_bf16x2(y[10], y[11])), "r"(pack_bf16x2(y[12], y[13])),
+                 "r"(pack_bf16x2(y[14], y[15]))
+                 : "memory");
+}
+__device__ __forceinline__ bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* o, const float* y, int nvalid) {
+    if (nvalid == 8) {
+        *reinterpret_cast<uint4*>(o) =
+            make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    } else {
+        for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(y[j]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // out = act(acc + bias) [* dropout]  ->  bf16 or fp32, optional row re-map, optional "ones" column
+// scratch floats: [0,256) bias of the slice
 // ------------------------------------------------------------------------------------------------
 struct EpiStore {
     void* out;
@@ -59,10 +83,8 @@ struct EpiStore {
     int ones_col;       // >=0: column set to 1.0 (bias-gradient trick for the next weight-grad GEMM); -1 off
     int ones_cols_zero_upto;  // columns (ones_col, upto) are zeroed
 
-    // The slice's bias is staged ONCE in shared memory: with ~220 KB of smem carved out the L1 holds next to
-    // nothing, and per-element global bias loads were the whole epilogue (ncu: 27k cycles per tile).
     __device__ void init(int col0, int ncols, int tid, float* scratch) const {
-        for (int i = tid; i < 256; i += 128) scratch[i] = (bias != nullptr && i < ncols) ? bias[col0 + i] : 0.f;
+        for (int i = tid; i < 256; i += kEpiThreads) scratch[i] = (bias != nullptr && i < ncols) ? bias[col0 + i] : 0.f;
         epi_bar_sync();
     }
     __device__ void finish(int, int, int, float*) const {}
@@ -72,56 +94,59 @@ struct EpiStore {
         long long orow;
         int t;
         const bool v = rm.map(c.grow, orow, t) && c.valid;
-        const int nch = (c.ncols + 31) >> 5;
-        for (int ch = 0; ch < nch; ++ch) {
+        if (c.ch0 >= c.ch1) acc.release();
+        for (int ch = c.ch0; ch < c.ch1; ++ch) {
             float x[32];
             acc.load32(ch, x);
-            if (ch == nch - 1) acc.release();
+            if (ch == c.ch1 - 1) acc.release();
             if (!v) continue;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int lc = ch * 32 + g * 8;  // column inside the slice
+            for (int g = 0; g < 2; ++g) {
+                const int lc = ch * 32 + g * 16;  // column inside the slice
                 if (lc >= c.ncols) break;
                 const int col = c.col0 + lc;
-                float y[8];
-                const float4 b0 = *reinterpret_cast<const float4*>(c.scratch + lc);
-                const float4 b1 = *reinterpret_cast<const float4*>(c.scratch + lc + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float y[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float val = x[g * 8 + j] + bb[j];
-                    if (relu) val = fmaxf(val, 0.f);
-                    y[j] = val;
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(c.scratch + lc + j);
+                    y[j] = x[g * 16 + j] + b4.x;
+                    y[j + 1] = x[g * 16 + j + 1] + b4.y;
+                    y[j + 2] = x[g * 16 + j + 2] + b4.z;
+                    y[j + 3] = x[g * 16 + j + 3] + b4.w;
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
                 }
                 if (drop.p > 0.f) {
-                    float m[8];
-                    drop.mask4(orow, ld, col, m);
-                    drop.mask4(orow, ld, col + 4, m + 4);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) y[j] *= m[j];
+                    for (int j = 0; j < 16; j += 4) {
+                        float m[4];
+                        drop.mask4(orow, ld, col + j, m);
+                        y[j] *= m[0]; y[j + 1] *= m[1]; y[j + 2] *= m[2]; y[j + 3] *= m[3];
+                    }
                 }
-                const int nvalid = min(8, min(c.ncols - lc, N - col));
+                const int nvalid = min(16, min(c.ncols - lc, N - col));
                 if (out_bf16) {
                     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld + col;
-                    if (nvalid == 8) {
-                        uint4 u = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
-                                             pack_bf16x2(y[6], y[7]));
-                        *reinterpret_cast<uint4*>(o) = u;
+                    if (nvalid == 16 && aligned32(o)) {
+                        store_bf16x16(o, y);
                     } else {
-                        for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(y[j]);
+                        store_bf16x8(o, y, min(nvalid, 8));
+                        if (nvalid > 8) store_bf16x8(o + 8, y + 8, nvalid - 8);
                     }
                 } else {
                     float* o = static_cast<float*>(out) + orow * ld + col;
-                    if (nvalid == 8) {
-                        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-                        *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                    if (nvalid == 16) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
                     } else {
                         for (int j = 0; j < nvalid; ++j) o[j] = y[j];
                     }
                 }
             }
         }
-        if (v && c.col0 == 0) {
+        if (v && c.col0 == 0 && c.half == 0) {
             if (ones_col >= 0 && out_bf16) {
                 __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld;
                 o[ones_col] = __float2bfloat16_rn(1.0f);
@@ -140,6 +165,7 @@ struct EpiStore {
 // Additive-attention pooling (reference additive.py:35-53) fused behind  pre = X.Wa^T:
 //   score_r = sum_c tanh(pre_rc + ba_c) * qv_c ; w = softmax over the segment ; out_s = sum_r w_r X_r
 // Requires n_slices == 1 and rows_per_tile = (segments per tile) * seg_len.
+// scratch floats: [0,256) partial scores (half*128 + row) | [256,384) weights | [512,768) bias | [768,1024) query
 // ------------------------------------------------------------------------------------------------
 struct EpiPool {
     const float* bias;
@@ -154,11 +180,10 @@ struct EpiPool {
     int ldo;
     float* w_out; // [rows] fp32 softmax weights (saved for backward); may be null
 
-    // scratch: [0,128) scores | [128,256) weights | [256,512) bias | [512,768) query vector
     __device__ void init(int col0, int ncols, int tid, float* scratch) const {
-        for (int i = tid; i < 256; i += 128) {
-            scratch[256 + i] = i < ncols ? bias[col0 + i] : 0.f;
-            scratch[512 + i] = i < ncols ? qv[col0 + i] : 0.f;
+        for (int i = tid; i < 256; i += kEpiThreads) {
+            scratch[512 + i] = i < ncols ? bias[col0 + i] : 0.f;
+            scratch[768 + i] = i < ncols ? qv[col0 + i] : 0.f;
         }
         epi_bar_sync();
     }
@@ -167,13 +192,13 @@ struct EpiPool {
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         float score = 0.f;
-        const int nch = (c.ncols + 31) >> 5;
-        for (int ch = 0; ch < nch; ++ch) {
+        if (c.ch0 >= c.ch1) acc.release();
+        for (int ch = c.ch0; ch < c.ch1; ++ch) {
             float x[32];
             acc.load32(ch, x);
-            if (ch == nch - 1) acc.release();
-            const float* sb = c.scratch + 256 + ch * 32;
-            const float* sq = c.scratch + 512 + ch * 32;
+            if (ch == c.ch1 - 1) acc.release();
+            const float* sb = c.scratch + 512 + ch * 32;
+            const float* sq = c.scratch + 768 + ch * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
@@ -184,21 +209,24 @@ struct EpiPool {
                 score = fmaf(fast_tanh(x[j + 3] + b4.w), q4.w, score);
             }
         }
-        float* s_score = c.scratch;
-        float* s_w = c.scratch + 128;
-        s_score[c.r] = c.valid ? score : -INFINITY;
+        float* s_part = c.scratch;
+        float* s_w = c.scratch + 256;
+        s_part[c.half * 128 + c.r] = score;
         epi_bar_sync();
-        float w = 0.f;
-        if (c.valid) {
-            const int s0 = (c.r / seg_len) * seg_len;
-            float m = -INFINITY;
-            for (int t = 0; t < seg_len; ++t) m = fmaxf(m, s_score[s0 + t]);
-            float sum = 0.f;
-            for (int t = 0; t < seg_len; ++t) sum += __expf(s_score[s0 + t] - m);
-            w = __fdividef(__expf(score - m), sum);
-            if (w_out != nullptr) w_out[c.grow] = w;
+        if (c.half == 0) {
+            float w = 0.f;
+            if (c.valid) {
+                const int s0 = (c.r / seg_len) * seg_len;
+                const float mine = s_part[c.r] + s_part[128 + c.r];
+                float m = -INFINITY;
+                for (int t = 0; t < seg_len; ++t) m = fmaxf(m, s_part[s0 + t] + s_part[128 + s0 + t]);
+                float sum = 0.f;
+                for (int t = 0; t < seg_len; ++t) sum += __expf(s_part[s0 + t] + s_part[128 + s0 + t] - m);
+                w = __fdividef(__expf(mine - m), sum);
+                if (w_out != nullptr) w_out[c.grow] = w;
+            }
+            s_w[c.r] = w;
         }
-        s_w[c.r] = w;
         epi_bar_sync();
         const int row0 = c.tile * rows_per_tile;
         const int nseg = rows_per_tile / seg_len;
@@ -206,7 +234,7 @@ struct EpiPool {
             const int r0 = row0 + s * seg_len;
             if (r0 >= M) break;
             const int gs = r0 / seg_len;
-            for (int pidx = c.tid; pidx < (D >> 1); pidx += 128) {
+            for (int pidx = c.tid; pidx < (D >> 1); pidx += kEpiThreads) {
                 float a0 = 0.f, a1 = 0.f;
                 const __nv_bfloat16* xp = X + static_cast<size_t>(r0) * lda + 2 * pidx;
                 int t = 0;
@@ -239,6 +267,7 @@ struct EpiPool {
 // ------------------------------------------------------------------------------------------------
 // Backward of the additive scorer, fused behind the recomputed pre = X.Wa^T:
 //   T = tanh(pre + ba);  dPre_rc = dscore_r * qv_c * (1 - T^2)  -> bf16;   dqv_c += sum_r dscore_r * T_rc
+// scratch floats: [0,256) column sums | [256,512) bias | [512,768) query vector
 // ------------------------------------------------------------------------------------------------
 struct EpiDPre {
     const float* bias;
@@ -248,9 +277,8 @@ struct EpiDPre {
     int ld;
     float* dqv;               // [q] fp32, accumulated
 
-    // scratch: [0,256) column sums | [256,512) bias | [512,768) query vector
     __device__ void init(int col0, int ncols, int tid, float* scratch) const {
-        for (int i = tid; i < 256; i += 128) {
+        for (int i = tid; i < 256; i += kEpiThreads) {
             scratch[i] = 0.f;
             scratch[256 + i] = i < ncols ? bias[col0 + i] : 0.f;
             scratch[512 + i] = i < ncols ? qv[col0 + i] : 0.f;
@@ -259,17 +287,17 @@ struct EpiDPre {
     }
     __device__ void finish(int col0, int ncols, int tid, float* scratch) const {
         epi_bar_sync();
-        for (int i = tid; i < ncols; i += 128) atomicAdd(dqv + col0 + i, scratch[i]);
+        for (int i = tid; i < ncols; i += kEpiThreads) atomicAdd(dqv + col0 + i, scratch[i]);
     }
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         const float ds = c.valid ? __ldg(dscore + c.grow) : 0.f;
-        const int nch = (c.ncols + 31) >> 5;
         const int lane = c.tid & 31;
-        for (int ch = 0; ch < nch; ++ch) {
+        if (c.ch0 >= c.ch1) acc.release();
+        for (int ch = c.ch0; ch < c.ch1; ++ch) {
             float x[32];
             acc.load32(ch, x);
-            if (ch == nch - 1) acc.release();
+            if (ch == c.ch1 - 1) acc.release();
             float dp[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -282,11 +310,15 @@ struct EpiDPre {
             if (c.valid) {
                 __nv_bfloat16* o = dpre + static_cast<size_t>(c.grow) * ld + c.col0 + ch * 32;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (ch * 32 + g * 8 >= c.ncols) break;  // ld is padded to a multiple of 8: whole groups are in bounds
-                    *reinterpret_cast<uint4*>(o + g * 8) =
-                        make_uint4(pack_bf16x2(dp[g * 8], dp[g * 8 + 1]), pack_bf16x2(dp[g * 8 + 2], dp[g * 8 + 3]),
-                                   pack_bf16x2(dp[g * 8 + 4], dp[g * 8 + 5]), pack_bf16x2(dp[g * 8 + 6], dp[g * 8 + 7]));
+                for (int g = 0; g < 2; ++g) {
+                    const int lc = ch * 32 + g * 16;
+                    if (lc >= c.ncols) break;  // ld is padded to a multiple of 8: whole 8-groups are in bounds
+                    if (lc + 16 <= ld - c.col0 && aligned32(o + g * 16)) {
+                        store_bf16x16(o + g * 16, dp + g * 16);
+                    } else {
+                        store_bf16x8(o + g * 16, dp + g * 16, 8);
+                        if (lc + 8 < c.ncols) store_bf16x8(o + g * 16 + 8, dp + g * 16 + 8, 8);
+                    }
                 }
             }
             const float colsum = warp_transpose_sum32(x);
@@ -296,7 +328,8 @@ struct EpiDPre {
 };
 
 // ------------------------------------------------------------------------------------------------
-// dX_rc = acc_rc + w_r * dOut[seg(r)][c]  (pool backward, both paths into X) [* dropout of X] -> bf16
+// dX_rc = acc_rc + w_r * dOut[seg(r)][c]  (pool backward, both paths into X) [* relu mask] [* dropout] -> bf16
+// scratch floats: half*1280 + [segments of this tile][32 columns of the current chunk] (dOut staging per half)
 // ------------------------------------------------------------------------------------------------
 struct EpiDPoolIn {
     const float* w;      // [rows]
@@ -311,15 +344,14 @@ struct EpiDPoolIn {
     Dropout drop;
     const __nv_bfloat16* relu_src;  // non-null: multiply by (relu_src[r][c] > 0) (ReLU backward of the CNN); pitch relu_ld
     int relu_ld;
-
     int M;
     int rows_per_tile;
 
     __device__ void init(int, int, int, float*) const {}
     __device__ void finish(int, int, int, float*) const {}
 
-    // scratch: dOut[segments of this tile][32 columns of the current chunk], restaged per chunk (the rows of a
-    // segment all need the same dOut row: one coalesced global read instead of 128 x 32 latency-bound ones)
+    // The rows of a segment all need the same dOut row: one coalesced global read per chunk instead of 128 x 32
+    // latency-bound ones.  The two column halves run different chunk counts -> per-half staging and barriers.
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         long long orow;
@@ -331,20 +363,22 @@ struct EpiDPoolIn {
         const int seg_last = min(row0 + 127, M - 1) / seg_len;
         const int nseg = seg_last - seg_first + 1;
         const int myseg = (c.valid ? c.grow / seg_len : seg_first) - seg_first;
-        const int nch = (c.ncols + 31) >> 5;
-        for (int ch = 0; ch < nch; ++ch) {
+        float* stage = c.scratch + c.half * 1280;
+        const int htid = c.tid & 127;
+        if (c.ch0 >= c.ch1) acc.release();
+        for (int ch = c.ch0; ch < c.ch1; ++ch) {
             float x[32];
             acc.load32(ch, x);
-            if (ch == nch - 1) acc.release();
-            epi_bar_sync();  // previous chunk's readers are done with the staging buffer
-            for (int i = c.tid; i < nseg * 32; i += 128) {
+            if (ch == c.ch1 - 1) acc.release();
+            epi_bar_sync_half(c.half);  // previous chunk's readers are done with the staging buffer
+            for (int i = htid; i < nseg * 32; i += 128) {
                 const int sgi = i >> 5, j = i & 31;
                 const int col = c.col0 + ch * 32 + j;
-                c.scratch[i] = (col < N && ch * 32 + j < c.ncols) ? dout[static_cast<size_t>(seg_first + sgi) * ldo + col] : 0.f;
+                stage[i] = (col < N && ch * 32 + j < c.ncols) ? dout[static_cast<size_t>(seg_first + sgi) * ldo + col] : 0.f;
             }
-            epi_bar_sync();
+            epi_bar_sync_half(c.half);
             if (!v) continue;
-            const float* sd = c.scratch + myseg * 32;
+            const float* sd = stage + myseg * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int lc = ch * 32 + g * 8;
@@ -374,16 +408,10 @@ struct EpiDPoolIn {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) y[j] *= m[j];
                 }
-                __nv_bfloat16* o = dx + orow * ld + col;
-                if (nvalid == 8) {
-                    *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
-                                                              pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-                } else {
-                    for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(y[j]);
-                }
+                store_bf16x8(dx + orow * ld + col, y, nvalid);
             }
         }
-        if (v && c.col0 == 0 && zero_pad_rows) {
+        if (v && c.col0 == 0 && c.half == 0 && zero_pad_rows) {
             if (t == 0) zero_row_bf16(dx + (orow - 1) * ld, ld);
             if (t == rm.seg_len - 1) zero_row_bf16(dx + (orow + 1) * ld, ld);
         }
@@ -411,11 +439,11 @@ struct EpiScatter {
         const bool v = rm.map(c.grow, trow, t) && c.valid;
         const long long id = v ? ids[trow] : 0;
         float* dst = demb + static_cast<size_t>(id) * D;
-        const int nch = (c.ncols + 31) >> 5;
-        for (int ch = 0; ch < nch; ++ch) {
+        if (c.ch0 >= c.ch1) acc.release();
+        for (int ch = c.ch0; ch < c.ch1; ++ch) {
             float x[32];
             acc.load32(ch, x);
-            if (ch == nch - 1) acc.release();
+            if (ch == c.ch1 - 1) acc.release();
             if (id == 0) continue;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {

@@ -10,14 +10,18 @@
 //  gemm_tn : D[Ma x Nb] += A[Kr x Ma]^T . B[Kr x Nb]  (both MN-major; weight gradients, Kr = all tokens)
 //            split over Kr across CTAs, fp32 red.global.add epilogue.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
-// warp 5 MMA issuer + TMEM allocator.
+// Warp roles of gemm_nt (320 threads): warps 0-7 epilogue (TMEM lane quarter = warp & 3; the two warps of a quarter
+// split the accumulator columns -- with 4 warps the row-per-thread epilogue was latency bound at ~20 % issue
+// utilisation, ncu profiles/), warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+// gemm_tn keeps 192 threads (4 epilogue warps, one-shot epilogue).
 #pragma once
 #include "nr_common.cuh"
 
 namespace nr {
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // gemm_nt
+constexpr int kTnThreads = 192;     // gemm_tn
+constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                     // bf16 elements per 128-byte swizzle row
 constexpr int kAStageBytes = kTileM * 128;      // 16 KB
@@ -30,7 +34,7 @@ struct GemmNTParams {
     int rows_per_tile;  // rows OWNED by one M tile (<=128); tile t loads rows [t*rpt, t*rpt+128)
     int num_m_tiles;
     int N;              // output columns
-    int n_stride;       // columns per weight slice (multiple of 8)
+    int n_stride;       // columns per weight slice (multiple of 16)
     int n_slices;
     int n_box;          // rows of one resident weight box (multiple of 16, <=256)
     int K;              // reduction length per tap (elements)
@@ -50,11 +54,20 @@ struct EpiCtx {
     bool valid;   // r < rows_per_tile && grow < M
     int col0;     // first output column of this CTA's slice
     int ncols;    // valid output columns in the slice
-    int tid;      // 0..127 within the epilogue group
+    int tid;      // 0..255 within the epilogue group
+    int half;     // 0 / 1: which of the two warps of this TMEM lane quarter
+    int ch0, ch1; // this thread's range of 32-column chunks
     float* scratch;  // kEpiScratchBytes of shared memory private to the epilogue group
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// the two column halves run different chunk counts: barriers inside a chunk loop are per half
+__device__ __forceinline__ void epi_bar_sync_half(int half) { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); }
+__device__ __forceinline__ void epi_chunk_range(int ncols, int half, int& ch0, int& ch1) {
+    const int nch = (ncols + 31) >> 5, mid = (nch + 1) >> 1;
+    ch0 = half ? mid : 0;
+    ch1 = half ? nch : mid;
+}
 
 struct TmemAcc {
     uint32_t taddr;
@@ -109,7 +122,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_mma = (ncols + 15) & ~15;
     const int tap_shift = p.taps / 2;
 
-    if (warp == 4 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < p.stages; ++i) {
@@ -119,10 +132,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(bfull, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 128);
+            mbar_init(&tempty[i], kEpiThreads);
         }
         fence_barrier_init();
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         tmem_alloc(tmem_slot, 512);
     }
     tc_fence_before();
@@ -130,7 +143,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_arrive_expect_tx(bfull, static_cast<uint32_t>(p.taps * p.k_chunks * b_region));
@@ -151,7 +164,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(kTileM, n_mma, 0, 0);
@@ -185,8 +198,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue warps 0..3 =====================
+        // ===================== epilogue warps 0..7 =====================
         epi.init(col0, ncols, threadIdx.x, scratch);
+        const int quarter = warp & 3;
         int it = 0;
         for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
@@ -194,14 +208,16 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             EpiCtx c;
             c.tile = tile;
-            c.r = warp * 32 + lane;
+            c.r = quarter * 32 + lane;
             c.grow = tile * p.rows_per_tile + c.r;
             c.valid = (c.r < p.rows_per_tile) && (c.grow < p.M);
             c.col0 = col0;
             c.ncols = ncols;
             c.tid = threadIdx.x;
+            c.half = warp >> 2;
+            epi_chunk_range(ncols, c.half, c.ch0, c.ch1);
             c.scratch = scratch;
-            TmemAcc acc{tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + as * 256, &tempty[as]};
+            TmemAcc acc{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 256, &tempty[as]};
             epi(acc, c);
         }
         epi.finish(col0, ncols, threadIdx.x, scratch);
@@ -209,32 +225,34 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 // Debug backend (triage only, NR_DEBUG_SIMT_GEMM=1): plain SIMT accumulate + the SAME epilogue functors.
 __global__ void gemm_nt_simt_acc_kernel(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                                         GemmNTParams p);
 template <class Epi>
-__global__ void __launch_bounds__(128, 1) gemm_nt_simt_epi_kernel(const GemmNTParams p, const Epi epi) {
+__global__ void __launch_bounds__(kEpiThreads, 1) gemm_nt_simt_epi_kernel(const GemmNTParams p, const Epi epi) {
     __shared__ float scratch[kEpiScratchBytes / 4];
     const int slice = blockIdx.x % p.n_slices;
     const int tile0 = blockIdx.x / p.n_slices;
     const int tile_step = gridDim.x / p.n_slices;
     const int col0 = slice * p.n_stride;
     const int ncols = min(p.n_stride, p.N - col0);
-    for (int i = threadIdx.x; i < kEpiScratchBytes / 4; i += 128) scratch[i] = 0.f;
+    for (int i = threadIdx.x; i < kEpiScratchBytes / 4; i += kEpiThreads) scratch[i] = 0.f;
     __syncthreads();
     epi.init(col0, ncols, threadIdx.x, scratch);
     for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step) {
         EpiCtx c;
         c.tile = tile;
-        c.r = threadIdx.x;
+        c.r = threadIdx.x & 127;
         c.grow = tile * p.rows_per_tile + c.r;
         c.valid = (c.r < p.rows_per_tile) && (c.grow < p.M);
         c.col0 = col0;
         c.ncols = ncols;
         c.tid = threadIdx.x;
+        c.half = threadIdx.x >> 7;
+        epi_chunk_range(ncols, c.half, c.ch0, c.ch1);
         c.scratch = scratch;
         GlobalAcc acc{p.dbg_acc + (static_cast<size_t>(tile) * 128 + c.r) * p.dbg_ld + col0};
         epi(acc, c);
@@ -260,7 +278,7 @@ struct GemmTNParams {
     int ldd;
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kTnThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTNParams p);
 
 // ---------------------------------------------------------------------------------------------
@@ -291,7 +309,7 @@ int launch_gemm_nt(const GemmNTPlan& plan, const Epi& epi, const void* A, int ld
         dim3 g(ceil_div(static_cast<int>(ld), 128), p.num_m_tiles);
         gemm_nt_simt_acc_kernel<<<g, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda,
                                                        static_cast<const __nv_bfloat16*>(B), ldb, p);
-        gemm_nt_simt_epi_kernel<Epi><<<plan.grid, 128, 0, stream>>>(p, epi);
+        gemm_nt_simt_epi_kernel<Epi><<<plan.grid, kEpiThreads, 0, stream>>>(p, epi);
         NR_CHECK_CUDA(cudaGetLastError());
         NR_CHECK_CUDA(cudaFreeAsync(acc, stream));
         return 0;

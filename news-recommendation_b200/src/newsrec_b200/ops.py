@@ -18,6 +18,10 @@ def ru8(x: int) -> int:
     return (x + 7) // 8 * 8
 
 
+def ru16(x: int) -> int:
+    return (x + 15) // 16 * 16
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -70,7 +74,7 @@ def cast_pad(src: torch.Tensor, ld: int, transpose: bool = False) -> torch.Tenso
 
 def mhsa_operands(cache: OperandCache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
     d, q = Wq.shape[0], Wa.shape[0]
-    ldx, ld3, ldq = ru8(d + 1), ru8(3 * d), ru8(q)
+    ldx, ld3, ldq = ru8(d + 1), ru16(3 * d), ru16(q)
 
     def build(Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
         wqkv = torch.cat((Wq, Wk, Wv), dim=0)
@@ -102,7 +106,7 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         lib = load_library()
         dev = require_cuda()
         d, q = Wq.shape[0], Wa.shape[0]
-        ldx, ld3 = ru8(d + 1), ru8(3 * d)
+        ldx, ld3 = ru8(d + 1), ru16(3 * d)
         ops = mhsa_operands(cache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv)
         a = MhsaEncoderFwdArgs()
         if ids is not None:
@@ -146,7 +150,7 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         m = ctx.meta
         dev = X.device
         d, q, T, n_seq = m["d"], m["q"], m["T"], m["n_seq"]
-        ldx, ld3, ldq = ru8(d + 1), ru8(3 * d), ru8(q)
+        ldx, ld3, ldq = ru8(d + 1), ru16(3 * d), ru16(q)
         ops = m["ops"]
         dout = dout.contiguous().float()
         dWqkv = torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev)
@@ -189,7 +193,7 @@ class AdditiveAttentionFn(torch.autograd.Function):
         dev = require_cuda()
         N, S, D = x.shape
         q = Wa.shape[0]
-        ldx, ldq = ru8(D + 1), ru8(q)
+        ldx, ldq = ru8(D + 1), ru16(q)
         ops = cache.get(prefix, (Wa, ba, qv), lambda Wa, ba, qv: dict(
             wa=cast_pad(Wa, ldx), waT=cast_pad(Wa, ldq, transpose=True), ba=ba.float().contiguous(),
             qv=qv.float().contiguous()))
@@ -212,7 +216,7 @@ class AdditiveAttentionFn(torch.autograd.Function):
         m = ctx.meta
         N, S, D, q, ops = m["N"], m["S"], m["D"], m["q"], m["ops"]
         dev = X.device
-        ldx, ldq = ru8(D + 1), ru8(q)
+        ldx, ldq = ru8(D + 1), ru16(q)
         dout = dout.contiguous().float()
         dX = torch.empty((N * S, ldx), dtype=torch.bfloat16, device=dev)
         dWa = torch.zeros((q, ldx), dtype=torch.float32, device=dev)
@@ -268,7 +272,7 @@ class MhsaFn(torch.autograd.Function):
         lib = load_library()
         dev = require_cuda()
         N, T, d = x.shape
-        ldx, ld3 = ru8(d + 1), ru8(3 * d)
+        ldx, ld3 = ru8(d + 1), ru16(3 * d)
 
         def build(Wq, bq, Wk, bk, Wv, bv):
             wqkv = torch.cat((Wq, Wk, Wv), dim=0)
@@ -295,7 +299,7 @@ class MhsaFn(torch.autograd.Function):
         m = ctx.meta
         N, T, d, heads, ops = m["N"], m["T"], m["d"], m["heads"], m["ops"]
         dev = X.device
-        ldx, ld3 = ru8(d + 1), ru8(3 * d)
+        ldx, ld3 = ru8(d + 1), ru16(3 * d)
         g = dctx.float().contiguous().view(N * T, d)
         dC = torch.empty((N * T, ldx), dtype=torch.bfloat16, device=dev)
         check(lib.nr_rows_to_bf16(_p(g), N * T, d, d, 1, _p(dC), ldx, _stream()), "nr_rows_to_bf16")

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import CnnEncoderBwdArgs, CnnEncoderFwdArgs, NewsrecError, check, load_library, require_cuda
-from .ops import _p, _stream, cast_pad, next_seed, ru8, table_operand
+from .ops import _p, _stream, cast_pad, next_seed, ru8, ru16, table_operand
 
 
 class CnnPoolEncoderFn(torch.autograd.Function):
@@ -23,7 +23,7 @@ class CnnPoolEncoderFn(torch.autograd.Function):
         if win != 3:
             raise NewsrecError(f"window_size={win}: the tcgen05 conv path implements the reference default window_size=3")
         q = Wa.shape[0]
-        ldx, ldf, ldq = ru8(d + 1), ru8(Fn + 1), ru8(q)
+        ldx, ldf, ldq = ru8(d + 1), ru8(Fn + 1), ru16(q)
         n_seq, T = ids.shape
         ids = ids.contiguous()
 
@@ -60,7 +60,7 @@ class CnnPoolEncoderFn(torch.autograd.Function):
         m = ctx.meta
         dev = Xp.device
         n_seq, T, d, Fn, q, ops = m["n_seq"], m["T"], m["d"], m["F"], m["q"], m["ops"]
-        ldx, ldf, ldq = ru8(d + 1), ru8(Fn + 1), ru8(q)
+        ldx, ldf, ldq = ru8(d + 1), ru8(Fn + 1), ru16(q)
         dout = dout.contiguous().float()
         dWc = torch.zeros((3, Fn, ldx), dtype=torch.float32, device=dev)
         dWa = torch.zeros((q, ldf), dtype=torch.float32, device=dev)

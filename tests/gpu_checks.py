@@ -13,7 +13,7 @@ import torch
 
 import newsrec_oracle as O
 from newsrec_b200 import check, load_library
-from newsrec_b200.ops import _p, _stream, cast_pad, ru8
+from newsrec_b200.ops import _p, _stream, cast_pad, ru8, ru16
 
 DEV = "cuda"
 
@@ -164,7 +164,7 @@ def check_gemm_tn(Kr=1000, Ma=900, Nb=301, shift=0):
 def check_mhsa_core(n_seq=7, T=20, heads=15, dk=20):
     lib = load_library()
     d = heads * dk
-    ld3, ldx = ru8(3 * d), ru8(d + 1)
+    ld3, ldx = ru16(3 * d), ru8(d + 1)
     qkv = _rand_bf16((n_seq * T, 3 * d), 21, 1.5).requires_grad_(True)
     Q, K, V = [t.view(n_seq, T, heads, dk).transpose(1, 2) for t in qkv.split(d, dim=1)]
     ctx = O.scaled_dot_product_attention(Q, K, V, O.BF16).transpose(1, 2).reshape(n_seq * T, d)
@@ -398,7 +398,7 @@ def _encoder_fwd_raw(ids, dense, sd, prefix, heads, V):
     from newsrec_b200 import MhsaEncoderFwdArgs
     lib = load_library()
     d, q = 300, 200
-    ldx, ld3 = ru8(d + 1), ru8(3 * d)
+    ldx, ld3 = ru8(d + 1), ru16(3 * d)
     g = lambda k: sd[f"{prefix}.{k}"].to(DEV)
     wqkv = torch.cat([g(f"multihead_self_attention.W_{n}.weight") for n in "QKV"], 0)
     ops = dict(wqkv=cast_pad(wqkv, ldx), bqkv=torch.cat([g(f"multihead_self_attention.W_{n}.bias") for n in "QKV"]).contiguous(),

@@ -12,13 +12,13 @@ sys.path.insert(0, os.path.join(ROOT, "news-recommendation_b200", "src"))
 import torch  # noqa: E402
 
 from newsrec_b200 import check, load_library  # noqa: E402
-from newsrec_b200.ops import _p, _stream, ru8  # noqa: E402
+from newsrec_b200.ops import _p, _stream, ru8, ru16  # noqa: E402
 
 lib = load_library()
 dev = torch.device("cuda", 0)
 n_seq, T, d, heads, q = 512 * 55, 20, 300, 15, 200
 n_tok = n_seq * T
-ldx, ld3, ldq = ru8(d + 1), ru8(3 * d), ru8(q)
+ldx, ld3, ldq = ru8(d + 1), ru16(3 * d), ru16(q)
 bf = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(torch.bfloat16)
 X, QKV, Cx, dC, dQKV = bf(n_tok, ldx), bf(n_tok, ld3), bf(n_tok, ldx), bf(n_tok, ldx), bf(n_tok, ld3)
 Wqkv, WqkvT, Wa, WaT = bf(3 * d, ldx), bf(d, ld3), bf(q, ldx), bf(d, ldq)
