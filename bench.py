@@ -271,6 +271,9 @@ def main():
     ms_e2e, _ = timed(host_batches, read_loss=True)
     log(f"end-to-end: {ms_e2e / args.steps:.3f} ms/step")
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     pk = peaks()

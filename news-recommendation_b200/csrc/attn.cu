@@ -75,28 +75,34 @@ __device__ __forceinline__ float drop_mult(uint64_t seed, uint32_t thresh, float
 // Row-block softmax on the S fragments of one 16-row m-tile.  s[nt][4] holds (row g: c0,c1 ; row g+8: c2,c3)
 // for key columns nt*8 + 2t, +1.  Input scores are pre-scaled into the log2 domain.  Returns P in place.
 template <int NTJ>
-__device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4) {
+__device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4, int ntj, float sc) {
+    // raw scores in, probabilities out; `sc` = log2(e)/sqrt(d_k) is folded into the exp2 argument.
+    // Only the last live n-tile can contain key columns >= T; tiles >= ntj are dead (skipped everywhere).
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NTJ; ++nt) {
+        if (nt >= ntj) break;
+        if (nt * 8 + 8 > T) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const bool ok = nt * 8 + 2 * t4 + e < T;
-            s[nt][e] = ok ? s[nt][e] : -INFINITY;
-            s[nt][2 + e] = ok ? s[nt][2 + e] : -INFINITY;
-            m0 = fmaxf(m0, s[nt][e]);
-            m1 = fmaxf(m1, s[nt][2 + e]);
+            for (int e = 0; e < 2; ++e) {
+                const bool ok = nt * 8 + 2 * t4 + e < T;
+                s[nt][e] = ok ? s[nt][e] : -INFINITY;
+                s[nt][2 + e] = ok ? s[nt][2 + e] : -INFINITY;
+            }
         }
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
     }
-    m0 = quad_max(m0);
-    m1 = quad_max(m1);
+    m0 = quad_max(m0) * sc;
+    m1 = quad_max(m1) * sc;
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NTJ; ++nt) {
+        if (nt >= ntj) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; continue; }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            s[nt][e] = exp2f(s[nt][e] - m0);
-            s[nt][2 + e] = exp2f(s[nt][2 + e] - m1);
+            s[nt][e] = exp2f(fmaf(s[nt][e], sc, -m0));
+            s[nt][2 + e] = exp2f(fmaf(s[nt][2 + e], sc, -m1));
             l0 += s[nt][e];
             l1 += s[nt][2 + e];
         }
@@ -107,6 +113,7 @@ __device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4) {
     const float i1 = 1.f / (l1 + 1e-8f * exp2f(-m1));
 #pragma unroll
     for (int nt = 0; nt < NTJ; ++nt) {
+        if (nt >= ntj) break;
         s[nt][0] *= i0;
         s[nt][1] *= i0;
         s[nt][2] *= i1;
@@ -359,11 +366,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
                     mma_bf16(s[nt], a, b);
                 }
             }
-#pragma unroll
-            for (int nt = 0; nt < NTJ; ++nt) {
-                s[nt][0] *= sc; s[nt][1] *= sc; s[nt][2] *= sc; s[nt][3] *= sc;
-            }
-            softmax_rows<NTJ>(s, T, t4);
+            softmax_rows<NTJ>(s, T, t4, ntj, sc);
             float o[NTD][4];
 #pragma unroll
             for (int nd = 0; nd < NTD; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
@@ -521,11 +524,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
                     mma_bf16(dp[nt], ag, bv);   // dA = dCtx V^T
                 }
             }
-#pragma unroll
-            for (int nt = 0; nt < NTJ; ++nt) {
-                s[nt][0] *= sc; s[nt][1] *= sc; s[nt][2] *= sc; s[nt][3] *= sc;
-            }
-            softmax_rows<NTJ>(s, T, t4);
+            softmax_rows<NTJ>(s, T, t4, ntj, sc);
             float del0 = 0.f, del1 = 0.f;
 #pragma unroll
             for (int nt = 0; nt < NTJ; ++nt) {

@@ -90,19 +90,27 @@ __global__ void gather_rows_kernel(const long long* __restrict__ ids, long long 
     const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     const long long total = n_tok * chunks;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long tok = i / chunks;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    // software pipeline: the (id -> table row) loads of the NEXT element are in flight while this one is stored
+    long long n_tok_i = i < total ? i / chunks : 0;
+    long long n_id = i < total ? __ldg(ids + n_tok_i) : 0;
+    if (i < total && (n_id < 0 || n_id >= V)) { atomicExch(bad_flag, 1); n_id = 0; }
+    uint4 n_u = i < total ? __ldg(table + n_id * chunks + (i - n_tok_i * chunks)) : make_uint4(0, 0, 0, 0);
+    for (; i < total; i += stride) {
+        const long long tok = n_tok_i;
         const int c = static_cast<int>(i - tok * chunks);
-        long long id = __ldg(ids + tok);
-        if (id < 0 || id >= V) {
-            if (c == 0) atomicExch(bad_flag, 1);
-            id = 0;
+        uint4 u = n_u;
+        const long long i2 = i + stride;
+        if (i2 < total) {
+            n_tok_i = i2 / chunks;
+            n_id = __ldg(ids + n_tok_i);
+            if (n_id < 0 || n_id >= V) { atomicExch(bad_flag, 1); n_id = 0; }
+            n_u = __ldg(table + n_id * chunks + (i2 - n_tok_i * chunks));
         }
         const long long seg = tok / T;
         const int t = static_cast<int>(tok - seg * T);
         const long long xr = padded ? seg * (T + 2) + 1 + t : tok;
-        uint4 u = __ldg(table + id * chunks + c);
         uint32_t w[4] = {u.x, u.y, u.z, u.w};
         const int col = c * 8;
         if (p > 0.f) {
@@ -145,36 +153,78 @@ int gather_rows(const long long* ids, long long n_tok, int T, const void* table,
 // ------------------------------------------------------------------------------------------------
 // pooling backward, scalar part: dw_r = dOut[seg] . X_r ; dscore_r = w_r (dw_r - sum_seg w dw)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pool_dscore_kernel(const __nv_bfloat16* __restrict__ X, int lda, int D,
+// Two phases inside one block (= a few segments): (1) every warp takes rows round-robin and keeps the 16-byte loads of
+// up to 4 rows in flight before reducing (the first version walked rows one by one and was latency bound at ~1.3 TB/s);
+// (2) one thread per row turns the row dots into dscore.
+constexpr int kDsSegs = 6;    // segments per block iteration
+__global__ void __launch_bounds__(256) pool_dscore_kernel(const __nv_bfloat16* __restrict__ X, int lda, int D,
                                                           long long n_seg, int seg_len, const float* __restrict__ w,
                                                           const float* __restrict__ dout, int ldo,
                                                           float* __restrict__ dscore) {
-    __shared__ float s_dw[128];
+    extern __shared__ float s_dw[];  // [kDsSegs * seg_len]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunks = D >> 3;  // whole 16-byte chunks of the row; the tail (D % 8) is handled element-wise
-    for (long long seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
-        const float* dob = dout + seg * ldo;
-        for (int t = warp; t < seg_len; t += 4) {
-            const __nv_bfloat16* xr = X + (seg * seg_len + t) * static_cast<long long>(lda);
-            float a = 0.f;
-            for (int c = lane; c < chunks; c += 32) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr) + c);
-                const float4 d0 = *reinterpret_cast<const float4*>(dob + c * 8);
-                const float4 d1 = *reinterpret_cast<const float4*>(dob + c * 8 + 4);
-                const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-                a = fmaf(f0.x, d0.x, a); a = fmaf(f0.y, d0.y, a); a = fmaf(f1.x, d0.z, a); a = fmaf(f1.y, d0.w, a);
-                a = fmaf(f2.x, d1.x, a); a = fmaf(f2.y, d1.y, a); a = fmaf(f3.x, d1.z, a); a = fmaf(f3.y, d1.w, a);
+    const int chunks = D >> 3;
+    const long long n_groups = (n_seg + kDsSegs - 1) / kDsSegs;
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const long long seg0 = grp * kDsSegs;
+        const int nsg = static_cast<int>(min(static_cast<long long>(kDsSegs), n_seg - seg0));
+        const int nrows = nsg * seg_len;
+        for (int r0 = warp * 4; r0 < nrows; r0 += 8 * 4) {
+            uint4 u[4][2];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r0 + k;
+                const uint4* xr = reinterpret_cast<const uint4*>(X + (seg0 * seg_len + r) * static_cast<long long>(lda));
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = lane + 32 * h;
+                    u[k][h] = (r < nrows && c < chunks) ? __ldg(xr + c) : make_uint4(0, 0, 0, 0);
+                }
             }
-            for (int c = chunks * 8 + lane; c < D; c += 32) a = fmaf(__bfloat162float(xr[c]), dob[c], a);
-            a = warp_sum(a);
-            if (lane == 0) s_dw[t] = a;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r0 + k;
+                if (r >= nrows) break;
+                const float* dob = dout + (seg0 + r / seg_len) * ldo;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = lane + 32 * h;
+                    if (c < chunks) {
+                        const float4 d0 = *reinterpret_cast<const float4*>(dob + c * 8);
+                        const float4 d1 = *reinterpret_cast<const float4*>(dob + c * 8 + 4);
+                        const uint4 v = u[k][h];
+                        const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+                        float a = acc[k];
+                        a = fmaf(f0.x, d0.x, a); a = fmaf(f0.y, d0.y, a); a = fmaf(f1.x, d0.z, a); a = fmaf(f1.y, d0.w, a);
+                        a = fmaf(f2.x, d1.x, a); a = fmaf(f2.y, d1.y, a); a = fmaf(f3.x, d1.z, a); a = fmaf(f3.y, d1.w, a);
+                        acc[k] = a;
+                    }
+                }
+                // columns beyond 64 chunks (D > 512) and the D % 8 tail
+                const __nv_bfloat16* xe = X + (seg0 * seg_len + r) * static_cast<long long>(lda);
+                for (int c = 64 + lane; c < chunks; c += 32) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xe) + c);
+                    const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16x2(vw[j]);
+                        acc[k] = fmaf(f.x, dob[c * 8 + 2 * j], acc[k]);
+                        acc[k] = fmaf(f.y, dob[c * 8 + 2 * j + 1], acc[k]);
+                    }
+                }
+                for (int c = chunks * 8 + lane; c < D; c += 32) acc[k] = fmaf(__bfloat162float(xe[c]), dob[c], acc[k]);
+                const float tot = warp_sum(acc[k]);
+                if (lane == 0) s_dw[r] = tot;
+            }
         }
         __syncthreads();
-        if (threadIdx.x < seg_len) {
-            const float* wr = w + seg * seg_len;
+        for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+            const int sgi = r / seg_len;
+            const float* wr = w + (seg0 + sgi) * seg_len;
+            const float* dwr = s_dw + sgi * seg_len;
             float dot = 0.f;
-            for (int t = 0; t < seg_len; ++t) dot = fmaf(wr[t], s_dw[t], dot);
-            dscore[seg * seg_len + threadIdx.x] = wr[threadIdx.x] * (s_dw[threadIdx.x] - dot);
+            for (int t = 0; t < seg_len; ++t) dot = fmaf(wr[t], dwr[t], dot);
+            dscore[seg0 * seg_len + r] = wr[r - sgi * seg_len] * (s_dw[r] - dot);
         }
         __syncthreads();
     }
@@ -183,10 +233,11 @@ int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, con
                 float* dscore, cudaStream_t stream) {
     if (n_seg == 0) return 0;
     NR_REQUIRE(seg_len <= 128 && D % 4 == 0 && ldo % 4 == 0 && lda % 8 == 0, "pool_dscore: seg_len=%d D=%d ldo=%d lda=%d", seg_len, D, ldo, lda);
-    const int blocks = static_cast<int>(std::min<long long>(n_seg, 148 * 16));
+    const long long groups = (n_seg + kDsSegs - 1) / kDsSegs;
+    const int blocks = static_cast<int>(std::min<long long>(groups, 148 * 8));
     ProfScope ps("pool_dscore", static_cast<int>(n_seg), seg_len, D, stream);
-    pool_dscore_kernel<<<blocks, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(X), lda, D, n_seg, seg_len, w, dout,
-                                                   ldo, dscore);
+    pool_dscore_kernel<<<blocks, 256, sizeof(float) * kDsSegs * seg_len, stream>>>(
+        static_cast<const __nv_bfloat16*>(X), lda, D, n_seg, seg_len, w, dout, ldo, dscore);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;
