@@ -35,6 +35,11 @@ int nr_num_sms(void);
 /* TRIAGE ONLY (tests): route the GEMMs through a plain SIMT accumulate + the same epilogue functors, to
  * tell a tcgen05/TMA pipeline bug from an epilogue bug.  Never enabled by the product path. */
 void nr_debug_set_simt_gemm(int on);
+/* TUNING ONLY (tools/kbench.py): dev_buf holds slots x 148 x 16 int64; the k-th gemm_nt planned after this call
+ * writes, per CTA, cycle counters into slot k: [0] TMA producer waiting for a free A stage, [1] MMA issuer waiting
+ * for A data, [2] MMA issuer waiting for a free TMEM accumulator, [3] epilogue waiting for a finished accumulator,
+ * [4] epilogue body, [5] kernel, [6] tiles, [7] MMA issue loops, [8] tcgen05.commit.  Null (default) switches the counters off. */
+void nr_debug_set_gemm_timing(void* dev_buf, int slots);
 /* Live per-kernel timing for bench.py: CUDA events on the launching stream around every kernel of this
  * library.  nr_profile_report writes JSON {"<context>/<op>[shape]": [launches, total_ms], ...}, returns its
  * length (or -1 if cap is too small) and clears the records.  Off by default. */

@@ -133,6 +133,14 @@ bool debug_simt_gemm() {
     return g_debug_simt == 1;
 }
 void set_debug_simt_gemm(int on) { g_debug_simt = on ? 1 : 0; }
+// tuning (tools/kbench.py): device buffer [slots][148][16]; every planned gemm_nt takes the next slot
+static long long* g_gemm_timing = nullptr;
+static int g_gemm_timing_slots = 0, g_gemm_timing_next = 0;
+void set_debug_gemm_timing(void* dev_buf, int slots) {
+    g_gemm_timing = static_cast<long long*>(dev_buf);
+    g_gemm_timing_slots = slots;
+    g_gemm_timing_next = 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // TMA descriptor encoding via the driver entry point (resolved at run time: the library must load
@@ -178,7 +186,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
 // gemm_nt planning
 // ------------------------------------------------------------------------------------------------
 int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B, int N, int ldb, int K, int taps,
-                 int b_tap_rows, int rows_per_tile, int sms, int max_slices) {
+                 int b_tap_rows, int rows_per_tile, int sms, int max_slices, int scratch_bytes, int max_n_stride) {
     NR_REQUIRE(M >= 0 && N >= 1 && K >= 1 && taps >= 1 && rows_per_tile >= 1 && rows_per_tile <= kTileM,
                "plan_gemm_nt: bad shape M=%d N=%d K=%d taps=%d rpt=%d", M, N, K, taps, rows_per_tile);
     NR_REQUIRE(sms > 0, "no CUDA device (SM count unknown)");
@@ -192,29 +200,35 @@ int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B,
     p.k_chunks = ceil_div(K, kChunkK);
     p.taps = taps;
     p.b_tap_rows = b_tap_rows;
-    const int fixed = 1024 + kEpiScratchBytes + 512;
+    if (g_gemm_timing != nullptr && g_gemm_timing_next < g_gemm_timing_slots) {
+        p.timing = g_gemm_timing + static_cast<size_t>(g_gemm_timing_next) * 148 * 16;
+        fprintf(stderr, "[nr] gemm timing slot %d: M=%d N=%d K=%d taps=%d\n", g_gemm_timing_next, M, N, K, taps);
+        ++g_gemm_timing_next;
+    }
+    const int fixed = 1024 + round_up(scratch_bytes, 16) + 512;
     int slices = 1;
     for (;; ++slices) {
         NR_REQUIRE(slices <= 64, "plan_gemm_nt: cannot fit weight slice (N=%d K=%d taps=%d)", N, K, taps);
         p.n_stride = round_up(ceil_div(N, slices), 16);  // 32-byte aligned slice starts (STG.256 epilogues)
         p.n_box = round_up(std::min(p.n_stride, N), 16);
-        if (p.n_box > 256) continue;
-        const long bbytes = static_cast<long>(taps) * p.k_chunks * p.n_box * 128;
+        if (p.n_box > 256 || (max_n_stride > 0 && p.n_stride > max_n_stride)) continue;
+        const long bbytes = static_cast<long>(taps) * p.k_chunks * (p.n_box / 2) * 128;  // per CTA: half the slice
         if (bbytes + 4L * kAStageBytes + fixed <= kSmemLimit) break;
         // epilogues that reduce over the whole output row need ONE slice: accept a shallower A ring instead
         if (slices == max_slices && bbytes + 2L * kAStageBytes + fixed <= kSmemLimit) break;
     }
     p.n_slices = ceil_div(N, p.n_stride);
-    const long bbytes = static_cast<long>(taps) * p.k_chunks * p.n_box * 128;
+    const long bbytes = static_cast<long>(taps) * p.k_chunks * (p.n_box / 2) * 128;
     p.stages = static_cast<int>(std::min<long>(kMaxStages, (kSmemLimit - fixed - bbytes) / kAStageBytes));
     NR_REQUIRE(p.stages >= 2, "plan_gemm_nt: only %d pipeline stages fit", p.stages);
     plan->smem = static_cast<size_t>(bbytes) + static_cast<size_t>(p.stages) * kAStageBytes + fixed;
-    const int groups = std::max(1, std::min(sms / p.n_slices, p.num_m_tiles));
-    plan->grid = groups * p.n_slices;
+    // CTA pairs: a group = n_slices pairs working on the same 256-row blocks
+    const int groups = std::max(1, std::min((sms / 2) / p.n_slices, ceil_div(p.num_m_tiles, 2)));
+    plan->grid = 2 * groups * p.n_slices;
     if (p.num_m_tiles == 0) return 0;
     NR_PROPAGATE(make_tmap_bf16_2d(&plan->tmA, A, M, K, lda, kChunkK, kTileM));
     const int64_t brows = (taps > 1) ? static_cast<int64_t>(taps) * b_tap_rows : N;
-    NR_PROPAGATE(make_tmap_bf16_2d(&plan->tmB, B, brows, K, ldb, kChunkK, p.n_box));
+    NR_PROPAGATE(make_tmap_bf16_2d(&plan->tmB, B, brows, K, ldb, kChunkK, p.n_box / 2));
     return 0;
 }
 
@@ -435,7 +449,7 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
                int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream) {
     if (M == 0) return 0;
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0));
+    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0, EpiStore::kScratchBytes, 0));
     NR_REQUIRE(out_bf16 ? (ld_out % 8 == 0) : (ld_out % 4 == 0), "gemm_store: output pitch %d breaks vector stores", ld_out);
     EpiStore e;
     e.out = out;
@@ -449,6 +463,8 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
     e.drop = to_drop(drop);
     e.ones_col = ones_col;
     e.ones_cols_zero_upto = ones_zero_upto;
+    static const int dbg_skip = [] { const char* v = getenv("NEWSREC_EPI_DBG"); return v != nullptr && v[0] == '1' ? 1 : 0; }();
+    e.dbg_skip = dbg_skip;
     g_launches += debug_simt_gemm() ? 2 : 1;
     ProfScope ps("gemm_store", M, N, K * taps, stream);
     return launch_gemm_nt(plan, e, A, lda, W, ldw, stream);
@@ -461,7 +477,7 @@ int gemm_additive_pool(const void* X, int M, int lda, int D, const void* Wa, int
     NR_REQUIRE(q <= 256 && (D % 2) == 0 && (ldo % 2) == 0, "additive_pool: q=%d D=%d ldo=%d unsupported", q, D, ldo);
     const int rpt = (kTileM / seg_len) * seg_len;
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, rpt, num_sms(), 1));
+    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, rpt, num_sms(), 1, EpiPool::kScratchBytes, 0));
     NR_REQUIRE(plan.p.n_slices == 1, "additive_pool: the query dimension must fit one weight slice (q=%d D=%d)", q, D);
     EpiPool e;
     e.bias = ba;
@@ -486,7 +502,7 @@ int gemm_additive_dpre(const void* X, int M, int lda, int D, const void* Wa, int
     if (M == 0) return 0;
     NR_REQUIRE(q <= 256 && ld_dpre % 8 == 0 && ld_dpre >= round_up(q, 8), "additive_dpre: q=%d ld=%d", q, ld_dpre);
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, kTileM, num_sms(), 1));
+    NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, kTileM, num_sms(), 1, EpiDPre::kScratchBytes, 0));
     NR_REQUIRE(plan.p.n_slices == 1, "additive_dpre: q=%d D=%d does not fit one weight slice", q, D);
     EpiDPre e;
     e.bias = ba;
@@ -504,8 +520,14 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
                      const float* dout, int ldo, int seg_len, void* dx, int ld_dx, RowMapCfg rm, int zero_pad_rows,
                      DropoutCfg drop, const void* relu_src, int relu_ld, cudaStream_t stream) {
     if (M == 0) return 0;
+    NR_REQUIRE(seg_len >= 1, "pool_dinput: seg_len=%d", seg_len);
+    // the epilogue stages the dOut rows of every segment a tile touches: cap the slice width so that they fit
+    const int nseg_max = kTileM / seg_len + 2;
+    const int max_stride = (EpiDPoolIn::kStageFloats / nseg_max) & ~15;
+    NR_REQUIRE(max_stride >= 16, "pool_dinput: seg_len=%d needs %d staged segments per tile", seg_len, nseg_max);
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, dpre, M, ld_dpre, WaT, D, ldwT, q, 1, 0, kTileM, num_sms(), 0));
+    NR_PROPAGATE(plan_gemm_nt(&plan, dpre, M, ld_dpre, WaT, D, ldwT, q, 1, 0, kTileM, num_sms(), 0,
+                              EpiDPoolIn::kScratchBytes, max_stride));
     NR_REQUIRE(ld_dx % 8 == 0, "pool_dinput: ld_dx=%d", ld_dx);
     EpiDPoolIn e;
     e.w = w;
@@ -522,7 +544,6 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
     e.relu_ld = relu_ld;
     e.M = M;
     e.rows_per_tile = kTileM;
-    NR_REQUIRE(seg_len >= 4, "pool_dinput: seg_len=%d (each column half stages up to 40 segments per tile)", seg_len);
     g_launches += debug_simt_gemm() ? 2 : 1;
     ProfScope ps("gemm_pool_dinput", M, D, q, stream);
     return launch_gemm_nt(plan, e, dpre, ld_dpre, WaT, ldwT, stream);
@@ -534,7 +555,8 @@ int gemm_scatter_emb(const void* A, int M, int lda, const void* W, int N, int ld
     if (M == 0) return 0;
     NR_REQUIRE(N == D && D % 4 == 0, "scatter_emb: N=%d D=%d", N, D);
     GemmNTPlan plan;
-    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0));
+    NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0,
+                              EpiScatter::kScratchBytes, 0));
     EpiScatter e;
     e.ids = ids;
     e.demb = demb;

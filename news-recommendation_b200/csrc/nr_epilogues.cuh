@@ -1,11 +1,14 @@
 // Fused epilogue functors for gemm_nt.  256 epilogue threads: thread (quarter, lane) owns accumulator row
 // r = 32*quarter + lane (= TMEM lane) and the two warps of a quarter ("halves") split the row's 32-column chunks
 // [ch0, ch1).  Contract for every functor:
-//   * a thread calls acc.load32() exactly once per chunk of ITS range (tcgen05.ld is warp-collective and the
-//     range is warp-uniform), and acc.release() exactly once per tile after its last load (also when the range is empty)
+//   * the accumulator is read through epi_chunks() (nr_gemm.cuh): one tcgen05.ld per chunk of the thread's range
+//     (warp-collective, the range is warp-uniform), software pipelined, acc.release() exactly once per tile
 //   * init()/finish() bracket the CTA's whole tile loop (all 256 epilogue threads call them)
+//   * kScratchBytes of shared memory belong to the functor (the planner sizes the A ring around it)
 //   * per-slice vectors (bias, query vector, dOut rows) are staged in shared memory: with ~220 KB of smem carved out
-//     the L1 holds next to nothing and per-element global loads made the epilogue 10x the MMA time (ncu, profiles/)
+//     the L1 holds next to nothing and per-element global loads made the epilogue 10x the MMA time (ncu, profiles/).
+//     Anything that must come from global memory per tile is fetched with many loads in flight or prefetched one
+//     tile ahead with cp.async -- a dependent L2 round trip (~600 cycles) per chunk was the whole epilogue time.
 #pragma once
 #include "nr_gemm.cuh"
 
@@ -71,6 +74,7 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* o, const float* y, i
 // scratch floats: [0,256) bias of the slice
 // ------------------------------------------------------------------------------------------------
 struct EpiStore {
+    static constexpr int kScratchBytes = 1024;
     void* out;
     int ld;
     int out_bf16;
@@ -82,70 +86,75 @@ struct EpiStore {
     Dropout drop;
     int ones_col;       // >=0: column set to 1.0 (bias-gradient trick for the next weight-grad GEMM); -1 off
     int ones_cols_zero_upto;  // columns (ones_col, upto) are zeroed
+    int dbg_skip;       // tuning only (NEWSREC_EPI_DBG=1): release the accumulator untouched -> MMA/TMA pipeline alone
 
-    __device__ void init(int col0, int ncols, int tid, float* scratch) const {
-        for (int i = tid; i < 256; i += kEpiThreads) scratch[i] = (bias != nullptr && i < ncols) ? bias[col0 + i] : 0.f;
+    __device__ void init(const EpiInit& e, int) const {
+        for (int i = e.tid; i < 256; i += kEpiThreads) e.scratch[i] = (bias != nullptr && i < e.ncols) ? bias[e.col0 + i] : 0.f;
         epi_bar_sync();
     }
-    __device__ void finish(int, int, int, float*) const {}
+    __device__ void finish(const EpiInit&) const {}
 
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         long long orow;
         int t;
         const bool v = rm.map(c.grow, orow, t) && c.valid;
-        if (c.ch0 >= c.ch1) acc.release();
-        for (int ch = c.ch0; ch < c.ch1; ++ch) {
-            float x[32];
-            acc.load32(ch, x);
-            if (ch == c.ch1 - 1) acc.release();
-            if (!v) continue;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int lc = ch * 32 + g * 16;  // column inside the slice
-                if (lc >= c.ncols) break;
-                const int col = c.col0 + lc;
-                float y[16];
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(c.scratch + lc + j);
-                    y[j] = x[g * 16 + j] + b4.x;
-                    y[j + 1] = x[g * 16 + j + 1] + b4.y;
-                    y[j + 2] = x[g * 16 + j + 2] + b4.z;
-                    y[j + 3] = x[g * 16 + j + 3] + b4.w;
-                }
-                if (relu) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-                }
-                if (drop.p > 0.f) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float m[4];
-                        drop.mask4(orow, ld, col + j, m);
-                        y[j] *= m[0]; y[j + 1] *= m[1]; y[j + 2] *= m[2]; y[j + 3] *= m[3];
-                    }
-                }
-                const int nvalid = min(16, min(c.ncols - lc, N - col));
-                if (out_bf16) {
-                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld + col;
-                    if (nvalid == 16 && aligned32(o)) {
-                        store_bf16x16(o, y);
-                    } else {
-                        store_bf16x8(o, y, min(nvalid, 8));
-                        if (nvalid > 8) store_bf16x8(o + 8, y + 8, nvalid - 8);
-                    }
-                } else {
-                    float* o = static_cast<float*>(out) + orow * ld + col;
-                    if (nvalid == 16) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-                    } else {
-                        for (int j = 0; j < nvalid; ++j) o[j] = y[j];
-                    }
-                }
-            }
+        if (dbg_skip) {
+            acc.release();
+            return;
         }
+        float b[32];
+        epi_chunks(
+            acc, c,
+            [&](int ch) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = lds_f4(c.scratch + ch * 32 + j);
+                    b[j] = b4.x; b[j + 1] = b4.y; b[j + 2] = b4.z; b[j + 3] = b4.w;
+                }
+            },
+            [&](int ch, float* x) {
+                if (!v) return;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int lc = ch * 32 + g * 16;  // column inside the slice
+                    if (lc >= c.ncols) break;
+                    const int col = c.col0 + lc;
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) y[j] = x[g * 16 + j] + b[g * 16 + j];
+                    if (relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+                    }
+                    if (drop.p > 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float m[4];
+                            drop.mask4(orow, ld, col + j, m);
+                            y[j] *= m[0]; y[j + 1] *= m[1]; y[j + 2] *= m[2]; y[j + 3] *= m[3];
+                        }
+                    }
+                    const int nvalid = min(16, min(c.ncols - lc, N - col));
+                    if (out_bf16) {
+                        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld + col;
+                        if (nvalid == 16 && aligned32(o)) {
+                            store_bf16x16(o, y);
+                        } else {
+                            store_bf16x8(o, y, min(nvalid, 8));
+                            if (nvalid > 8) store_bf16x8(o + 8, y + 8, nvalid - 8);
+                        }
+                    } else {
+                        float* o = static_cast<float*>(out) + orow * ld + col;
+                        if (nvalid == 16) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                        } else {
+                            for (int j = 0; j < nvalid; ++j) o[j] = y[j];
+                        }
+                    }
+                }
+            });
         if (v && c.col0 == 0 && c.half == 0) {
             if (ones_col >= 0 && out_bf16) {
                 __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld;
@@ -168,6 +177,7 @@ struct EpiStore {
 // scratch floats: [0,256) partial scores (half*128 + row) | [256,384) weights | [512,768) bias | [768,1024) query
 // ------------------------------------------------------------------------------------------------
 struct EpiPool {
+    static constexpr int kScratchBytes = 4096;
     const float* bias;
     const float* qv;
     const __nv_bfloat16* X;  // the GEMM's A operand (rows x lda), re-read (L2 hits) for the weighted sum
@@ -180,35 +190,54 @@ struct EpiPool {
     int ldo;
     float* w_out; // [rows] fp32 softmax weights (saved for backward); may be null
 
-    __device__ void init(int col0, int ncols, int tid, float* scratch) const {
-        for (int i = tid; i < 256; i += kEpiThreads) {
-            scratch[512 + i] = i < ncols ? bias[col0 + i] : 0.f;
-            scratch[768 + i] = i < ncols ? qv[col0 + i] : 0.f;
+    __device__ void init(const EpiInit& e, int) const {
+        for (int i = e.tid; i < 256; i += kEpiThreads) {
+            e.scratch[512 + i] = i < e.ncols ? bias[e.col0 + i] : 0.f;
+            e.scratch[768 + i] = i < e.ncols ? qv[e.col0 + i] : 0.f;
         }
         epi_bar_sync();
     }
-    __device__ void finish(int, int, int, float*) const {}
+    __device__ void finish(const EpiInit&) const {}
+
+    // 16-byte column chunk ck of the rows [r0, r0 + seg_len): weighted sum with the weights in s_w, U loads in flight
+    template <int U>
+    __device__ __forceinline__ void wsum_rows(const uint4* xp, size_t pitch16, const float* s_w, int& t, float* a) const {
+        for (; t + U <= seg_len; t += U) {
+            uint4 u[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) u[k] = __ldg(xp + static_cast<size_t>(t + k) * pitch16);
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const float wt = lds_f(s_w + t + k);
+                const uint32_t uw[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16x2(uw[j]);
+                    a[2 * j] = fmaf(wt, f.x, a[2 * j]);
+                    a[2 * j + 1] = fmaf(wt, f.y, a[2 * j + 1]);
+                }
+            }
+        }
+    }
 
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         float score = 0.f;
-        if (c.ch0 >= c.ch1) acc.release();
-        for (int ch = c.ch0; ch < c.ch1; ++ch) {
-            float x[32];
-            acc.load32(ch, x);
-            if (ch == c.ch1 - 1) acc.release();
-            const float* sb = c.scratch + 512 + ch * 32;
-            const float* sq = c.scratch + 768 + ch * 32;
+        epi_chunks(
+            acc, c, [](int) {},
+            [&](int ch, float* x) {
+                const float* sb = c.scratch + 512 + ch * 32;
+                const float* sq = c.scratch + 768 + ch * 32;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(sb + j);
-                const float4 q4 = *reinterpret_cast<const float4*>(sq + j);  // zero beyond ncols: no contribution
-                score = fmaf(fast_tanh(x[j] + b4.x), q4.x, score);
-                score = fmaf(fast_tanh(x[j + 1] + b4.y), q4.y, score);
-                score = fmaf(fast_tanh(x[j + 2] + b4.z), q4.z, score);
-                score = fmaf(fast_tanh(x[j + 3] + b4.w), q4.w, score);
-            }
-        }
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = lds_f4(sb + j);
+                    const float4 q4 = lds_f4(sq + j);  // zero beyond ncols: no contribution
+                    score = fmaf(fast_tanh(x[j] + b4.x), q4.x, score);
+                    score = fmaf(fast_tanh(x[j + 1] + b4.y), q4.y, score);
+                    score = fmaf(fast_tanh(x[j + 2] + b4.z), q4.z, score);
+                    score = fmaf(fast_tanh(x[j + 3] + b4.w), q4.w, score);
+                }
+            });
         float* s_part = c.scratch;
         float* s_w = c.scratch + 256;
         s_part[c.half * 128 + c.r] = score;
@@ -228,36 +257,29 @@ struct EpiPool {
             s_w[c.r] = w;
         }
         epi_bar_sync();
+        // out[segment] = sum_t w_t X_t: work item = (segment, 16-byte column chunk); the rows come back from L2 and
+        // the loop keeps 10 (then 4, then 1) independent loads in flight per thread.
         const int row0 = c.tile * rows_per_tile;
         const int nseg = rows_per_tile / seg_len;
-        for (int s = 0; s < nseg; ++s) {
+        const int nck = (D + 7) >> 3;  // the A pitch is a multiple of 8 elements: the last chunk stays in bounds
+        const size_t pitch16 = static_cast<size_t>(lda) >> 3;
+        for (int item = c.tid; item < nseg * nck; item += kEpiThreads) {
+            const int s = item / nck, ck = item - s * nck;
             const int r0 = row0 + s * seg_len;
-            if (r0 >= M) break;
-            const int gs = r0 / seg_len;
-            for (int pidx = c.tid; pidx < (D >> 1); pidx += kEpiThreads) {
-                float a0 = 0.f, a1 = 0.f;
-                const __nv_bfloat16* xp = X + static_cast<size_t>(r0) * lda + 2 * pidx;
-                int t = 0;
-                for (; t + 4 <= seg_len; t += 4) {  // 4 independent L2 loads in flight per thread
-                    uint32_t u[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        u[k] = __ldg(reinterpret_cast<const unsigned int*>(xp + static_cast<size_t>(t + k) * lda));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float2 f = unpack_bf16x2(u[k]);
-                        const float wt = s_w[s * seg_len + t + k];
-                        a0 = fmaf(wt, f.x, a0);
-                        a1 = fmaf(wt, f.y, a1);
-                    }
-                }
-                for (; t < seg_len; ++t) {
-                    const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const unsigned int*>(xp + static_cast<size_t>(t) * lda)));
-                    const float wt = s_w[s * seg_len + t];
-                    a0 = fmaf(wt, f.x, a0);
-                    a1 = fmaf(wt, f.y, a1);
-                }
-                *reinterpret_cast<float2*>(out + static_cast<size_t>(gs) * ldo + 2 * pidx) = make_float2(a0, a1);
+            if (r0 >= M) continue;
+            const uint4* xp = reinterpret_cast<const uint4*>(X + static_cast<size_t>(r0) * lda) + ck;
+            const float* sw = s_w + s * seg_len;
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int t = 0;
+            wsum_rows<10>(xp, pitch16, sw, t, a);
+            wsum_rows<4>(xp, pitch16, sw, t, a);
+            wsum_rows<1>(xp, pitch16, sw, t, a);
+            float* o = out + static_cast<size_t>(r0 / seg_len) * ldo + ck * 8;
+            if (ck * 8 + 8 <= D && (ldo & 3) == 0) {
+                *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(a[4], a[5], a[6], a[7]);
+            } else {
+                for (int j = 0; j < 8 && ck * 8 + j < D; ++j) o[j] = a[j];
             }
         }
         epi_bar_sync();
@@ -270,6 +292,7 @@ struct EpiPool {
 // scratch floats: [0,256) column sums | [256,512) bias | [512,768) query vector
 // ------------------------------------------------------------------------------------------------
 struct EpiDPre {
+    static constexpr int kScratchBytes = 3072;
     const float* bias;
     const float* qv;
     const float* dscore;      // [rows]
@@ -277,61 +300,66 @@ struct EpiDPre {
     int ld;
     float* dqv;               // [q] fp32, accumulated
 
-    __device__ void init(int col0, int ncols, int tid, float* scratch) const {
-        for (int i = tid; i < 256; i += kEpiThreads) {
-            scratch[i] = 0.f;
-            scratch[256 + i] = i < ncols ? bias[col0 + i] : 0.f;
-            scratch[512 + i] = i < ncols ? qv[col0 + i] : 0.f;
+    __device__ void init(const EpiInit& e, int) const {
+        for (int i = e.tid; i < 256; i += kEpiThreads) {
+            e.scratch[i] = 0.f;
+            e.scratch[256 + i] = i < e.ncols ? bias[e.col0 + i] : 0.f;
+            e.scratch[512 + i] = i < e.ncols ? qv[e.col0 + i] : 0.f;
         }
         epi_bar_sync();
     }
-    __device__ void finish(int col0, int ncols, int tid, float* scratch) const {
+    __device__ void finish(const EpiInit& e) const {
         epi_bar_sync();
-        for (int i = tid; i < ncols; i += kEpiThreads) atomicAdd(dqv + col0 + i, scratch[i]);
+        for (int i = e.tid; i < e.ncols; i += kEpiThreads) atomicAdd(dqv + e.col0 + i, e.scratch[i]);
     }
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         const float ds = c.valid ? __ldg(dscore + c.grow) : 0.f;
         const int lane = c.tid & 31;
-        if (c.ch0 >= c.ch1) acc.release();
-        for (int ch = c.ch0; ch < c.ch1; ++ch) {
-            float x[32];
-            acc.load32(ch, x);
-            if (ch == c.ch1 - 1) acc.release();
-            float dp[32];
+        epi_chunks(
+            acc, c, [](int) {},
+            [&](int ch, float* x) {
+                float dp[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = ch * 32 + j;
-                const float qq = c.scratch[512 + col];  // 0 beyond ncols
-                const float tt = (col < c.ncols) ? fast_tanh(x[j] + c.scratch[256 + col]) : 0.f;
-                dp[j] = ds * qq * (1.f - tt * tt);
-                x[j] = ds * tt;
-            }
-            if (c.valid) {
-                __nv_bfloat16* o = dpre + static_cast<size_t>(c.grow) * ld + c.col0 + ch * 32;
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = lds_f4(c.scratch + 256 + ch * 32 + j);
+                    const float4 q4 = lds_f4(c.scratch + 512 + ch * 32 + j);  // 0 beyond ncols
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, qq[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int lc = ch * 32 + g * 16;
-                    if (lc >= c.ncols) break;  // ld is padded to a multiple of 8: whole 8-groups are in bounds
-                    if (lc + 16 <= ld - c.col0 && aligned32(o + g * 16)) {
-                        store_bf16x16(o + g * 16, dp + g * 16);
-                    } else {
-                        store_bf16x8(o + g * 16, dp + g * 16, 8);
-                        if (lc + 8 < c.ncols) store_bf16x8(o + g * 16 + 8, dp + g * 16 + 8, 8);
+                    for (int i = 0; i < 4; ++i) {
+                        const float tt = (ch * 32 + j + i < c.ncols) ? fast_tanh(x[j + i] + bb[i]) : 0.f;
+                        dp[j + i] = ds * qq[i] * (1.f - tt * tt);
+                        x[j + i] = ds * tt;
                     }
                 }
-            }
-            const float colsum = warp_transpose_sum32(x);
-            if (ch * 32 + lane < c.ncols) atomicAdd(c.scratch + ch * 32 + lane, colsum);
-        }
+                if (c.valid) {
+                    __nv_bfloat16* o = dpre + static_cast<size_t>(c.grow) * ld + c.col0 + ch * 32;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const int lc = ch * 32 + g * 16;
+                        if (lc >= c.ncols) break;  // ld is padded to a multiple of 8: whole 8-groups are in bounds
+                        if (lc + 16 <= ld - c.col0 && aligned32(o + g * 16)) {
+                            store_bf16x16(o + g * 16, dp + g * 16);
+                        } else {
+                            store_bf16x8(o + g * 16, dp + g * 16, 8);
+                            if (lc + 8 < c.ncols) store_bf16x8(o + g * 16 + 8, dp + g * 16 + 8, 8);
+                        }
+                    }
+                }
+                const float colsum = warp_transpose_sum32(x);
+                if (ch * 32 + lane < c.ncols) atomicAdd(c.scratch + ch * 32 + lane, colsum);
+            });
     }
 };
 
 // ------------------------------------------------------------------------------------------------
 // dX_rc = acc_rc + w_r * dOut[seg(r)][c]  (pool backward, both paths into X) [* relu mask] [* dropout] -> bf16
-// scratch floats: half*1280 + [segments of this tile][32 columns of the current chunk] (dOut staging per half)
+// scratch floats: two staging buffers of kStageFloats: the dOut rows (slice columns only) of every segment the tile
+// touches, [segment][pitch = slice width]; the buffer of the NEXT tile is filled by cp.async while this one is used.
 // ------------------------------------------------------------------------------------------------
 struct EpiDPoolIn {
+    static constexpr int kStageFloats = 2560;
+    static constexpr int kScratchBytes = 2 * kStageFloats * 4;
     const float* w;      // [rows]
     const float* dout;   // [segments][ldo]
     int ldo;
@@ -347,70 +375,79 @@ struct EpiDPoolIn {
     int M;
     int rows_per_tile;
 
-    __device__ void init(int, int, int, float*) const {}
-    __device__ void finish(int, int, int, float*) const {}
+    // all 256 threads: queue the dOut rows of `tile` (columns [col0, col0 + ncols)) into buf
+    __device__ __forceinline__ void stage_tile(int tile, int col0, int ncols, int tid, float* buf) const {
+        const int row0 = tile * rows_per_tile;
+        const int seg_first = row0 / seg_len;
+        const int seg_last = min(row0 + 127, M - 1) / seg_len;
+        const int total = (seg_last - seg_first + 1) * ncols;
+        for (int i = tid; i < total; i += kEpiThreads) {
+            const int sgi = i / ncols, j = i - sgi * ncols;
+            const bool ok = col0 + j < N;
+            cp_async_f32(buf + i, dout + static_cast<size_t>(seg_first + sgi) * ldo + (ok ? col0 + j : 0), ok);
+        }
+        cp_async_commit();
+    }
+    __device__ void init(const EpiInit& e, int) const {
+        if (e.first_tile < e.num_tiles) stage_tile(e.first_tile, e.col0, e.ncols, e.tid, e.scratch);
+    }
+    __device__ void finish(const EpiInit&) const {}
 
-    // The rows of a segment all need the same dOut row: one coalesced global read per chunk instead of 128 x 32
-    // latency-bound ones.  The two column halves run different chunk counts -> per-half staging and barriers.
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         long long orow;
         int t;
         const bool v = rm.map(c.grow, orow, t) && c.valid;
         const float wr = c.valid ? __ldg(w + c.grow) : 0.f;
-        const int row0 = c.tile * rows_per_tile;
-        const int seg_first = row0 / seg_len;
-        const int seg_last = min(row0 + 127, M - 1) / seg_len;
-        const int nseg = seg_last - seg_first + 1;
+        const int seg_first = (c.tile * rows_per_tile) / seg_len;
         const int myseg = (c.valid ? c.grow / seg_len : seg_first) - seg_first;
-        float* stage = c.scratch + c.half * 1280;
-        const int htid = c.tid & 127;
-        if (c.ch0 >= c.ch1) acc.release();
-        for (int ch = c.ch0; ch < c.ch1; ++ch) {
-            float x[32];
-            acc.load32(ch, x);
-            if (ch == c.ch1 - 1) acc.release();
-            epi_bar_sync_half(c.half);  // previous chunk's readers are done with the staging buffer
-            for (int i = htid; i < nseg * 32; i += 128) {
-                const int sgi = i >> 5, j = i & 31;
-                const int col = c.col0 + ch * 32 + j;
-                stage[i] = (col < N && ch * 32 + j < c.ncols) ? dout[static_cast<size_t>(seg_first + sgi) * ldo + col] : 0.f;
-            }
-            epi_bar_sync_half(c.half);
-            if (!v) continue;
-            const float* sd = stage + myseg * 32;
+        float* cur = c.scratch + (c.it & 1) * kStageFloats;
+        cp_async_wait_all();
+        epi_bar_sync();  // this tile's dOut rows are visible; everybody is done with the other buffer
+        if (c.next_tile >= 0) stage_tile(c.next_tile, c.col0, c.ncols, c.tid, c.scratch + ((c.it + 1) & 1) * kStageFloats);
+        const float* sd = cur + myseg * c.ncols;
+        epi_chunks(
+            acc, c, [](int) {},
+            [&](int ch, float* x) {
+                if (!v) return;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int lc = ch * 32 + g * 8;
-                if (lc >= c.ncols) break;
-                const int col = c.col0 + lc;
-                const int nvalid = min(8, min(c.ncols - lc, N - col));
-                float y[8];
-                const float4 d0 = *reinterpret_cast<const float4*>(sd + g * 8);
-                const float4 d1 = *reinterpret_cast<const float4*>(sd + g * 8 + 4);
-                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                for (int g = 0; g < 4; ++g) {
+                    const int lc = ch * 32 + g * 8;
+                    if (lc >= c.ncols) break;
+                    const int col = c.col0 + lc;
+                    const int nvalid = min(8, min(c.ncols - lc, N - col));
+                    float dd[8];
+                    if (((c.ncols & 3) == 0) && lc + 8 <= c.ncols) {
+                        const float4 d0 = lds_f4(sd + lc), d1 = lds_f4(sd + lc + 4);
+                        dd[0] = d0.x; dd[1] = d0.y; dd[2] = d0.z; dd[3] = d0.w;
+                        dd[4] = d1.x; dd[5] = d1.y; dd[6] = d1.z; dd[7] = d1.w;
+                    } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = (j < nvalid) ? fmaf(wr, dd[j], x[g * 8 + j]) : 0.f;
-                if (relu_src != nullptr) {
-                    const uint4 ru = *reinterpret_cast<const uint4*>(relu_src + static_cast<size_t>(c.grow) * relu_ld + col);
-                    const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = unpack_bf16x2(rw[j]);
-                        if (!(f.x > 0.f)) y[2 * j] = 0.f;
-                        if (!(f.y > 0.f)) y[2 * j + 1] = 0.f;
+                        for (int j = 0; j < 8; ++j) dd[j] = (j < nvalid) ? lds_f(sd + lc + j) : 0.f;
                     }
-                }
-                if (drop.p > 0.f) {
-                    float m[8];
-                    drop.mask4(c.grow, relu_src != nullptr ? relu_ld : ld, col, m);
-                    drop.mask4(c.grow, relu_src != nullptr ? relu_ld : ld, col + 4, m + 4);
+                    float y[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) y[j] *= m[j];
+                    for (int j = 0; j < 8; ++j) y[j] = (j < nvalid) ? fmaf(wr, dd[j], x[g * 8 + j]) : 0.f;
+                    if (relu_src != nullptr) {
+                        const uint4 ru = *reinterpret_cast<const uint4*>(relu_src + static_cast<size_t>(c.grow) * relu_ld + col);
+                        const uint32_t rw[4] = {ru.x, ru.y, ru.z, ru.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = unpack_bf16x2(rw[j]);
+                            if (!(f.x > 0.f)) y[2 * j] = 0.f;
+                            if (!(f.y > 0.f)) y[2 * j + 1] = 0.f;
+                        }
+                    }
+                    if (drop.p > 0.f) {
+                        float m[8];
+                        drop.mask4(c.grow, relu_src != nullptr ? relu_ld : ld, col, m);
+                        drop.mask4(c.grow, relu_src != nullptr ? relu_ld : ld, col + 4, m + 4);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[j] *= m[j];
+                    }
+                    store_bf16x8(dx + orow * ld + col, y, nvalid);
                 }
-                store_bf16x8(dx + orow * ld + col, y, nvalid);
-            }
-        }
+            });
         if (v && c.col0 == 0 && c.half == 0 && zero_pad_rows) {
             if (t == 0) zero_row_bf16(dx + (orow - 1) * ld, ld);
             if (t == rm.seg_len - 1) zero_row_bf16(dx + (orow + 1) * ld, ld);
@@ -422,6 +459,7 @@ struct EpiDPoolIn {
 // Embedding gradient: dEmb[ids[r]][c] += acc_rc [* dropout of the gathered row]; row 0 (padding_idx) skipped
 // ------------------------------------------------------------------------------------------------
 struct EpiScatter {
+    static constexpr int kScratchBytes = 16;
     const long long* ids;  // [rows] token ids (row-mapped through rm for the padded CNN layout)
     float* demb;           // [V][D] fp32
     int D;
@@ -429,8 +467,8 @@ struct EpiScatter {
     Dropout drop;
     int drop_ld;           // pitch used when the forward mask was drawn
 
-    __device__ void init(int, int, int, float*) const {}
-    __device__ void finish(int, int, int, float*) const {}
+    __device__ void init(const EpiInit&, int) const {}
+    __device__ void finish(const EpiInit&) const {}
 
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
@@ -439,32 +477,30 @@ struct EpiScatter {
         const bool v = rm.map(c.grow, trow, t) && c.valid;
         const long long id = v ? ids[trow] : 0;
         float* dst = demb + static_cast<size_t>(id) * D;
-        if (c.ch0 >= c.ch1) acc.release();
-        for (int ch = c.ch0; ch < c.ch1; ++ch) {
-            float x[32];
-            acc.load32(ch, x);
-            if (ch == c.ch1 - 1) acc.release();
-            if (id == 0) continue;
+        epi_chunks(
+            acc, c, [](int) {},
+            [&](int ch, float* x) {
+                if (id == 0) return;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                const int lc = ch * 32 + g * 4;
-                if (lc >= c.ncols) break;
-                const int col = c.col0 + lc;
-                float y[4] = {x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]};
-                if (drop.p > 0.f) {
-                    float m[4];
-                    drop.mask4(c.grow, drop_ld, col, m);
+                for (int g = 0; g < 8; ++g) {
+                    const int lc = ch * 32 + g * 4;
+                    if (lc >= c.ncols) break;
+                    const int col = c.col0 + lc;
+                    float y[4] = {x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]};
+                    if (drop.p > 0.f) {
+                        float m[4];
+                        drop.mask4(c.grow, drop_ld, col, m);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) y[j] *= m[j];
+                        for (int j = 0; j < 4; ++j) y[j] *= m[j];
+                    }
+                    if (col + 4 <= D && lc + 4 <= c.ncols) {
+                        red_add_v4_f32(dst + col, y[0], y[1], y[2], y[3]);
+                    } else {
+                        for (int j = 0; j < 4; ++j)
+                            if (col + j < D && lc + j < c.ncols) red_add_f32(dst + col + j, y[j]);
+                    }
                 }
-                if (col + 4 <= D && lc + 4 <= c.ncols) {
-                    red_add_v4_f32(dst + col, y[0], y[1], y[2], y[3]);
-                } else {
-                    for (int j = 0; j < 4; ++j)
-                        if (col + j < D && lc + j < c.ncols) red_add_f32(dst + col + j, y[j]);
-                }
-            }
-        }
+            });
     }
 };
 

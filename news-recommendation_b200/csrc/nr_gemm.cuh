@@ -1,18 +1,19 @@
 // Weight-stationary persistent tcgen05 GEMMs for the news-recommendation hot path (sm_100a).
 //
 //  gemm_nt : D[M x N] = A[M x K] . B[N x K]^T      (both K-major; "activation x weight^T")
-//            * the CTA's weight slice (<=256 output columns, all K, all conv taps) is loaded ONCE by
-//              TMA and stays resident in shared memory; 128-row activation tiles stream through a
-//              TMA/mbarrier ring; accumulators are double buffered in TMEM (2 x 256 fp32 columns);
-//              4 epilogue warps run a fused epilogue functor on tcgen05.ld'ed rows.
+//            * a CTA pair's weight slice (<=256 output columns, all K, all conv taps; half the rows in
+//              each CTA) is loaded ONCE by TMA and stays resident in shared memory; 128-row activation
+//              tiles stream through a TMA/mbarrier ring; accumulators are double buffered in TMEM
+//              (2 x 256 fp32 columns); 8 epilogue warps run a fused epilogue functor on tcgen05.ld'ed rows.
 //            * conv taps: tap s re-loads the A tile shifted by (s - taps/2) rows (zero rows separate
 //              the segments in the padded layout), accumulating into the same TMEM tile.
 //  gemm_tn : D[Ma x Nb] += A[Kr x Ma]^T . B[Kr x Nb]  (both MN-major; weight gradients, Kr = all tokens)
 //            split over Kr across CTAs, fp32 red.global.add epilogue.
 //
-// Warp roles of gemm_nt (320 threads): warps 0-7 epilogue (TMEM lane quarter = warp & 3; the two warps of a quarter
-// split the accumulator columns -- with 4 warps the row-per-thread epilogue was latency bound at ~20 % issue
-// utilisation, ncu profiles/), warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+// Warp roles of gemm_nt (320 threads per CTA, CTAs launched as pairs): warps 0-7 epilogue (TMEM lane quarter =
+// warp & 3; the two warps of a quarter split the accumulator columns -- with 4 warps the row-per-thread epilogue was
+// latency bound at ~20 % issue utilisation, ncu profiles/), warp 8 TMA producer, warp 9 TMEM allocator and, in the
+// leader CTA, MMA issuer.
 // gemm_tn keeps 192 threads (4 epilogue warps, one-shot epilogue).
 #pragma once
 #include "nr_common.cuh"
@@ -25,8 +26,7 @@ constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                     // bf16 elements per 128-byte swizzle row
 constexpr int kAStageBytes = kTileM * 128;      // 16 KB
-constexpr int kMaxStages = 8;
-constexpr int kEpiScratchBytes = 10240;
+constexpr int kMaxStages = 12;
 constexpr int kSmemLimit = 232448;              // 227 KB
 
 struct GemmNTParams {
@@ -44,6 +44,7 @@ struct GemmNTParams {
     int stages;
     float* dbg_acc;     // debug backend only: fp32 accumulators [num_m_tiles*128][dbg_ld]
     int dbg_ld;
+    long long* timing;  // tuning only (nr_debug_set_gemm_timing): per CTA 16 cycle counters, see the kernel
 };
 
 // What an epilogue functor sees for one (tile,row).
@@ -57,7 +58,16 @@ struct EpiCtx {
     int tid;      // 0..255 within the epilogue group
     int half;     // 0 / 1: which of the two warps of this TMEM lane quarter
     int ch0, ch1; // this thread's range of 32-column chunks
-    float* scratch;  // kEpiScratchBytes of shared memory private to the epilogue group
+    float* scratch;  // Epi::kScratchBytes of shared memory private to the epilogue group
+    int it;          // how many tiles this CTA has finished before this one (double-buffer parity)
+    int next_tile;   // the tile this CTA processes next, or -1
+};
+// What init()/finish() see.
+struct EpiInit {
+    int col0, ncols, tid;
+    float* scratch;
+    int first_tile;  // first tile of this CTA (>= num_tiles: the CTA has no work)
+    int num_tiles;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -71,14 +81,18 @@ __device__ __forceinline__ void epi_chunk_range(int ncols, int half, int& ch0, i
 
 struct TmemAcc {
     uint32_t taddr;
-    uint64_t* release_bar;
+    uint32_t release_bar;  // shared::cluster address of the leader CTA's "accumulator free" barrier
     __device__ __forceinline__ void load32(int chunk, float* v) const {
         tmem_ld32(taddr + chunk * 32, v);
         tmem_ld_wait();
     }
-    __device__ __forceinline__ void release() const {  // all TMEM reads of this tile by this thread are done
+    __device__ __forceinline__ void issue32(int chunk, float* v) const { tmem_ld32(taddr + chunk * 32, v); }
+    __device__ __forceinline__ void wait32(float* v) const { tmem_ld_wait32(v); }
+    // All TMEM reads of this tile by this WARP are done (every call site is warp-uniform): one arrival per warp.
+    __device__ __forceinline__ void release() const {
         tc_fence_before();
-        mbar_arrive(release_bar);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(release_bar);
     }
 };
 struct GlobalAcc {  // debug backend: accumulators computed by a plain SIMT kernel
@@ -87,22 +101,63 @@ struct GlobalAcc {  // debug backend: accumulators computed by a plain SIMT kern
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = row[chunk * 32 + j];
     }
+    __device__ __forceinline__ void issue32(int chunk, float* v) const { load32(chunk, v); }
+    __device__ __forceinline__ void wait32(float*) const {}
     __device__ __forceinline__ void release() const {}
 };
 
+// The chunk loop every epilogue shares, software pipelined over two register buffers: the tcgen05.ld of chunk i+1 is
+// in flight while body(i) runs (a single-buffered loop exposed the TMEM round trip once per chunk).  pre(ch) runs
+// before the wait of chunk ch (shared-memory operand loads go there).  Calls acc.release() exactly once, right after
+// the last chunk has landed in registers.
+template <class Acc, class Pre, class Body>
+__device__ __forceinline__ void epi_chunks(const Acc& acc, const EpiCtx& c, Pre&& pre, Body&& body) {
+    if (c.ch0 >= c.ch1) {
+        acc.release();
+        return;
+    }
+    float xa[32], xb[32];
+    acc.issue32(c.ch0, xa);
+    for (int ch = c.ch0; ch < c.ch1; ch += 2) {
+        pre(ch);
+        acc.wait32(xa);
+        if (ch + 1 < c.ch1) acc.issue32(ch + 1, xb); else acc.release();
+        body(ch, xa);
+        if (ch + 1 < c.ch1) {
+            pre(ch + 1);
+            acc.wait32(xb);
+            if (ch + 2 < c.ch1) acc.issue32(ch + 2, xa); else acc.release();
+            body(ch + 1, xb);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// gemm_nt kernel
+// gemm_nt kernel: one CTA PAIR (cluster of 2, tcgen05 cta_group::2) per (256-row block, weight slice)
 // ---------------------------------------------------------------------------------------------
+// Both CTAs stream their own 128-row activation tiles and hold HALF of the slice's weight rows; the leader (cluster rank
+// 0) issues M=256 MMAs that read A and B from both CTAs' shared memory and leave rows 0-127 of D in its own TMEM, rows
+// 128-255 in the peer's.  Halving the resident weight bytes is what buys the A ring its depth: with 4 stages the ring
+// was latency bound (a stage is refilled only after its MMAs retire; (TMA latency + MMA time) / stages > MMA time).
+// mbarrier protocol (every barrier exists in both CTAs at the same offset; "L" = only the leader's copy is used):
+//   bfull  L  count 1 + tx of both weight halves        -> MMA issuer may start
+//   full[s] L count 1 + tx of both CTAs' A boxes         (leader's producer arrives with expect_tx of 2 boxes; the
+//                                                         peer's TMA signals the leader's barrier, cta_group::2)
+//   empty[s]  count 1, multicast tcgen05.commit          -> each CTA's producer refills its own stage s
+//   tfull[a]  count 1, multicast tcgen05.commit          -> each CTA's epilogue reads its own TMEM rows
+//   tempty[a] L count 16 (8 epilogue warps x 2 CTAs, the peer arrives through shared::cluster)
 template <class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmNTParams p,
                const Epi epi) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
 
-    const int b_region = p.n_box * 128;  // bytes of one (tap, k-chunk) weight box
+    const int b_region = (p.n_box >> 1) * 128;  // bytes of one (tap, k-chunk) box of this CTA's weight half
     uint8_t* sB = smem;
     uint8_t* sA = sB + p.taps * p.k_chunks * b_region;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * kAStageBytes);
@@ -114,13 +169,30 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
     float* scratch = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);
 
-    const int slice = blockIdx.x % p.n_slices;
-    const int tile0 = blockIdx.x / p.n_slices;
-    const int tile_step = gridDim.x / p.n_slices;
+    const int pair = blockIdx.x >> 1;
+    const int slice = pair % p.n_slices;
+    const int ptile0 = pair / p.n_slices;                // pair tile = 256 rows_per_tile-rows: tiles 2*pt and 2*pt + 1
+    const int ptile_step = (gridDim.x >> 1) / p.n_slices;
+    const int num_ptiles = (p.num_m_tiles + 1) >> 1;
     const int col0 = slice * p.n_stride;
     const int ncols = min(p.n_stride, p.N - col0);
-    const int n_mma = (ncols + 15) & ~15;
+    const int n_mma = (ncols + 15) & ~15;                // MMA N of this slice; each CTA supplies n_mma/2 weight rows
     const int tap_shift = p.taps / 2;
+    // tuning counters: [0] producer waits for a free A stage, [1] MMA waits for A data, [2] MMA waits for a free
+    // accumulator, [3] epilogue waits for a finished accumulator, [4] epilogue body, [5] kernel, [6] tiles,
+    // [7] MMA issue loops, [8] tcgen05.commit
+    long long* tmr = p.timing != nullptr ? p.timing + blockIdx.x * 16 : nullptr;
+    const long long t_begin = tmr != nullptr ? clock64() : 0;
+    long long tw_a = 0, tw_b = 0, tw_c = 0, tw_d = 0;
+    auto timed_wait = [&](uint64_t* bar, uint32_t parity, int code, long long& acc_t) {
+        if (tmr != nullptr) {
+            const long long t = clock64();
+            mbar_wait(bar, parity, code);
+            acc_t += clock64() - t;
+        } else {
+            mbar_wait(bar, parity, code);
+        }
+    };
 
     if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -132,80 +204,93 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(bfull, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], kEpiThreads);
+            mbar_init(&tempty[i], 2 * (kEpiThreads / 32));
         }
         fence_barrier_init();
     } else if (warp == 9) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc_pair(tmem_slot, 512);
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
-            mbar_arrive_expect_tx(bfull, static_cast<uint32_t>(p.taps * p.k_chunks * b_region));
+            const uint32_t bfull_l = mapa_shared(bfull, 0);
+            if (leader) mbar_arrive_expect_tx(bfull, static_cast<uint32_t>(2 * p.taps * p.k_chunks * b_region));
             for (int s = 0; s < p.taps; ++s)
                 for (int kc = 0; kc < p.k_chunks; ++kc)
-                    tma_load_2d(sB + (s * p.k_chunks + kc) * b_region, &tmB, bfull, kc * kChunkK,
-                                s * p.b_tap_rows + col0);
+                    tma_load_2d_pair(sB + (s * p.k_chunks + kc) * b_region, &tmB, bfull_l, kc * kChunkK,
+                                     s * p.b_tap_rows + col0 + static_cast<int>(rank) * (n_mma >> 1));
             int st = 0;
             uint32_t ph = 0;
-            for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step) {
-                const int row0 = tile * p.rows_per_tile;
+            for (int pt = ptile0; pt < num_ptiles; pt += ptile_step) {
+                const int row0 = (2 * pt + static_cast<int>(rank)) * p.rows_per_tile;  // past M: zero filled
                 for (int s = 0; s < p.taps; ++s)
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty[st], ph ^ 1, 101);
-                        mbar_arrive_expect_tx(&full[st], kAStageBytes);
-                        tma_load_2d(sA + st * kAStageBytes, &tmA, &full[st], kc * kChunkK, row0 + s - tap_shift);
+                        timed_wait(&empty[st], ph ^ 1, 101, tw_a);
+                        if (leader) mbar_arrive_expect_tx(&full[st], 2 * kAStageBytes);
+                        tma_load_2d_pair(sA + st * kAStageBytes, &tmA, mapa_shared(&full[st], 0), kc * kChunkK,
+                                         row0 + s - tap_shift);
                         if (++st == p.stages) { st = 0; ph ^= 1; }
                     }
             }
+            if (tmr != nullptr) tmr[0] = tw_a;
         }
     } else if (warp == 9) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(kTileM, n_mma, 0, 0);
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_bf16(2 * kTileM, n_mma, 0, 0);
             mbar_wait(bfull, 0, 102);
             tc_fence_after();
             int st = 0;
             uint32_t ph = 0;
             int it = 0;
-            for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step, ++it) {
+            for (int pt = ptile0; pt < num_ptiles; pt += ptile_step, ++it) {
                 const int as = it & 1;
-                mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1, 103);
+                timed_wait(&tempty[as], ((it >> 1) & 1) ^ 1, 103, tw_b);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256;
                 uint32_t acc = 0;
                 for (int s = 0; s < p.taps; ++s)
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&full[st], ph, 104);
+                        timed_wait(&full[st], ph, 104, tw_a);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(sA + st * kAStageBytes);
                         const uint32_t b_addr = smem_u32(sB + (s * p.k_chunks + kc) * b_region);
                         const int ksteps = min(4, (p.K - kc * kChunkK + 15) >> 4);
+                        const long long t_i0 = tmr != nullptr ? clock64() : 0;
                         for (int k = 0; k < ksteps; ++k) {
-                            umma_bf16(d_tmem, make_sw128_desc(a_addr + k * 32, 0, 1024),
-                                      make_sw128_desc(b_addr + k * 32, 0, 1024), idesc, acc);
+                            umma_bf16_pair(d_tmem, make_sw128_desc(a_addr + k * 32, 0, 1024),
+                                           make_sw128_desc(b_addr + k * 32, 0, 1024), idesc, acc);
                             acc = 1;
                         }
-                        umma_commit(&empty[st]);  // frees the A stage when these MMAs retire
+                        const long long t_i1 = tmr != nullptr ? clock64() : 0;
+                        umma_commit_pair(&empty[st]);  // frees stage st in both CTAs when these MMAs retire
+                        if (tmr != nullptr) { tw_c += t_i1 - t_i0; tw_d += clock64() - t_i1; }
                         if (++st == p.stages) { st = 0; ph ^= 1; }
                     }
-                umma_commit(&tfull[as]);
+                umma_commit_pair(&tfull[as]);
             }
+            if (tmr != nullptr) { tmr[1] = tw_a; tmr[2] = tw_b; tmr[7] = tw_c; tmr[8] = tw_d; }
         }
     } else {
-        // ===================== epilogue warps 0..7 =====================
-        epi.init(col0, ncols, threadIdx.x, scratch);
+        // ===================== epilogue warps 0..7 (both CTAs, own TMEM rows) =====================
+        const int tile_step = 2 * ptile_step;
+        const EpiInit ei{col0, ncols, static_cast<int>(threadIdx.x), scratch, 2 * ptile0 + static_cast<int>(rank), p.num_m_tiles};
+        epi.init(ei, tile_step);
         const int quarter = warp & 3;
+        const uint32_t tempty_l[2] = {mapa_shared(&tempty[0], 0), mapa_shared(&tempty[1], 0)};
         int it = 0;
-        for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step, ++it) {
+        for (int pt = ptile0; pt < num_ptiles; pt += ptile_step, ++it) {
+            const int tile = 2 * pt + static_cast<int>(rank);  // may be one past the last tile: every row invalid
             const int as = it & 1;
-            mbar_wait(&tfull[as], (it >> 1) & 1, 105);
+            timed_wait(&tfull[as], (it >> 1) & 1, 105, tw_a);
             tc_fence_after();
+            const long long t_epi = tmr != nullptr ? clock64() : 0;
             EpiCtx c;
             c.tile = tile;
             c.r = quarter * 32 + lane;
@@ -217,15 +302,20 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             c.half = warp >> 2;
             epi_chunk_range(ncols, c.half, c.ch0, c.ch1);
             c.scratch = scratch;
-            TmemAcc acc{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 256, &tempty[as]};
+            c.it = it;
+            c.next_tile = tile + tile_step < p.num_m_tiles ? tile + tile_step : -1;
+            TmemAcc acc{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 256, tempty_l[as]};
             epi(acc, c);
+            if (tmr != nullptr) tw_b += clock64() - t_epi;
         }
-        epi.finish(col0, ncols, threadIdx.x, scratch);
+        epi.finish(ei);
+        if (tmr != nullptr && threadIdx.x == 0) { tmr[3] = tw_a; tmr[4] = tw_b; tmr[5] = clock64() - t_begin; tmr[6] = it; }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    cluster_sync_all();  // nobody leaves (or frees TMEM) while the partner may still read its shared memory / signal it
+    if (warp == 9) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // Debug backend (triage only, NR_DEBUG_SIMT_GEMM=1): plain SIMT accumulate + the SAME epilogue functors.
@@ -233,16 +323,18 @@ __global__ void gemm_nt_simt_acc_kernel(const __nv_bfloat16* A, int lda, const _
                                         GemmNTParams p);
 template <class Epi>
 __global__ void __launch_bounds__(kEpiThreads, 1) gemm_nt_simt_epi_kernel(const GemmNTParams p, const Epi epi) {
-    __shared__ float scratch[kEpiScratchBytes / 4];
+    __shared__ __align__(16) float scratch[Epi::kScratchBytes / 4];
     const int slice = blockIdx.x % p.n_slices;
     const int tile0 = blockIdx.x / p.n_slices;
     const int tile_step = gridDim.x / p.n_slices;
     const int col0 = slice * p.n_stride;
     const int ncols = min(p.n_stride, p.N - col0);
-    for (int i = threadIdx.x; i < kEpiScratchBytes / 4; i += kEpiThreads) scratch[i] = 0.f;
+    for (int i = threadIdx.x; i < Epi::kScratchBytes / 4; i += kEpiThreads) scratch[i] = 0.f;
     __syncthreads();
-    epi.init(col0, ncols, threadIdx.x, scratch);
-    for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step) {
+    const EpiInit ei{col0, ncols, static_cast<int>(threadIdx.x), scratch, tile0, p.num_m_tiles};
+    epi.init(ei, tile_step);
+    int it = 0;
+    for (int tile = tile0; tile < p.num_m_tiles; tile += tile_step, ++it) {
         EpiCtx c;
         c.tile = tile;
         c.r = threadIdx.x & 127;
@@ -254,10 +346,12 @@ __global__ void __launch_bounds__(kEpiThreads, 1) gemm_nt_simt_epi_kernel(const 
         c.half = threadIdx.x >> 7;
         epi_chunk_range(ncols, c.half, c.ch0, c.ch1);
         c.scratch = scratch;
+        c.it = it;
+        c.next_tile = tile + tile_step < p.num_m_tiles ? tile + tile_step : -1;
         GlobalAcc acc{p.dbg_acc + (static_cast<size_t>(tile) * 128 + c.r) * p.dbg_ld + col0};
         epi(acc, c);
     }
-    epi.finish(col0, ncols, threadIdx.x, scratch);
+    epi.finish(ei);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,8 +385,10 @@ struct GemmNTPlan {
     size_t smem;
 };
 // Fills slices/boxes/stages and encodes the tensor maps.  A: [M rows][K] pitch lda; B: [taps*b_tap_rows][K] pitch ldb.
+// scratch_bytes = Epi::kScratchBytes; max_n_stride (0 = none) caps the slice width for epilogues whose staging
+// grows with it.
 int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B, int N, int ldb, int K, int taps,
-                 int b_tap_rows, int rows_per_tile, int num_sms, int max_slices);
+                 int b_tap_rows, int rows_per_tile, int num_sms, int max_slices, int scratch_bytes, int max_n_stride);
 bool debug_simt_gemm();
 
 template <class Epi>

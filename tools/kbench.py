@@ -50,8 +50,18 @@ demb_big = None
 names = sys.argv[1:] or ["mhsa_fwd", "mhsa_fwd_drop", "mhsa_bwd", "qkv", "pool", "tn900", "tn200", "gather"]
 if "dx_fp32" in names:
     demb_big = torch.empty(n_tok, d, device=dev)
+def lin_op(spec):
+    """lin:N:K[:bf16out] -> nr_linear at M = n_tok with fresh operands"""
+    parts = spec.split(":")
+    N, K = int(parts[1]), int(parts[2])
+    lda, ldo = ru8(K + 1), ru16(N)
+    A, W, O = bf(n_tok, lda), bf(N, lda), torch.empty(n_tok, ldo, device=dev, dtype=torch.bfloat16)
+    b = torch.randn(N, device=dev)
+    return lambda: lib.nr_linear(_p(A), n_tok, lda, _p(W), N, lda, K, 1, 0, 128, _p(b), 0, _p(O), ldo, 1, st)
+
+
 for name in names:
-    fn = OPS[name]
+    fn = lin_op(name) if name.startswith("lin:") else OPS[name]
     for _ in range(2):
         check(fn(), name)
     ts = []
