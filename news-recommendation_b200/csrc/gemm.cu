@@ -163,19 +163,21 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_cols,
-                      int box_rows) {
+                      int box_rows, int swizzle_bytes) {
     EncodeTiledFn enc = get_encode();
     NR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
     NR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16B aligned", base);
     NR_REQUIRE((ld_elems * 2) % 16 == 0, "TMA row pitch %lld elements is not a multiple of 16 bytes", (long long)ld_elems);
-    NR_REQUIRE(box_cols * 2 <= 128 && box_rows <= 256 && box_rows >= 1, "bad TMA box %d x %d", box_cols, box_rows);
+    NR_REQUIRE(box_cols * 2 <= swizzle_bytes && (swizzle_bytes == 128 || swizzle_bytes == 64) && box_rows <= 256 && box_rows >= 1,
+               "bad TMA box %d x %d (swizzle %d)", box_cols, box_rows, swizzle_bytes);
     NR_REQUIRE(rows >= 1 && cols >= 1, "empty tensor for TMA (%lld x %lld)", (long long)rows, (long long)cols);
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
                (int)r, (long long)rows, (long long)cols, (long long)ld_elems, box_cols, box_rows);
@@ -452,6 +454,9 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
     NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0, EpiStore::kScratchBytes, 0));
     NR_REQUIRE(out_bf16 ? (ld_out % 8 == 0) : (ld_out % 4 == 0), "gemm_store: output pitch %d breaks vector stores", ld_out);
     EpiStore e;
+    memset(&e, 0, sizeof(e));
+    e.use_tma = (out_bf16 && rm.seg_in == 0 && rows_per_tile == kTileM && N >= 32) ? 1 : 0;
+    if (e.use_tma) NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_out, out, M, N, ld_out, 32, 32, 64));
     e.out = out;
     e.ld = ld_out;
     e.out_bf16 = out_bf16;
@@ -505,6 +510,9 @@ int gemm_additive_dpre(const void* X, int M, int lda, int D, const void* Wa, int
     NR_PROPAGATE(plan_gemm_nt(&plan, X, M, lda, Wa, q, ldw, D, 1, 0, kTileM, num_sms(), 1, EpiDPre::kScratchBytes, 0));
     NR_REQUIRE(plan.p.n_slices == 1, "additive_dpre: q=%d D=%d does not fit one weight slice", q, D);
     EpiDPre e;
+    memset(&e, 0, sizeof(e));
+    e.use_tma = q >= 32 ? 1 : 0;
+    if (e.use_tma) NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_out, dpre, M, ld_dpre, ld_dpre, 32, 32, 64));
     e.bias = ba;
     e.qv = qv;
     e.dscore = dscore;
@@ -530,6 +538,9 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
                               EpiDPoolIn::kScratchBytes, max_stride));
     NR_REQUIRE(ld_dx % 8 == 0, "pool_dinput: ld_dx=%d", ld_dx);
     EpiDPoolIn e;
+    memset(&e, 0, sizeof(e));
+    e.use_tma = (rm.seg_in == 0 && relu_src == nullptr && D >= 32) ? 1 : 0;
+    if (e.use_tma) NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_out, dx, M, D, ld_dx, 32, 32, 64));
     e.w = w;
     e.dout = dout;
     e.ldo = ldo;

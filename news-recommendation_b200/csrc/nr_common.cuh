@@ -122,6 +122,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// TMA store of one box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N groups of this thread still reading shared memory
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) ----------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -138,7 +152,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default (.release.cta) form, as CUTLASS's umma_arrive_2x1SM_sm0: the .release.cluster form compiles to
+    // MEMBAR.ALL.CTA + ERRBAR in front of the arrive and cost the epilogue warps a third of their time (ncu, profiles/);
+    // the TMEM reads this arrival publishes are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are counted on the mbarrier at
 // bar_cluster_addr, which may live in the peer (leader) CTA.
@@ -334,8 +351,9 @@ __device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t group)
 // ----------------------------------------------------------------------------------------------
 // host: TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency)
 // ----------------------------------------------------------------------------------------------
-// 2-D bf16 tensor [rows][cols] with row pitch ld (elements), box = [box_cols(<=64) x box_rows], 128B swizzle.
+// 2-D bf16 tensor [rows][cols] with row pitch ld (elements), box = [box_cols(<=64) x box_rows];
+// swizzle_bytes = 128 (operand tiles, box_cols <= 64) or 64 (epilogue store tiles, box_cols <= 32).
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_cols,
-                      int box_rows);
+                      int box_rows, int swizzle_bytes = 128);
 
 }  // namespace nr

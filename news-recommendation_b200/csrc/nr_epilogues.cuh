@@ -64,17 +64,21 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* o, const float* y, i
     if (nvalid == 8) {
         *reinterpret_cast<uint4*>(o) =
             make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
-    } else {
-        for (int j = 0; j < nvalid; ++j) o[j] = __float2bfloat16_rn(y[j]);
+    } else {  // fully unrolled + predicated: a run-time index into y would push the caller's accumulator registers to local memory
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nvalid) o[j] = __float2bfloat16_rn(y[j]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // out = act(acc + bias) [* dropout]  ->  bf16 or fp32, optional row re-map, optional "ones" column
-// scratch floats: [0,256) bias of the slice
+// scratch floats: [0,256) bias of the slice | then the WarpTileStore staging region
 // ------------------------------------------------------------------------------------------------
 struct EpiStore {
-    static constexpr int kScratchBytes = 1024;
+    static constexpr int kScratchBytes = 1024 + kTileStoreBytes;
+    CUtensorMap tm_out;  // bf16 output as a TMA tensor (32 x 32 boxes, SWIZZLE_64B); valid when use_tma
+    int use_tma;         // identity row map + bf16 output: full 32-column chunks leave through WarpTileStore
     void* out;
     int ld;
     int out_bf16;
@@ -92,7 +96,9 @@ struct EpiStore {
         for (int i = e.tid; i < 256; i += kEpiThreads) e.scratch[i] = (bias != nullptr && i < e.ncols) ? bias[e.col0 + i] : 0.f;
         epi_bar_sync();
     }
-    __device__ void finish(const EpiInit&) const {}
+    __device__ void finish(const EpiInit& e) const {
+        if (use_tma) WarpTileStore::drain(e.tid & 31);
+    }
 
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
@@ -102,6 +108,12 @@ struct EpiStore {
         if (dbg_skip) {
             acc.release();
             return;
+        }
+        const int lane = c.tid & 31;
+        WarpTileStore ts;
+        if (use_tma) {
+            ts.attach(c.scratch + 256, c.tid >> 5);
+            ts.begin_tile(lane);
         }
         float b[32];
         epi_chunks(
@@ -114,27 +126,36 @@ struct EpiStore {
                 }
             },
             [&](int ch, float* x) {
-                if (!v) return;
+                const int lc0 = ch * 32;
+                const bool whole = use_tma && lc0 + 32 <= c.ncols;  // warp-uniform
+                if (!whole && !v) return;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] += b[j];
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (drop.p > 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float m[4];
+                        drop.mask4(orow, ld, c.col0 + lc0 + j, m);
+                        x[j] *= m[0]; x[j + 1] *= m[1]; x[j + 2] *= m[2]; x[j + 3] *= m[3];
+                    }
+                }
+                if (whole) {  // columns >= N and rows >= M are clipped by the tensor map
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+                    ts.put(&tm_out, w, c.col0 + lc0, c.grow - lane, lane);
+                    return;
+                }
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
-                    const int lc = ch * 32 + g * 16;  // column inside the slice
+                    const int lc = lc0 + g * 16;  // column inside the slice
                     if (lc >= c.ncols) break;
                     const int col = c.col0 + lc;
-                    float y[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) y[j] = x[g * 16 + j] + b[g * 16 + j];
-                    if (relu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-                    }
-                    if (drop.p > 0.f) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float m[4];
-                            drop.mask4(orow, ld, col + j, m);
-                            y[j] *= m[0]; y[j + 1] *= m[1]; y[j + 2] *= m[2]; y[j + 3] *= m[3];
-                        }
-                    }
+                    const float* y = x + g * 16;
                     const int nvalid = min(16, min(c.ncols - lc, N - col));
                     if (out_bf16) {
                         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + orow * ld + col;
@@ -150,7 +171,9 @@ struct EpiStore {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
                         } else {
-                            for (int j = 0; j < nvalid; ++j) o[j] = y[j];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < nvalid) o[j] = y[j];
                         }
                     }
                 }
@@ -292,7 +315,9 @@ struct EpiPool {
 // scratch floats: [0,256) column sums | [256,512) bias | [512,768) query vector
 // ------------------------------------------------------------------------------------------------
 struct EpiDPre {
-    static constexpr int kScratchBytes = 3072;
+    static constexpr int kScratchBytes = 3072 + kTileStoreBytes;
+    CUtensorMap tm_out;       // dpre as a TMA tensor (32 x 32 boxes); valid when use_tma
+    int use_tma;
     const float* bias;
     const float* qv;
     const float* dscore;      // [rows]
@@ -311,11 +336,17 @@ struct EpiDPre {
     __device__ void finish(const EpiInit& e) const {
         epi_bar_sync();
         for (int i = e.tid; i < e.ncols; i += kEpiThreads) atomicAdd(dqv + e.col0 + i, e.scratch[i]);
+        if (use_tma) WarpTileStore::drain(e.tid & 31);
     }
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
         const float ds = c.valid ? __ldg(dscore + c.grow) : 0.f;
         const int lane = c.tid & 31;
+        WarpTileStore ts;
+        if (use_tma) {
+            ts.attach(c.scratch + 768, c.tid >> 5);
+            ts.begin_tile(lane);
+        }
         epi_chunks(
             acc, c, [](int) {},
             [&](int ch, float* x) {
@@ -332,7 +363,12 @@ struct EpiDPre {
                         x[j + i] = ds * tt;
                     }
                 }
-                if (c.valid) {
+                if (use_tma && ch * 32 + 32 <= c.ncols) {  // invalid rows carry ds = 0 and are clipped at M anyway
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(dp[2 * j], dp[2 * j + 1]);
+                    ts.put(&tm_out, w, c.col0 + ch * 32, c.grow - lane, lane);
+                } else if (c.valid) {
                     __nv_bfloat16* o = dpre + static_cast<size_t>(c.grow) * ld + c.col0 + ch * 32;
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
@@ -359,7 +395,9 @@ struct EpiDPre {
 // ------------------------------------------------------------------------------------------------
 struct EpiDPoolIn {
     static constexpr int kStageFloats = 2560;
-    static constexpr int kScratchBytes = 2 * kStageFloats * 4;
+    static constexpr int kScratchBytes = 2 * kStageFloats * 4 + kTileStoreBytes;
+    CUtensorMap tm_out;  // dx as a TMA tensor (32 x 32 boxes); valid when use_tma (identity row map, no ReLU mask)
+    int use_tma;
     const float* w;      // [rows]
     const float* dout;   // [segments][ldo]
     int ldo;
@@ -391,7 +429,9 @@ struct EpiDPoolIn {
     __device__ void init(const EpiInit& e, int) const {
         if (e.first_tile < e.num_tiles) stage_tile(e.first_tile, e.col0, e.ncols, e.tid, e.scratch);
     }
-    __device__ void finish(const EpiInit&) const {}
+    __device__ void finish(const EpiInit& e) const {
+        if (use_tma) WarpTileStore::drain(e.tid & 31);
+    }
 
     template <class Acc>
     __device__ void operator()(const Acc& acc, const EpiCtx& c) const {
@@ -406,9 +446,38 @@ struct EpiDPoolIn {
         epi_bar_sync();  // this tile's dOut rows are visible; everybody is done with the other buffer
         if (c.next_tile >= 0) stage_tile(c.next_tile, c.col0, c.ncols, c.tid, c.scratch + ((c.it + 1) & 1) * kStageFloats);
         const float* sd = cur + myseg * c.ncols;
+        const int lane = c.tid & 31;
+        WarpTileStore ts;
+        if (use_tma) {
+            ts.attach(c.scratch + 2 * kStageFloats, c.tid >> 5);
+            ts.begin_tile(lane);
+        }
         epi_chunks(
             acc, c, [](int) {},
             [&](int ch, float* x) {
+                const bool whole = use_tma && ch * 32 + 32 <= c.ncols && (c.ncols & 3) == 0;  // warp-uniform
+                if (whole) {  // identity row map, no ReLU mask; rows >= M / columns >= N are clipped by the tensor map
+                    const float* sdc = c.valid ? sd + ch * 32 : cur;  // invalid rows: any staged address (wr = 0)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 d4 = lds_f4(sdc + j);
+                        x[j] = fmaf(wr, d4.x, x[j]); x[j + 1] = fmaf(wr, d4.y, x[j + 1]);
+                        x[j + 2] = fmaf(wr, d4.z, x[j + 2]); x[j + 3] = fmaf(wr, d4.w, x[j + 3]);
+                    }
+                    if (drop.p > 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float m[4];
+                            drop.mask4(c.grow, ld, c.col0 + ch * 32 + j, m);
+                            x[j] *= m[0]; x[j + 1] *= m[1]; x[j + 2] *= m[2]; x[j + 3] *= m[3];
+                        }
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+                    ts.put(&tm_out, pk, c.col0 + ch * 32, c.grow - lane, lane);
+                    return;
+                }
                 if (!v) return;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {

@@ -132,6 +132,48 @@ __device__ __forceinline__ void epi_chunks(const Acc& acc, const EpiCtx& c, Pre&
     }
 }
 
+// bf16 output tiles leave through TMA instead of 32 scattered rows per store instruction: a warp packs its 32 rows x 32
+// columns into a private staging buffer (SWIZZLE_64B layout: 16-byte chunk q of row r at r*64 + ((q ^ (r>>1)) & 3)*16,
+// conflict-free for row-per-lane 16-byte writes) and one lane issues cp.async.bulk.tensor.  Two buffers per warp.
+// Measured alone (tools/stbench.cu): 5.7 TB/s vs 2.6 (2 x STG.128) / 5.0 (STG.256); inside the GEMM the row-per-thread
+// stores sat in the LSU queue and stalled the warps on their source registers (ncu, profiles/).
+constexpr int kTileStoreBufs = 2;                                  // staging tiles per warp (2 KB each)
+constexpr int kTileStoreBytes = 8 * kTileStoreBufs * 2048 + 1024;  // 8 warps + alignment slack
+struct WarpTileStore {
+    uint8_t* buf;  // this warp's kTileStoreBufs x 2 KB (1024-byte aligned)
+    int nput;
+    __device__ __forceinline__ void attach(void* region, int warp_in_group) {
+        buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(region) + 1023) & ~uintptr_t(1023)) + warp_in_group * (kTileStoreBufs * 2048);
+    }
+    __device__ __forceinline__ void begin_tile(int lane) {
+        nput = 0;
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+    }
+    // w: this lane's row, 32 columns as 16 packed bf16 pairs; (col, row0) = global coordinates of the warp's tile
+    __device__ __forceinline__ void put(const CUtensorMap* tm, const uint32_t* w, int col, int row0, int lane) {
+        uint8_t* b = buf + (nput % kTileStoreBufs) * 2048;
+        if (nput >= kTileStoreBufs) {
+            if (lane == 0) bulk_wait_read<kTileStoreBufs - 1>();  // the store issued from this buffer has been read out
+            __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(b + lane * 64 + ((q ^ (lane >> 1)) & 3) * 16) =
+                make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tm, b, col, row0);
+            bulk_commit();
+        }
+        ++nput;
+    }
+    static __device__ __forceinline__ void drain(int lane) {  // before the CTA exits
+        if (lane == 0) bulk_wait_all();
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // gemm_nt kernel: one CTA PAIR (cluster of 2, tcgen05 cta_group::2) per (256-row block, weight slice)
 // ---------------------------------------------------------------------------------------------
@@ -149,7 +191,7 @@ __device__ __forceinline__ void epi_chunks(const Acc& acc, const EpiCtx& c, Pre&
 template <class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmNTParams p,
-               const Epi epi) {
+               const __grid_constant__ Epi epi) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5;
@@ -283,7 +325,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const EpiInit ei{col0, ncols, static_cast<int>(threadIdx.x), scratch, 2 * ptile0 + static_cast<int>(rank), p.num_m_tiles};
         epi.init(ei, tile_step);
         const int quarter = warp & 3;
-        const uint32_t tempty_l[2] = {mapa_shared(&tempty[0], 0), mapa_shared(&tempty[1], 0)};
+        const uint32_t tempty_l0 = mapa_shared(&tempty[0], 0), tempty_l1 = mapa_shared(&tempty[1], 0);
         int it = 0;
         for (int pt = ptile0; pt < num_ptiles; pt += ptile_step, ++it) {
             const int tile = 2 * pt + static_cast<int>(rank);  // may be one past the last tile: every row invalid
@@ -304,7 +346,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             c.scratch = scratch;
             c.it = it;
             c.next_tile = tile + tile_step < p.num_m_tiles ? tile + tile_step : -1;
-            TmemAcc acc{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 256, tempty_l[as]};
+            TmemAcc acc{tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * 256, as ? tempty_l1 : tempty_l0};
             epi(acc, c);
             if (tmr != nullptr) tw_b += clock64() - t_epi;
         }
@@ -322,8 +364,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void gemm_nt_simt_acc_kernel(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                                         GemmNTParams p);
 template <class Epi>
-__global__ void __launch_bounds__(kEpiThreads, 1) gemm_nt_simt_epi_kernel(const GemmNTParams p, const Epi epi) {
-    __shared__ __align__(16) float scratch[Epi::kScratchBytes / 4];
+__global__ void __launch_bounds__(kEpiThreads, 1) gemm_nt_simt_epi_kernel(const GemmNTParams p, const __grid_constant__ Epi epi) {
+    extern __shared__ __align__(1024) float scratch[];  // Epi::kScratchBytes
     const int slice = blockIdx.x % p.n_slices;
     const int tile0 = blockIdx.x / p.n_slices;
     const int tile_step = gridDim.x / p.n_slices;
@@ -405,7 +447,13 @@ int launch_gemm_nt(const GemmNTPlan& plan, const Epi& epi, const void* A, int ld
         dim3 g(ceil_div(static_cast<int>(ld), 128), p.num_m_tiles);
         gemm_nt_simt_acc_kernel<<<g, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda,
                                                        static_cast<const __nv_bfloat16*>(B), ldb, p);
-        gemm_nt_simt_epi_kernel<Epi><<<plan.grid, kEpiThreads, 0, stream>>>(p, epi);
+        static bool dbg_attr_set = false;  // per Epi instantiation
+        if (!dbg_attr_set) {
+            NR_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_simt_epi_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               Epi::kScratchBytes));
+            dbg_attr_set = true;
+        }
+        gemm_nt_simt_epi_kernel<Epi><<<plan.grid, kEpiThreads, Epi::kScratchBytes, stream>>>(p, epi);
         NR_CHECK_CUDA(cudaGetLastError());
         NR_CHECK_CUDA(cudaFreeAsync(acc, stream));
         return 0;
