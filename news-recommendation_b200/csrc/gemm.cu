@@ -202,6 +202,8 @@ int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B,
     p.k_chunks = ceil_div(K, kChunkK);
     p.taps = taps;
     p.b_tap_rows = b_tap_rows;
+    static const int dbg_flags = [] { const char* v = getenv("NEWSREC_GEMM_DBG"); return v != nullptr ? atoi(v) : 0; }();
+    p.dbg_flags = dbg_flags;
     if (g_gemm_timing != nullptr && g_gemm_timing_next < g_gemm_timing_slots) {
         p.timing = g_gemm_timing + static_cast<size_t>(g_gemm_timing_next) * 148 * 16;
         fprintf(stderr, "[nr] gemm timing slot %d: M=%d N=%d K=%d taps=%d\n", g_gemm_timing_next, M, N, K, taps);

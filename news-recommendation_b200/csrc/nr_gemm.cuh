@@ -44,6 +44,7 @@ struct GemmNTParams {
     int stages;
     float* dbg_acc;     // debug backend only: fp32 accumulators [num_m_tiles*128][dbg_ld]
     int dbg_ld;
+    int dbg_flags;      // tuning only (NEWSREC_GEMM_DBG): bit 1 = the producers skip the A loads (MMA on stale data)
     long long* timing;  // tuning only (nr_debug_set_gemm_timing): per CTA 16 cycle counters, see the kernel
 };
 
@@ -259,32 +260,45 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
-            const uint32_t bfull_l = mapa_shared(bfull, 0);
+        // ===================== TMA producer (both CTAs; uniform loops, one elected lane issues) =====================
+        const uint32_t bfull_l = mapa_shared(bfull, 0);
+        if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(bfull, static_cast<uint32_t>(2 * p.taps * p.k_chunks * b_region));
             for (int s = 0; s < p.taps; ++s)
                 for (int kc = 0; kc < p.k_chunks; ++kc)
                     tma_load_2d_pair(sB + (s * p.k_chunks + kc) * b_region, &tmB, bfull_l, kc * kChunkK,
                                      s * p.b_tap_rows + col0 + static_cast<int>(rank) * (n_mma >> 1));
-            int st = 0;
-            uint32_t ph = 0;
-            for (int pt = ptile0; pt < num_ptiles; pt += ptile_step) {
-                const int row0 = (2 * pt + static_cast<int>(rank)) * p.rows_per_tile;  // past M: zero filled
-                for (int s = 0; s < p.taps; ++s)
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        timed_wait(&empty[st], ph ^ 1, 101, tw_a);
-                        if (leader) mbar_arrive_expect_tx(&full[st], 2 * kAStageBytes);
-                        tma_load_2d_pair(sA + st * kAStageBytes, &tmA, mapa_shared(&full[st], 0), kc * kChunkK,
-                                         row0 + s - tap_shift);
-                        if (++st == p.stages) { st = 0; ph ^= 1; }
-                    }
-            }
-            if (tmr != nullptr) tmr[0] = tw_a;
         }
+        __syncwarp();
+        int st = 0;
+        uint32_t ph = 0;
+        for (int pt = ptile0; pt < num_ptiles; pt += ptile_step) {
+            const int row0 = (2 * pt + static_cast<int>(rank)) * p.rows_per_tile;  // past M: zero filled
+            for (int s = 0; s < p.taps; ++s)
+                for (int kc = 0; kc < p.k_chunks; ++kc) {
+                    timed_wait(&empty[st], ph ^ 1, 101, tw_a);
+                    if (elect_one()) {
+                        if (p.dbg_flags & 2) {
+                            if (leader) mbar_arrive(&full[st]);
+                        } else {
+                            if (leader) mbar_arrive_expect_tx(&full[st], 2 * kAStageBytes);
+                            tma_load_2d_pair(sA + st * kAStageBytes, &tmA, mapa_shared(&full[st], 0), kc * kChunkK,
+                                             row0 + s - tap_shift);
+                        }
+                    }
+                    __syncwarp();
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+        }
+        if (tmr != nullptr && lane == 0) tmr[0] = tw_a;
     } else if (warp == 9) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && leader) {
+        // The whole warp runs the loops (uniform control flow) and one elected lane issues: under an `if (lane == 0)`
+        // the compiler wraps every tcgen05 instruction in a uniform-register waterfall loop, and together with the
+        // run-time k-step count that made the issuing thread -- not the tensor pipe -- the limiter (~240 cycles per MMA
+        // against the pipe's 120 even with loads and epilogue switched off).  Columns past K are zero filled by TMA in
+        // both operands, so every k-chunk issues all four k-steps.
+        if (leader) {
             const uint32_t idesc = make_idesc_bf16(2 * kTileM, n_mma, 0, 0);
             mbar_wait(bfull, 0, 102);
             tc_fence_after();
@@ -301,23 +315,24 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
                         timed_wait(&full[st], ph, 104, tw_a);
                         tc_fence_after();
-                        const uint32_t a_addr = smem_u32(sA + st * kAStageBytes);
-                        const uint32_t b_addr = smem_u32(sB + (s * p.k_chunks + kc) * b_region);
-                        const int ksteps = min(4, (p.K - kc * kChunkK + 15) >> 4);
                         const long long t_i0 = tmr != nullptr ? clock64() : 0;
-                        for (int k = 0; k < ksteps; ++k) {
-                            umma_bf16_pair(d_tmem, make_sw128_desc(a_addr + k * 32, 0, 1024),
-                                           make_sw128_desc(b_addr + k * 32, 0, 1024), idesc, acc);
-                            acc = 1;
+                        if (elect_one()) {
+                            const uint64_t da = make_sw128_desc(smem_u32(sA + st * kAStageBytes), 0, 1024);
+                            const uint64_t db = make_sw128_desc(smem_u32(sB + (s * p.k_chunks + kc) * b_region), 0, 1024);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)  // +32 bytes per k-step = +2 in the descriptor's >>4 address field
+                                umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (k == 0) ? acc : 1u);
+                            umma_commit_pair(&empty[st]);  // frees stage st in both CTAs when these MMAs retire
                         }
-                        const long long t_i1 = tmr != nullptr ? clock64() : 0;
-                        umma_commit_pair(&empty[st]);  // frees stage st in both CTAs when these MMAs retire
-                        if (tmr != nullptr) { tw_c += t_i1 - t_i0; tw_d += clock64() - t_i1; }
+                        __syncwarp();
+                        acc = 1;
+                        if (tmr != nullptr) tw_c += clock64() - t_i0;
                         if (++st == p.stages) { st = 0; ph ^= 1; }
                     }
-                umma_commit_pair(&tfull[as]);
+                if (elect_one()) umma_commit_pair(&tfull[as]);
+                __syncwarp();
             }
-            if (tmr != nullptr) { tmr[1] = tw_a; tmr[2] = tw_b; tmr[7] = tw_c; tmr[8] = tw_d; }
+            if (tmr != nullptr && lane == 0) { tmr[1] = tw_a; tmr[2] = tw_b; tmr[7] = tw_c; tmr[8] = tw_d; }
         }
     } else {
         // ===================== epilogue warps 0..7 (both CTAs, own TMEM rows) =====================

@@ -13,8 +13,9 @@ using namespace nr;
 
 // mode 0: A and B both from smem, new A stage every k-block (ring of `stages`), B slice resident
 // mode bit0: tcgen05.commit to an mbarrier after every k-block (as the GEMM's stage release does)
+// mode bit2: warps 4-11 poll an mbarrier with try_wait (the GEMM's epilogue warps waiting for an accumulator)
 // mode bit1: warp 2 streams 16 KB bulk copies global->smem (the GEMM's TMA producer traffic) while the MMAs run
-__global__ void __launch_bounds__(128, 1) mma_kernel(int N, int kblocks, int stages, int iters, long long* out, int mode,
+__global__ void __launch_bounds__(384, 1) mma_kernel(int N, int kblocks, int stages, int iters, long long* out, int mode,
                                                      const uint8_t* gsrc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -24,7 +25,7 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int N, int kblocks, int sta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* sB = smem;                         // kblocks boxes of N x 128 B
     uint8_t* sA = smem + kblocks * N * 128;     // stages x 16 KB
-    for (int i = threadIdx.x; i < (kblocks * N * 128 + stages * 16384) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    for (int i = threadIdx.x; i < (kblocks * N * 128 + stages * 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
     if (warp == 0) tmem_alloc(&slot, 512);
     if (threadIdx.x == 32) {
         mbar_init(&bar, 1);
@@ -87,6 +88,11 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int N, int kblocks, int sta
         mbar_wait(&cbar[1], ph[1], 3);
         out[148 + blockIdx.x] = n;
     }
+    else if (warp >= 4 && (mode & 4)) {
+        while (!done) {
+            if (mbar_try_wait(&kbar[7], 1 ^ 1)) break;  // phase 0 never completes (nobody arrives on kbar[7] when stages <= 7)
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -99,13 +105,13 @@ int main() {
     CK(cudaMalloc(&gsrc, 148ull * (8u << 20)));
     CK(cudaMemset(gsrc, 0, 148ull * (8u << 20)));
     CK(cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    const int shapes[][2] = {{80, 15}, {128, 5}, {160, 4}, {240, 5}};
+    const int shapes[][2] = {{160, 4}, {240, 5}};
     for (auto& s : shapes) {
-        const int N = s[0], kb = s[1], stages = 2, iters = 400;
+        const int N = s[0], kb = s[1], stages = 4, iters = 400;
         const size_t smem = static_cast<size_t>(kb) * N * 128 + (stages + 2) * 16384 + 1024;
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode : {0, 4, 5, 7}) {
             const int grid = 148;
-            mma_kernel<<<grid, 128, smem>>>(N, kb, stages, iters, out, mode, gsrc);
+            mma_kernel<<<grid, 384, smem>>>(N, kb, stages, iters, out, mode, gsrc);
             CK(cudaDeviceSynchronize());
             long long h[296];
             CK(cudaMemcpy(h, out, 2 * 148 * 8, cudaMemcpyDeviceToHost));
