@@ -175,6 +175,8 @@ __device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloa
 // offsets are computed ONCE per kernel (ncu: per-piece index arithmetic was 30 % of all instructions).
 constexpr int kMaxP = 4;  // pieces per lane covered by the plan (T * pieces_per_row <= 128); larger tiles use the loops
 struct PieceMap {
+    int total;        // pieces of the whole tile: lane l moves pieces l, l+32, ... < total
+    int lane;
     int n;            // pieces of this lane
     int src[kMaxP];   // element offset in the global matrix:  r * ld + c
     int dst[kMaxP];   // element offset in the tile:            r * kPitch + c
@@ -184,6 +186,8 @@ struct PieceMap {
 __device__ __forceinline__ bool make_piece_map(PieceMap& m, int T, int dk, int piece, int ld, int lane) {
     const int epp = piece >> 1, ppr = dk / epp, n = T * ppr;
     m.n = 0;
+    m.total = n;
+    m.lane = lane;
     if (piece < 4 || n > kMaxP * 32) return false;
 #pragma unroll
     for (int k = 0; k < kMaxP; ++k) {
@@ -199,8 +203,8 @@ __device__ __forceinline__ bool make_piece_map(PieceMap& m, int T, int dk, int p
 }
 __device__ __forceinline__ void tile_load_map(uint32_t tile_saddr, const __nv_bfloat16* g, const PieceMap& m, int piece) {
 #pragma unroll
-    for (int k = 0; k < kMaxP; ++k) {
-        if (k < m.n) {
+ for (int k = 0; k < kMaxP; ++k) {
+        if (m.lane + 32 * k < m.total) {
             if (piece == 8)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_saddr + 2 * m.dst[k]), "l"(g + m.src[k]) : "memory");
             else
@@ -211,7 +215,7 @@ __device__ __forceinline__ void tile_load_map(uint32_t tile_saddr, const __nv_bf
 __device__ __forceinline__ void tile_store_map(const __nv_bfloat16* tile, __nv_bfloat16* g, const PieceMap& m, int piece) {
 #pragma unroll
     for (int k = 0; k < kMaxP; ++k) {
-        if (k < m.n) {
+        if (m.lane + 32 * k < m.total) {
             if (piece == 8) *reinterpret_cast<uint2*>(g + m.src[k]) = *reinterpret_cast<const uint2*>(tile + m.dst[k]);
             else *reinterpret_cast<uint32_t*>(g + m.src[k]) = *reinterpret_cast<const uint32_t*>(tile + m.dst[k]);
         }
@@ -222,7 +226,7 @@ __device__ __forceinline__ void tile_store_dropout_map(const __nv_bfloat16* tile
                                                        long long row0, int col0, uint64_t seed, uint32_t thresh, float scale) {
 #pragma unroll
     for (int k = 0; k < kMaxP; ++k) {
-        if (k < m.n) {
+        if (m.lane + 32 * k < m.total) {
             const int gc = col0 + m.col[k];
             const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row0 + m.row[k]) * ld + gc) >> 2);
             if (piece == 8) {
@@ -285,11 +289,15 @@ __host__ __device__ inline int piece_bytes(int dk, int ld_a, int ld_b, int d) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST>
+// CT/CDK/CH > 0 pin the sequence length, head width and head count at compile time (8-byte pieces guaranteed by the
+// launcher): every shape guard, the piece plan and the task -> (sequence, head) division fold away.  ncu on the run-time
+// shaped kernel: 1200 warp instructions per 20x20 head, 650 of them integer/predicate/branch overhead.
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH>
 __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
-                                                                  int T, int heads, int dk, __nv_bfloat16* __restrict__ ctx,
+                                                                  int T_, int heads_, int dk_, __nv_bfloat16* __restrict__ ctx,
                                                                   int ld_ctx, float p, uint64_t seed) {
     constexpr int NTJ = TP / 8, MT = TP / 16;
+    const int T = CT > 0 ? CT : T_, heads = CH > 0 ? CH : heads_, dk = CDK > 0 ? CDK : dk_;
     // A tile holds exactly T rows (pitch kPitch).  Fragment loads of rows >= T run into the neighbouring tile or the
     // zeroed slack behind the last one: finite bytes that only ever meet zero probabilities / unused output rows.
     const int TILE = T * kPitch;
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
     const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
     const float dscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     const int ntj = (T + 7) >> 3;
-    const int piece = piece_bytes(dk, ld, ld_ctx, d);
+    const int piece = CT > 0 ? 8 : piece_bytes(dk, ld, ld_ctx, d);
     const int n_tasks = static_cast<int>(n_seq * heads);  // < 2^31, checked by the launcher
     const int W = gridDim.x * WPS;
     const int gw = blockIdx.x * WPS + warp;
@@ -426,12 +434,13 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST>
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH>
 __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
                                                                   const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
-                                                                  long long n_seq, int T, int heads, int dk,
+                                                                  long long n_seq, int T_, int heads_, int dk_,
                                                                   __nv_bfloat16* __restrict__ dqkv, int ld_d) {
     constexpr int NTJ = TP / 8, MT = TP / 16, SP = TP + 8;
+    const int T = CT > 0 ? CT : T_, heads = CH > 0 ? CH : heads_, dk = CDK > 0 ? CDK : dk_;
     const int TILE = T * kPitch;  // packed rows, see the forward kernel
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
@@ -445,7 +454,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
     const float rs = rsqrtf(static_cast<float>(dk));
     const float sc = rs * 1.4426950408889634f;
     const int ntj = (T + 7) >> 3;
-    const int piece = piece_bytes(dk, ld, ld_dctx, d) == 8 && (ld_d % 4) == 0 ? 8 : (piece_bytes(dk, ld, ld_dctx, d) >= 4 && (ld_d % 2) == 0 ? 4 : 2);
+    const int piece = CT > 0 ? 8
+                             : (piece_bytes(dk, ld, ld_dctx, d) == 8 && (ld_d % 4) == 0 ? 8 : (piece_bytes(dk, ld, ld_dctx, d) >= 4 && (ld_d % 2) == 0 ? 4 : 2));
     const int n_tasks = static_cast<int>(n_seq * heads);
     const int W = gridDim.x * WPS;
     const int gw = blockIdx.x * WPS + warp;
@@ -639,7 +649,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
     cp_wait<0>();
 }
 
-template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST>
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT = 0, int CDK = 0, int CH = 0>
 int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     const long long tasks = n_seq * heads;
@@ -653,13 +663,13 @@ int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int
     const int grid = static_cast<int>(std::min<long long>(ceil_div(static_cast<int>(std::min<long long>(tasks, 1 << 30)), WPS),
                                                           static_cast<long long>(num_sms()) * per_sm));
     if (!bwd) {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out, drop.p,
                                                                              drop.seed);
     } else {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
                                                                              static_cast<const __nv_bfloat16*>(dctx), ld_dctx, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out);
     }
@@ -678,6 +688,13 @@ int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int 
     if (bwd) piece = (piece == 8 && (ld_out % 4) == 0) ? 8 : ((piece >= 4 && (ld_out % 2) == 0) ? 4 : 2);
     static const bool force_loops = getenv("NEWSREC_ATTN_LOOPS") != nullptr;  // tuning switch (tools/kbench.py)
     const bool fast = !force_loops && piece >= 4 && T * (dk / (piece / 2)) <= kMaxP * 32;
+    static const bool no_fixed = getenv("NEWSREC_ATTN_GENERIC") != nullptr;  // tuning switch: skip the fixed-shape kernels
+    if constexpr (TP == 32 && KSD == 2 && NTD == 3) {
+        // the reference's title encoder (config.py: num_words_title 20, 15 heads x 20) gets a fully fixed-shape kernel
+        if (fast && !no_fixed && piece == 8 && T == 20 && dk == 20 && heads == 15)
+            return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, true, 20, 20, 15>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out,
+                                                                             drop, stream);
+    }
     if (fast)
         return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
     return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, false>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);

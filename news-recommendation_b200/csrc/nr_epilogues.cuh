@@ -350,16 +350,18 @@ struct EpiDPre {
         epi_chunks(
             acc, c, [](int) {},
             [&](int ch, float* x) {
+                // bias and query vector are zero past ncols in shared memory: dp = 0 there without a column test, and
+                // the column sums of those columns are never added to dqv
                 float dp[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 b4 = lds_f4(c.scratch + 256 + ch * 32 + j);
-                    const float4 q4 = lds_f4(c.scratch + 512 + ch * 32 + j);  // 0 beyond ncols
+                    const float4 q4 = lds_f4(c.scratch + 512 + ch * 32 + j);
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, qq[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float tt = (ch * 32 + j + i < c.ncols) ? fast_tanh(x[j + i] + bb[i]) : 0.f;
-                        dp[j + i] = ds * qq[i] * (1.f - tt * tt);
+                        const float tt = tanh_approx(x[j + i] + bb[i]);
+                        dp[j + i] = (ds * qq[i]) * fmaf(-tt, tt, 1.f);
                         x[j + i] = ds * tt;
                     }
                 }
