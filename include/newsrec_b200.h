@@ -93,6 +93,11 @@ int nr_dot_score_fwd(const float* cand, const float* user, int B, int C, int D, 
 int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
                      float* duser, void* stream);
 
+/* Host-side glue of the weight-gradient GEMMs (nr_gemm_tn with the ones column): ext is [rows][ld] fp32 whose columns
+ * [0,D) hold dW and column D holds db.  Adds them into the parameters' own gradient storage (dW [rows][D] contiguous,
+ * db [rows] or null) and CLEARS ext, so the caller can keep it as a persistent accumulator across steps. */
+int nr_accumulate_ext_grad(float* ext, int rows, int ld, int D, float* dW, float* db, void* stream);
+
 /* ---- reference: NRMS NewsEncoder.forward / UserEncoder.forward -------------------------------------
  *   news  (src/model/NRMS/news_encoder.py:27-48): embedding -> dropout -> MHSA -> dropout -> additive pool
  *   user  (src/model/NRMS/user_encoder.py:15-26): MHSA -> additive pool over dense fp32 news vectors     */

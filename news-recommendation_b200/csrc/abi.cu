@@ -117,6 +117,11 @@ int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits,
     return dot_score_bwd(cand, user, dlogits, B, C, D, dcand, duser, S(stream));
 }
 
+int nr_accumulate_ext_grad(float* ext, int rows, int ld, int D, float* dW, float* db, void* stream) {
+    NR_REQUIRE(ext && dW && rows >= 0 && D >= 1, "nr_accumulate_ext_grad: null operand");
+    return accumulate_ext_grad(ext, rows, ld, D, dW, db, S(stream));
+}
+
 // ---- NRMS encoders ---------------------------------------------------------------------------------
 static int check_mhsa_shape(long long n_seq, int T, int d, int heads, int q, int ldx, int ld3) {
     NR_REQUIRE(n_seq >= 0 && T >= 1 && T <= 64 && d >= 8 && heads >= 1 && d % heads == 0 && q >= 1 && q <= 256,

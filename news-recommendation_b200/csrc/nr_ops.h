@@ -68,6 +68,7 @@ int dot_score_bwd(const float* cand, const float* user, const float* dlogits, in
                   float* duser, cudaStream_t stream);
 
 // dst bf16 [n][ldn] = dy[n][N] (pitch ld_dy) masked by (relu_out > 0) when relu_out != null (same pitch); zero padded
+int accumulate_ext_grad(float* ext, int rows, int ld, int D, float* dW, float* db, cudaStream_t stream);
 int relu_bwd_to_bf16(const float* dy, const float* relu_out, long long n, int N, int ld_dy, void* dst, int ldn, cudaStream_t stream);
 // fp32 embedding lookup / scatter-add (padding row 0: value read as-is, gradient skipped)
 int embedding_f32_fwd(const long long* ids, long long n, const float* table, int V, int D, float* out, int* bad_id_flag,

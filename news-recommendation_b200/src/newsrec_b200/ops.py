@@ -61,6 +61,15 @@ class OperandCache:
         self._store.clear()
 
 
+def grad_sink(p):
+    """The parameter's own gradient storage if the kernels can accumulate into it directly, else None."""
+    g = getattr(p, "grad", None)
+    if g is None or not p.requires_grad or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device \
+            or g.shape != p.shape:
+        return None
+    return g
+
+
 def cast_pad(src: torch.Tensor, ld: int, transpose: bool = False) -> torch.Tensor:
     """fp32 [R][C] -> zero padded bf16 [R][ld] (or the transpose [C][ld]) on the device."""
     lib = load_library()
@@ -140,7 +149,8 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         ctx.save_for_backward(X, QKV, Cx, w, ids if ids is not None else torch.empty(0, device=dev))
         ctx.meta = dict(n_seq=n_seq, T=T, d=d, q=q, heads=heads, p_drop=float(p_drop), seed=seed, ops=ops,
                         has_ids=ids is not None, V=emb_w.shape[0] if ids is not None else 0,
-                        dense_shape=None if dense is None else tuple(dense.shape))
+                        dense_shape=None if dense is None else tuple(dense.shape),
+                        params=(emb_w, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv), cache=cache, prefix=prefix)
         return out
 
     @staticmethod
@@ -153,12 +163,29 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         ldx, ld3, ldq = ru8(d + 1), ru16(3 * d), ru16(q)
         ops = m["ops"]
         dout = dout.contiguous().float()
-        dWqkv = torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev)
-        dWa = torch.zeros((q, ldx), dtype=torch.float32, device=dev)
-        dqv = torch.zeros((q,), dtype=torch.float32, device=dev)
+        emb_w, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv = m["params"]
+        # Parameters whose .grad already exists as contiguous fp32 storage (ddp.FlatGradients, or a plain earlier
+        # backward) are accumulated IN PLACE by the kernels and get None from this Function: no zero fill, no slice
+        # copies, no AccumulateGrad adds (together ~50 small framework kernels and 3 passes over the 85 MB embedding
+        # gradient per step).  Anything else takes the allocate-and-return path.
+        sinks = [grad_sink(t) for t in (Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv)]
+        direct = all(g is not None for g in sinks)
+        if direct:
+            ws_grads = m["cache"].get(m["prefix"] + ".grad_ws", (), lambda: dict(
+                dWqkv=torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev),
+                dWa=torch.zeros((q, ldx), dtype=torch.float32, device=dev)))
+            dWqkv, dWa, dqv = ws_grads["dWqkv"], ws_grads["dWa"], sinks[8]
+        else:
+            dWqkv = torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev)
+            dWa = torch.zeros((q, ldx), dtype=torch.float32, device=dev)
+            dqv = torch.zeros((q,), dtype=torch.float32, device=dev)
         demb = ddense = None
+        emb_direct = False
         if m["has_ids"]:
-            demb = torch.zeros((m["V"], d), dtype=torch.float32, device=dev)
+            demb = grad_sink(emb_w)
+            emb_direct = demb is not None
+            if not emb_direct:
+                demb = torch.zeros((m["V"], d), dtype=torch.float32, device=dev)
         else:
             ddense = torch.empty((n_seq * T, d), dtype=torch.float32, device=dev)
         ws_bytes = int(lib.nr_mhsa_encoder_bwd_workspace(n_seq, T, d, q))
@@ -174,10 +201,17 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         a.demb, a.ddense = _p(demb), _p(ddense)
         a.workspace, a.workspace_bytes = _p(ws), ws_bytes
         check(lib.nr_mhsa_encoder_bwd(C.byref(a), _stream()), "nr_mhsa_encoder_bwd")
+        g_dense = ddense.view(m["dense_shape"]) if ddense is not None else None
+        g_emb = None if emb_direct else demb
+        if direct:
+            for i in range(3):
+                check(lib.nr_accumulate_ext_grad(_p(dWqkv[i * d:(i + 1) * d]), d, ldx, d, _p(sinks[2 * i]), _p(sinks[2 * i + 1]),
+                                                 _stream()), "nr_accumulate_ext_grad")
+            check(lib.nr_accumulate_ext_grad(_p(dWa), q, ldx, d, _p(sinks[6]), _p(sinks[7]), _stream()), "nr_accumulate_ext_grad")
+            return (None, g_dense, g_emb) + (None,) * 14
         gW = [dWqkv[i * d:(i + 1) * d, :d].contiguous() for i in range(3)]
         gb = [dWqkv[i * d:(i + 1) * d, d].contiguous() for i in range(3)]
-        g_dense = ddense.view(m["dense_shape"]) if ddense is not None else None
-        return (None, g_dense, demb, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2],
+        return (None, g_dense, g_emb, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2],
                 dWa[:, :d].contiguous(), dWa[:, d].contiguous(), dqv, None, None, None, None, None)
 
 

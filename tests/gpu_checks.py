@@ -295,6 +295,40 @@ def check_nrms_random(B=8, Cn=5, H=50, T=20, V=500, seed=5):
     return out
 
 
+def check_nrms_direct_grad_accumulation(B=8, Cn=5, H=50, T=20, V=500, seed=6):
+    """Parameters with pre-allocated .grad storage (ddp.FlatGradients) are accumulated in place by the kernels; the
+    result must equal the allocate-and-return path, also when two backward passes accumulate."""
+    from newsrec_b200 import ddp
+    cand_t, clicked_t, _ = O.synth_batch(B, Cn, H, T, V, seed * 100)
+    label = torch.zeros(B, dtype=torch.long, device=DEV)
+    model_a, _ = nrms_model_and_params(V, seed)
+    model_b, _ = nrms_model_and_params(V, seed)
+    model_a.eval()
+    model_b.eval()
+    flat = ddp.FlatGradients(model_b.parameters(), 1)
+    flat.zero()
+    for _ in range(2):  # two accumulating backward passes
+        torch.nn.functional.cross_entropy(model_a(slots(cand_t), slots(clicked_t)), label).backward()
+        torch.nn.functional.cross_entropy(model_b(slots(cand_t), slots(clicked_t)), label).backward()
+    torch.cuda.synchronize()
+    worst = 0.0
+    for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        scale = float(pa.grad.abs().max()) + 1e-12
+        worst = max(worst, float((pa.grad - pb.grad).abs().max()) / scale)
+    # a third backward with the persistent workspaces must start from cleared accumulators
+    flat.zero()
+    model_a.zero_grad(set_to_none=True)
+    torch.nn.functional.cross_entropy(model_a(slots(cand_t), slots(clicked_t)), label).backward()
+    torch.nn.functional.cross_entropy(model_b(slots(cand_t), slots(clicked_t)), label).backward()
+    torch.cuda.synchronize()
+    again = 0.0
+    for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        scale = float(pa.grad.abs().max()) + 1e-12
+        again = max(again, float((pa.grad - pb.grad).abs().max()) / scale)
+    return {"direct_vs_returned_rel_maxabs": worst, "after_zero_rel_maxabs": again,
+            "grads_are_flat_views": all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in model_b.parameters())}
+
+
 def check_nrms_eval_api(V=300, seed=9):
     """get_news_vector / get_user_vector (non-contiguous input, evaluate.py:220-224) / get_prediction."""
     model, sd = nrms_model_and_params(V, seed)

@@ -35,6 +35,13 @@ def test_nrms_mind_shaped_batch_vs_oracle():
     assert r["logits_vs_exact_fp32"] < 1.25 * r["oracle_bf16_vs_exact"] + 1e-4, r
 
 
+def test_nrms_in_place_gradient_accumulation_matches_returned_gradients():
+    """fp32 red.add order differs between runs, nothing else: the two paths agree to accumulation noise."""
+    r = G.check_nrms_direct_grad_accumulation()
+    assert r["grads_are_flat_views"], r
+    assert r["direct_vs_returned_rel_maxabs"] < 1e-5 and r["after_zero_rel_maxabs"] < 1e-5, r
+
+
 def test_nrms_eval_api_noncontiguous_history():
     r = G.check_nrms_eval_api()
     assert r["user_input_noncontig"] and r["pred_tolist_len"] == 7, r
