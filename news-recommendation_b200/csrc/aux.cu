@@ -81,38 +81,44 @@ __device__ __forceinline__ float drop_mult(uint64_t seed, uint32_t thresh, float
     return (((bits >> (16 * (col & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
 }
 
-// one thread = one 16-byte chunk of one token row: consecutive threads copy consecutive chunks (coalesced);
+// one thread = one 16-byte chunk COLUMN: a block covers kGatherThreads / chunks consecutive token rows per iteration
+// (consecutive threads copy consecutive chunks: coalesced), so the chunk index and the row slot are computed once and
+// the loop carries no division (the flat-index version spent most of its instructions on 64-bit div/mod);
 // dropout draws ONE counter hash per 4 aligned columns (two per chunk)
-__global__ void gather_rows_kernel(const long long* __restrict__ ids, long long n_tok, int T,
-                                   const uint4* __restrict__ table, int V, int D, int ld, uint4* __restrict__ X,
-                                   int padded, float p, uint64_t seed, int* bad_flag) {
+constexpr int kGatherThreads = 320;
+__global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(const long long* __restrict__ ids, long long n_tok, int T,
+                                                                   const uint4* __restrict__ table, int V, int D, int ld,
+                                                                   uint4* __restrict__ X, int padded, float p, uint64_t seed,
+                                                                   int* bad_flag) {
     const int chunks = ld >> 3;  // 16-byte chunks per row
+    const int rows_per_it = kGatherThreads / chunks;
+    const int rl = threadIdx.x / chunks, c = threadIdx.x - rl * chunks;
+    if (rl >= rows_per_it) return;
     const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-    const long long total = n_tok * chunks;
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    // software pipeline: the (id -> table row) loads of the NEXT element are in flight while this one is stored
-    long long n_tok_i = i < total ? i / chunks : 0;
-    long long n_id = i < total ? __ldg(ids + n_tok_i) : 0;
-    if (i < total && (n_id < 0 || n_id >= V)) { atomicExch(bad_flag, 1); n_id = 0; }
-    uint4 n_u = i < total ? __ldg(table + n_id * chunks + (i - n_tok_i * chunks)) : make_uint4(0, 0, 0, 0);
-    for (; i < total; i += stride) {
-        const long long tok = n_tok_i;
-        const int c = static_cast<int>(i - tok * chunks);
+    const long long stride = static_cast<long long>(gridDim.x) * rows_per_it;
+    long long tok = static_cast<long long>(blockIdx.x) * rows_per_it + rl;
+    // software pipeline: the (id -> table row) loads of the NEXT row are in flight while this one is stored
+    long long n_id = tok < n_tok ? __ldg(ids + tok) : 0;
+    if (tok < n_tok && (n_id < 0 || n_id >= V)) { atomicExch(bad_flag, 1); n_id = 0; }
+    uint4 n_u = tok < n_tok ? __ldg(table + n_id * chunks + c) : make_uint4(0, 0, 0, 0);
+    const int col = c * 8;
+    for (; tok < n_tok; tok += stride) {
         uint4 u = n_u;
-        const long long i2 = i + stride;
-        if (i2 < total) {
-            n_tok_i = i2 / chunks;
-            n_id = __ldg(ids + n_tok_i);
+        const long long tok2 = tok + stride;
+        if (tok2 < n_tok) {
+            n_id = __ldg(ids + tok2);
             if (n_id < 0 || n_id >= V) { atomicExch(bad_flag, 1); n_id = 0; }
-            n_u = __ldg(table + n_id * chunks + (i2 - n_tok_i * chunks));
+            n_u = __ldg(table + n_id * chunks + c);
         }
-        const long long seg = tok / T;
-        const int t = static_cast<int>(tok - seg * T);
-        const long long xr = padded ? seg * (T + 2) + 1 + t : tok;
+        long long xr = tok;
+        int t = 0;
+        if (padded) {
+            const long long seg = tok / T;
+            t = static_cast<int>(tok - seg * T);
+            xr = seg * (T + 2) + 1 + t;
+        }
         uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        const int col = c * 8;
         if (p > 0.f) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -140,10 +146,12 @@ __global__ void gather_rows_kernel(const long long* __restrict__ ids, long long 
 int gather_rows(const long long* ids, long long n_tok, int T, const void* table, int V, int D, int ld_table, void* X,
                 int ld_x, int padded, DropoutCfg drop, int* bad_id_flag, cudaStream_t stream) {
     if (n_tok == 0) return 0;
-    NR_REQUIRE(ld_table == ld_x && ld_x % 8 == 0 && ld_x >= D + 1, "gather_rows: pitch %d/%d for D=%d", ld_table, ld_x, D);
-    const int blocks = static_cast<int>(std::min<long long>((n_tok + 7) / 8, 148 * 8));
+    NR_REQUIRE(ld_table == ld_x && ld_x % 8 == 0 && ld_x >= D + 1 && ld_x / 8 <= kGatherThreads,
+               "gather_rows: pitch %d/%d for D=%d", ld_table, ld_x, D);
+    const int rows_per_it = kGatherThreads / (ld_x / 8);
+    const int blocks = static_cast<int>(std::min<long long>((n_tok + rows_per_it - 1) / rows_per_it, 148 * 6));
     ProfScope ps("gather_rows", static_cast<int>(n_tok), D, ld_x, stream);
-    gather_rows_kernel<<<blocks, 256, 0, stream>>>(ids, n_tok, T, static_cast<const uint4*>(table), V, D, ld_x,
+    gather_rows_kernel<<<blocks, kGatherThreads, 0, stream>>>(ids, n_tok, T, static_cast<const uint4*>(table), V, D, ld_x,
                                                    static_cast<uint4*>(X), padded, drop.p, drop.seed, bad_id_flag);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
