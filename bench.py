@@ -136,6 +136,17 @@ def kernel_work(name):
     return 0.0, 0.0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in
+# profiles/ncu_r01_kernel_summary.csv (batch 512 shapes only; other shapes report null)
+NCU_DRAM_BYTES = {
+    "mhsa_core_bwd[28160,20,300]": 1.402330e9 + 0.996976e9,
+    "mhsa_core_fwd[28160,20,300]": 1.039078e9 + 0.326125e9,
+    "gemm_store[563200,900,300]": 0.443694e9 + 0.979511e9,
+    "gemm_additive_pool[563200,200,300]": 0.374886e9 + 0.030811e9,
+    "gemm_additive_dpre[563200,200,300]": 0.344909e9 + 0.191328e9,
+}
+
+
 def usable_cores():
     """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (os.cpu_count()
     reports the whole machine inside a container; oversubscribing OpenMP threads stalls the CPU arm)."""
@@ -294,7 +305,8 @@ def main():
         roof = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"]}
     else:
         roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
-    roof.update({"kernel": dom[0], "share_of_step": dom[1][1] / tot_prof, "avg_launch_ms": dur_s * 1e3, "traffic": None,
+    roof.update({"kernel": dom[0], "share_of_step": dom[1][1] / tot_prof, "avg_launch_ms": dur_s * 1e3,
+                 "traffic": NCU_DRAM_BYTES.get(dom[0].split("/")[1]), "algorithmic_bytes": bytes_,
                  "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)"})
     step_tf = value / world * 3 * FLOP_FWD_PER_IMPRESSION / 1e12
     breakdown = {k: round(v[1] / steps_profiled, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
