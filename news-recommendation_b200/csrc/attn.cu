@@ -141,12 +141,12 @@ template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // global rows [T][dk] at g (pitch ld, elements)  ->  tile rows.  piece = bytes per copy (8 / 4 / 2).
-__device__ __forceinline__ void tile_load(__nv_bfloat16* tile, const __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane) {
+__device__ __forceinline__ void tile_load(__nv_bfloat16* tile, const __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane, int nthr = 32) {
     const int epp = piece >> 1;        // elements per piece
     const int ppr = dk / epp;          // pieces per row
     const float inv = 1.0f / static_cast<float>(ppr);
     const int n = T * ppr;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += nthr) {
         const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
         const int c = (i - r * ppr) * epp;
         __nv_bfloat16* dst = tile + r * kPitch + c;
@@ -156,12 +156,12 @@ __device__ __forceinline__ void tile_load(__nv_bfloat16* tile, const __nv_bfloat
         else *dst = *src;
     }
 }
-__device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane) {
+__device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane, int nthr = 32) {
     const int epp = piece >> 1;
     const int ppr = dk / epp;
     const float inv = 1.0f / static_cast<float>(ppr);
     const int n = T * ppr;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += nthr) {
         const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
         const int c = (i - r * ppr) * epp;
         const __nv_bfloat16* src = tile + r * kPitch + c;
@@ -249,12 +249,12 @@ __device__ __forceinline__ void tile_store_dropout_map(const __nv_bfloat16* tile
 
 // context tile -> global with the dropout mask applied on the fly (one counter hash per 4 aligned columns)
 __device__ __forceinline__ void tile_store_dropout(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane,
-                                                   long long row0, int col0, uint64_t seed, uint32_t thresh, float scale) {
+                                                   long long row0, int col0, uint64_t seed, uint32_t thresh, float scale, int nthr = 32) {
     const int epp = piece >> 1;
     const int ppr = dk / epp;
     const float inv = 1.0f / static_cast<float>(ppr);
     const int n = T * ppr;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += nthr) {
         const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
         const int c = (i - r * ppr) * epp;
         const __nv_bfloat16* src = tile + r * kPitch + c;
@@ -292,8 +292,12 @@ __host__ __device__ inline int piece_bytes(int dk, int ld_a, int ld_b, int d) {
 // CT/CDK/CH > 0 pin the sequence length, head width and head count at compile time (8-byte pieces guaranteed by the
 // launcher): every shape guard, the piece plan and the task -> (sequence, head) division fold away.  ncu on the run-time
 // shaped kernel: 1200 warp instructions per 20x20 head, 650 of them integer/predicate/branch overhead.
-template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH>
-__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
+// COOP (history-level attention, T > 32): the WPS = TP/16 warps of a CTA share ONE task -- warp w owns the 16-row block w
+// -- instead of walking private tasks: 512 sequences x 15 heads are only 7,680 tasks, and one warp per 50x50 head left
+// 3 warps per SM resident (0.28 ms for 4 % of the tokens).  Tiles are loaded/stored by all threads, phases are separated
+// by __syncthreads instead of __syncwarp.
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH, bool COOP>
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
                                                                   int T_, int heads_, int dk_, __nv_bfloat16* __restrict__ ctx,
                                                                   int ld_ctx, float p, uint64_t seed) {
     constexpr int NTJ = TP / 8, MT = TP / 16;
@@ -304,17 +308,20 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int d = heads * dk;
-    for (int i = tid; i < (WPS * STG * 3 * TILE + (TP - T) * kPitch) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    static_assert(!COOP || (WPS == TP / 16 && !FAST), "cooperative CTAs: one warp per 16-row block, generic copy loops");
+    for (int i = tid; i < ((COOP ? 1 : WPS) * STG * 3 * TILE + (TP - T) * kPitch) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
     __syncthreads();
-    __nv_bfloat16* wbase = sm + warp * STG * 3 * TILE;
+    __nv_bfloat16* wbase = sm + (COOP ? 0 : warp) * STG * 3 * TILE;
+    const int ctid = COOP ? tid : lane, cnt = COOP ? WPS * 32 : 32;  // who copies a task's tiles
+    auto phase_sync = [&]() { if (COOP) __syncthreads(); else __syncwarp(); };
     const float sc = rsqrtf(static_cast<float>(dk)) * 1.4426950408889634f;
     const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
     const float dscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     const int ntj = (T + 7) >> 3;
     const int piece = CT > 0 ? 8 : piece_bytes(dk, ld, ld_ctx, d);
     const int n_tasks = static_cast<int>(n_seq * heads);  // < 2^31, checked by the launcher
-    const int W = gridDim.x * WPS;
-    const int gw = blockIdx.x * WPS + warp;
+    const int W = COOP ? gridDim.x : gridDim.x * WPS;
+    const int gw = COOP ? blockIdx.x : blockIdx.x * WPS + warp;
     PieceMap lmap, smap;
     if (FAST) {
         make_piece_map(lmap, T, dk, piece, ld, lane);
@@ -335,9 +342,9 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
                 tile_load_map(t0s + 4 * TILE, src + 2 * d, lmap, piece);
             } else {
                 __nv_bfloat16* t0 = wbase + stage * 3 * TILE;
-                tile_load(t0, src, ld, T, dk, piece, lane);
-                tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
-                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
+                tile_load(t0, src, ld, T, dk, piece, ctid, cnt);
+                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt);
+                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt);
             }
         }
         cp_commit();
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
     int stage = 0;
     for (int task = gw; task < n_tasks; task += W) {
         cp_wait<STG - 2>();
-        __syncwarp();
+        phase_sync();
         // the stage consumed in the previous iteration is free again: refill it before computing this task
         prefetch(task + (STG - 1) * W, (stage + STG - 1) % STG);
         const long long seq = task / heads;
@@ -359,6 +366,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             if (mt * 16 >= T) break;
+            if (COOP && mt != warp) continue;
             float s[NTJ][4];
 #pragma unroll
             for (int nt = 0; nt < NTJ; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
@@ -409,23 +417,23 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
                 }
             }
         }
-        __syncwarp();
+        phase_sync();
         __nv_bfloat16* out = ctx + seq * T * static_cast<long long>(ld_ctx);
         if constexpr (fast) {
             if (p > 0.f) tile_store_dropout_map(q, out + h * dk, smap, piece, ld_ctx, seq * T, h * dk, seed, thresh, dscale);
             else tile_store_map(q, out + h * dk, smap, piece);
         } else if (p > 0.f) {
-            tile_store_dropout(q, out + h * dk, ld_ctx, T, dk, piece, lane, seq * T, h * dk, seed, thresh, dscale);
+            tile_store_dropout(q, out + h * dk, ld_ctx, T, dk, piece, ctid, seq * T, h * dk, seed, thresh, dscale, cnt);
         } else {
-            tile_store(q, out + h * dk, ld_ctx, T, dk, piece, lane);
+            tile_store(q, out + h * dk, ld_ctx, T, dk, piece, ctid, cnt);
         }
         if (h == 0) {  // ones column + zero tail of the padded context rows
-            for (int i = lane; i < T * (ld_ctx - d); i += 32) {
+            for (int i = ctid; i < T * (ld_ctx - d); i += cnt) {
                 const int r = i / (ld_ctx - d), c = i - r * (ld_ctx - d);
                 out[static_cast<size_t>(r) * ld_ctx + d + c] = __float2bfloat16_rn(c == 0 ? 1.0f : 0.f);
             }
         }
-        __syncwarp();
+        phase_sync();
         stage = (stage + 1) % STG;
     }
     cp_wait<0>();
@@ -434,8 +442,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : 1)) mhsa_mma_fwd_ker
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH>
-__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH, bool COOP>
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
                                                                   const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
                                                                   long long n_seq, int T_, int heads_, int dk_,
                                                                   __nv_bfloat16* __restrict__ dqkv, int ld_d) {
@@ -446,9 +454,12 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int d = heads * dk;
     const int PER_WARP = STG * 4 * TILE + 2 * TP * SP;  // the P/dS scratch behind a warp's tiles doubles as read slack
-    for (int i = tid; i < WPS * PER_WARP / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    static_assert(!COOP || (WPS == TP / 16 && !FAST), "cooperative CTAs: one warp per 16-row block, generic copy loops");
+    for (int i = tid; i < (COOP ? 1 : WPS) * PER_WARP / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
     __syncthreads();
-    __nv_bfloat16* wbase = sm + warp * PER_WARP;
+    __nv_bfloat16* wbase = sm + (COOP ? 0 : warp) * PER_WARP;
+    const int ctid = COOP ? tid : lane, cnt = COOP ? WPS * 32 : 32;
+    auto phase_sync = [&]() { if (COOP) __syncthreads(); else __syncwarp(); };
     __nv_bfloat16* ps = wbase + STG * 4 * TILE;  // [TP][SP] probabilities (bf16)
     __nv_bfloat16* ds = ps + TP * SP;                // [TP][SP] score gradients (bf16)
     const float rs = rsqrtf(static_cast<float>(dk));
@@ -457,8 +468,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
     const int piece = CT > 0 ? 8
                              : (piece_bytes(dk, ld, ld_dctx, d) == 8 && (ld_d % 4) == 0 ? 8 : (piece_bytes(dk, ld, ld_dctx, d) >= 4 && (ld_d % 2) == 0 ? 4 : 2));
     const int n_tasks = static_cast<int>(n_seq * heads);
-    const int W = gridDim.x * WPS;
-    const int gw = blockIdx.x * WPS + warp;
+    const int W = COOP ? gridDim.x : gridDim.x * WPS;
+    const int gw = COOP ? blockIdx.x : blockIdx.x * WPS + warp;
     PieceMap lmap, gmap, smap;
     if (FAST) {
         make_piece_map(lmap, T, dk, piece, ld, lane);
@@ -482,10 +493,10 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
                 tile_load_map(t0s + 6 * TILE, gsrc, gmap, piece);
             } else {
                 __nv_bfloat16* t0 = wbase + stage * 4 * TILE;
-                tile_load(t0, src, ld, T, dk, piece, lane);
-                tile_load(t0 + TILE, src + d, ld, T, dk, piece, lane);
-                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, lane);
-                tile_load(t0 + 3 * TILE, gsrc, ld_dctx, T, dk, piece, lane);
+                tile_load(t0, src, ld, T, dk, piece, ctid, cnt);
+                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt);
+                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt);
+                tile_load(t0 + 3 * TILE, gsrc, ld_dctx, T, dk, piece, ctid, cnt);
             }
         }
         cp_commit();
@@ -496,7 +507,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
     int stage = 0;
     for (int task = gw; task < n_tasks; task += W) {
         cp_wait<STG - 2>();
-        __syncwarp();
+        phase_sync();
         // the stage consumed in the previous iteration is free again: refill it before computing this task
         prefetch(task + (STG - 1) * W, (stage + STG - 1) % STG);
         const long long seq = task / heads;
@@ -510,6 +521,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             if (mt * 16 >= T) continue;
+            if (COOP && mt != warp) continue;
             float dq[NTD][4];
 #pragma unroll
             for (int nd = 0; nd < NTD; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
@@ -594,12 +606,13 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
                 }
             }
         }
-        __syncwarp();
+        phase_sync();
         // ---- phase B (row blocks j): dK = dS^T Q, dV = P^T dCtx ----
         // (K and V tiles are dead after phase A: each row block's result goes straight into them)
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             if (mt * 16 >= T) continue;
+            if (COOP && mt != warp) continue;
             float dkk[NTD][4], dvv[NTD][4];
 #pragma unroll
             for (int nd = 0; nd < NTD; ++nd) {
@@ -635,41 +648,42 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : 1)) mhsa_mma_bwd_ker
                 }
             }
         }
-        __syncwarp();
+        phase_sync();
         if constexpr (fast) {
             tile_store_map(k, gout + d + h * dk, smap, piece);
             tile_store_map(v, gout + 2 * d + h * dk, smap, piece);
         } else {
-            tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, lane);
-            tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, lane);
+            tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, ctid, cnt);
+            tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, ctid, cnt);
         }
-        __syncwarp();
+        phase_sync();
         stage = (stage + 1) % STG;
     }
     cp_wait<0>();
 }
 
-template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT = 0, int CDK = 0, int CH = 0>
+template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT = 0, int CDK = 0, int CH = 0, bool COOP = false>
 int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     const long long tasks = n_seq * heads;
     NR_REQUIRE(tasks < (1ll << 31), "mhsa: too many (sequence, head) tasks");
     const size_t tile = sizeof(__nv_bfloat16) * T * kPitch;
-    const size_t smem_f = WPS * STG * 3 * tile + sizeof(__nv_bfloat16) * (TP - T) * kPitch;
-    const size_t smem_b = WPS * (STG * 4 * tile + sizeof(__nv_bfloat16) * 2 * TP * (TP + 8));
+    const int sets = COOP ? 1 : WPS;  // tile sets per CTA: one per warp, or one shared by the cooperative CTA
+    const size_t smem_f = sets * STG * 3 * tile + sizeof(__nv_bfloat16) * (TP - T) * kPitch;
+    const size_t smem_b = sets * (STG * 4 * tile + sizeof(__nv_bfloat16) * 2 * TP * (TP + 8));
     const size_t smem = bwd ? smem_b : smem_f;
     NR_REQUIRE(smem <= 227 * 1024, "mhsa: tile set of %zu bytes exceeds shared memory", smem);
-    const int per_sm = std::max<int>(1, std::min<size_t>(6, (224 * 1024) / (smem + 1024)));
-    const int grid = static_cast<int>(std::min<long long>(ceil_div(static_cast<int>(std::min<long long>(tasks, 1 << 30)), WPS),
+    const int per_sm = std::max<int>(1, std::min<size_t>(COOP ? 3 : 6, (224 * 1024) / (smem + 1024)));
+    const int grid = static_cast<int>(std::min<long long>(ceil_div(static_cast<int>(std::min<long long>(tasks, 1 << 30)), COOP ? 1 : WPS),
                                                           static_cast<long long>(num_sms()) * per_sm));
     if (!bwd) {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out, drop.p,
                                                                              drop.seed);
     } else {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
                                                                              static_cast<const __nv_bfloat16*>(dctx), ld_dctx, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out);
     }
@@ -703,9 +717,26 @@ int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int 
 template <int TP, int KSD, int NTD>
 int launch_mma(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
-    // 64-row tiles (history-level attention) are 4x larger: the backward keeps a shallower ring on fewer warps
-    if (TP > 32 && bwd)
-        return launch_mma_cfg<TP, KSD, NTD, 2, 3>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    // 64-row tiles (history-level attention): one cooperative CTA of TP/16 warps per (sequence, head)
+    if constexpr (TP > 32) {
+        static const bool no_coop = getenv("NEWSREC_ATTN_NOCOOP") != nullptr;  // tuning switch
+        if (!no_coop) {
+            if constexpr (TP == 64 && KSD == 2 && NTD == 3) {
+                // the reference's user encoder (config.py: num_clicked_news_a_user 50, 15 heads x 20): fixed shape
+                const int d = heads * dk;
+                int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, d);
+                if (bwd && (ld_out % 4) != 0) piece = 0;
+                static const bool no_fixed = getenv("NEWSREC_ATTN_GENERIC") != nullptr;
+                if (!no_fixed && piece == 8 && T == 50 && dk == 20 && heads == 15)
+                    return launch_mma_cfg2<TP, KSD, NTD, 2, TP / 16, false, 50, 20, 15, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads,
+                                                                                              dk, out, ld_out, drop, stream);
+            }
+            return launch_mma_cfg2<TP, KSD, NTD, 2, TP / 16, false, 0, 0, 0, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out,
+                                                                                   ld_out, drop, stream);
+        }
+        if (bwd)
+            return launch_mma_cfg<TP, KSD, NTD, 2, 3>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    }
     return launch_mma_cfg<TP, KSD, NTD, 2, 4>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
 }
 

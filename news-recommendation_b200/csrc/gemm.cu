@@ -302,13 +302,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (n_my > 0) {
+        // producer and issuer loops are warp-uniform, one elected lane issues (see gemm_nt)
         if (warp == 4) {
-            if (lane == 0) {
-                int st = 0;
-                uint32_t ph = 0;
-                for (int c = 0; c < n_my; ++c) {
-                    const int k0 = (chunk0 + c) * 64;
-                    mbar_wait(&empty[st], ph ^ 1, 201);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int c = 0; c < n_my; ++c) {
+                const int k0 = (chunk0 + c) * 64;
+                mbar_wait(&empty[st], ph ^ 1, 201);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full[st], static_cast<uint32_t>(stage_bytes));
                     uint8_t* sa = smem + st * stage_bytes;
                     uint8_t* sb = sa + 2 * 8192;
@@ -316,34 +317,38 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_2d(sa + 8192, &tmA, &full[st], mt * 128 + 64, k0);
                     for (int j = 0; j < p.n_boxes; ++j)
                         tma_load_2d(sb + j * 8192, &tmB, &full[st], p.b_col0 + j * 64, k0 + p.b_row_shift);
-                    if (++st == p.stages) { st = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++st == p.stages) { st = 0; ph ^= 1; }
             }
         } else if (warp == 5) {
-            if (lane == 0) {
-                const uint32_t idesc0 = make_idesc_bf16(kTileM, n0, 1, 1);
-                const uint32_t idesc1 = make_idesc_bf16(kTileM, n1 > 0 ? n1 : 16, 1, 1);
-                int st = 0;
-                uint32_t ph = 0;
-                uint32_t acc = 0;
-                for (int c = 0; c < n_my; ++c) {
-                    mbar_wait(&full[st], ph, 202);
-                    tc_fence_after();
+            const uint32_t idesc0 = make_idesc_bf16(kTileM, n0, 1, 1);
+            const uint32_t idesc1 = make_idesc_bf16(kTileM, n1 > 0 ? n1 : 16, 1, 1);
+            int st = 0;
+            uint32_t ph = 0;
+            uint32_t acc = 0;
+            for (int c = 0; c < n_my; ++c) {
+                mbar_wait(&full[st], ph, 202);
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t sa = smem_u32(smem + st * stage_bytes);
                     const uint32_t sb = sa + 2 * 8192;
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = make_sw128_desc(sa + k * 2048, 8192, 1024);
-                        umma_bf16(tmem_base, da, make_sw128_desc(sb + k * 2048, 8192, 1024), idesc0, acc);
-                        if (n1 > 0)
-                            umma_bf16(tmem_base + 256, da, make_sw128_desc(sb + 4 * 8192 + k * 2048, 8192, 1024), idesc1,
-                                      acc);
-                        acc = 1;
+                    const uint64_t da = make_sw128_desc(sa, 8192, 1024);
+                    const uint64_t db0 = make_sw128_desc(sb, 8192, 1024);
+                    const uint64_t db1 = make_sw128_desc(sb + 4 * 8192, 8192, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // +2048 bytes per k-step = +128 in the descriptor's >>4 address field
+                        umma_bf16(tmem_base, da + 128 * k, db0 + 128 * k, idesc0, (k == 0) ? acc : 1u);
+                        if (n1 > 0) umma_bf16(tmem_base + 256, da + 128 * k, db1 + 128 * k, idesc1, (k == 0) ? acc : 1u);
                     }
                     umma_commit(&empty[st]);
-                    if (++st == p.stages) { st = 0; ph ^= 1; }
                 }
-                umma_commit(tfull);
+                __syncwarp();
+                acc = 1;
+                if (++st == p.stages) { st = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(tfull);
+            __syncwarp();
         } else {
             mbar_wait(tfull, 0, 203);
             tc_fence_after();

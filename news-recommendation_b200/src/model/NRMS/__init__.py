@@ -7,7 +7,7 @@ from model.general.click_predictor.dot_product import DotProductClickPredictor
 from model.NRMS.news_encoder import NewsEncoder
 from model.NRMS.user_encoder import UserEncoder
 from newsrec_b200 import require_cuda
-from newsrec_b200.pack import SlotPacker
+from newsrec_b200.pack import PackedBatch, SlotPacker
 
 
 class NRMS(torch.nn.Module):
@@ -18,13 +18,27 @@ class NRMS(torch.nn.Module):
         self.user_encoder = UserEncoder(config)
         self.click_predictor = DotProductClickPredictor()
         self._packer = SlotPacker()
+        self._copy_stream = None
 
-    def forward(self, candidate_news, clicked_news):
-        """candidate_news: list of 1+K dicts {"title": (batch, T)}; clicked_news: list of H such dicts
-        (slot-major, exactly what the reference's DataLoader yields).  Returns (batch, 1+K) logits."""
+    def prefetch(self, candidate_news, clicked_news):
+        """Stage the NEXT batch while the current step runs: host-side stacking into pinned memory, one H2D copy and
+        the device-side re-ordering, all on a private copy stream.  Pass the returned PackedBatch to forward()."""
         dev = require_cuda()
-        C, H = len(candidate_news), len(clicked_news)
-        ids, B = self._packer.pack(clicked_news, candidate_news, "title", dev)  # (B*H + B*C, T): browsed block, then candidates
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        return self._packer.pack_on_stream(clicked_news, candidate_news, "title", dev, self._copy_stream)
+
+    def forward(self, candidate_news, clicked_news=None):
+        """candidate_news: list of 1+K dicts {"title": (batch, T)}; clicked_news: list of H such dicts
+        (slot-major, exactly what the reference's DataLoader yields) -- or one PackedBatch from prefetch().
+        Returns (batch, 1+K) logits."""
+        dev = require_cuda()
+        if isinstance(candidate_news, PackedBatch):
+            pb = candidate_news
+            ids, B, H, C = pb.wait(), pb.B, pb.H, pb.C
+        else:
+            C, H = len(candidate_news), len(clicked_news)
+            ids, B = self._packer.pack(clicked_news, candidate_news, "title", dev)  # (B*H + B*C, T): browsed block, then candidates
         vec = self.news_encoder.encode_ids(ids)
         d = vec.shape[1]
         clicked_news_vector = vec[:B * H].view(B, H, d)

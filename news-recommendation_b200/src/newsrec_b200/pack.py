@@ -6,6 +6,21 @@ from __future__ import annotations
 import torch
 
 
+class PackedBatch:
+    """Device-resident, impression-major ids of one batch, produced ahead of time on a copy stream
+    (`NRMS.prefetch`): `ids` (B*H + B*C, ...), the event that marks the end of its H2D copy and re-ordering."""
+
+    def __init__(self, ids, B, H, C, event):
+        self.ids, self.B, self.H, self.C, self.event = ids, B, H, C, event
+
+    def wait(self):
+        """Make the current stream wait for the copy and keep the allocator from recycling `ids` under it."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.event)
+        self.ids.record_stream(cur)
+        return self.ids
+
+
 class SlotPacker:
     """Two pinned staging buffers per shape, each guarded by a CUDA event so that a buffer is never
     rewritten by the host while its previous H2D copy is still in flight."""
@@ -46,3 +61,12 @@ class SlotPacker:
         a = slots[:H].transpose(0, 1).reshape(B * H, *tail)
         b = slots[H:].transpose(0, 1).reshape(B * (slots.shape[0] - H), *tail)
         return torch.cat((a, b), dim=0), B
+
+    def pack_on_stream(self, clicked, candidates, field, dev, stream):
+        """`pack` issued on `stream` (a copy stream): the host-side stacking, the H2D transfer and the device-side
+        re-ordering of the NEXT batch overlap the kernels of the current step.  Returns a PackedBatch."""
+        with torch.cuda.stream(stream):
+            ids, B = self.pack(clicked, candidates, field, dev)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return PackedBatch(ids, B, len(clicked), len(candidates), ev)

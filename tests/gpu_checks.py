@@ -329,6 +329,21 @@ def check_nrms_direct_grad_accumulation(B=8, Cn=5, H=50, T=20, V=500, seed=6):
             "grads_are_flat_views": all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in model_b.parameters())}
 
 
+def check_nrms_prefetch_equals_direct(B=8, Cn=5, H=50, T=20, V=500, seed=7):
+    """NRMS.prefetch (copy stream) + forward(PackedBatch) gives bit-identical logits to forward(lists)."""
+    cand_t, clicked_t, _ = O.synth_batch(B, Cn, H, T, V, seed * 100)
+    model, _ = nrms_model_and_params(V, seed)
+    model.eval()
+    with torch.no_grad():
+        a = model(slots(cand_t), slots(clicked_t))
+        pb = model.prefetch(slots(cand_t), slots(clicked_t))
+        b = model(pb)
+        pb2 = model.prefetch(slots(cand_t), slots(clicked_t))  # a second staged batch while the first is alive
+        c = model(pb2)
+    torch.cuda.synchronize()
+    return {"maxabs": float((a - b).abs().max()), "maxabs_second": float((a - c).abs().max())}
+
+
 def check_nrms_eval_api(V=300, seed=9):
     """get_news_vector / get_user_vector (non-contiguous input, evaluate.py:220-224) / get_prediction."""
     model, sd = nrms_model_and_params(V, seed)

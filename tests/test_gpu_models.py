@@ -42,6 +42,11 @@ def test_nrms_in_place_gradient_accumulation_matches_returned_gradients():
     assert r["direct_vs_returned_rel_maxabs"] < 1e-5 and r["after_zero_rel_maxabs"] < 1e-5, r
 
 
+def test_nrms_prefetched_batch_is_bit_identical():
+    r = G.check_nrms_prefetch_equals_direct()
+    assert r["maxabs"] == 0.0 and r["maxabs_second"] == 0.0, r
+
+
 def test_nrms_eval_api_noncontiguous_history():
     r = G.check_nrms_eval_api()
     assert r["user_input_noncontig"] and r["pred_tolist_len"] == 7, r
