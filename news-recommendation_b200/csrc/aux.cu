@@ -237,6 +237,65 @@ __global__ void __launch_bounds__(256) pool_dscore_kernel(const __nv_bfloat16* _
         __syncthreads();
     }
 }
+// Title-level shape (seg_len <= 32, D <= 512): one WARP per segment, no shared memory and no block barrier.  The
+// segment's dOut chunk stays in registers for all its rows, 5 rows x 2 16-byte loads are in flight per lane, and the
+// per-row totals come out of one 31-shuffle transpose reduction (lane t ends with dw_t) instead of 5 shuffles per row.
+__global__ void __launch_bounds__(256) pool_dscore_warp_kernel(const __nv_bfloat16* __restrict__ X, int lda, int D,
+                                                               long long n_seg, int seg_len, const float* __restrict__ w,
+                                                               const float* __restrict__ dout, int ldo,
+                                                               float* __restrict__ dscore) {
+    const int lane = threadIdx.x & 31;
+    const int chunks = (D + 7) >> 3;  // the last one may be half valid (D % 8 == 4): its dOut half is zeroed below
+    const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+    for (long long seg = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); seg < n_seg; seg += wstride) {
+        const float* dob = dout + seg * ldo;
+        float4 dd[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            dd[h][0] = (c < chunks && c * 8 + 4 <= D) ? *reinterpret_cast<const float4*>(dob + c * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dd[h][1] = (c < chunks && c * 8 + 8 <= D) ? *reinterpret_cast<const float4*>(dob + c * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const uint4* xs = reinterpret_cast<const uint4*>(X + seg * seg_len * static_cast<long long>(lda));
+        const int pitch16 = lda >> 3;
+        float pr[32];
+#pragma unroll
+        for (int tb = 0; tb < 32; tb += 4) {
+            uint4 u[4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int t = tb + k;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = lane + 32 * h;
+                    u[k][h] = (t < seg_len && c < chunks) ? __ldg(xs + static_cast<long long>(t) * pitch16 + c) : make_uint4(0, 0, 0, 0);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint4 v = u[k][h];
+                    const float2 f0 = unpack_bf16x2(v.x), f1 = unpack_bf16x2(v.y), f2 = unpack_bf16x2(v.z), f3 = unpack_bf16x2(v.w);
+                    a = fmaf(f0.x, dd[h][0].x, a); a = fmaf(f0.y, dd[h][0].y, a); a = fmaf(f1.x, dd[h][0].z, a); a = fmaf(f1.y, dd[h][0].w, a);
+                    a = fmaf(f2.x, dd[h][1].x, a); a = fmaf(f2.y, dd[h][1].y, a); a = fmaf(f3.x, dd[h][1].z, a); a = fmaf(f3.y, dd[h][1].w, a);
+                }
+                pr[tb + k] = a;
+            }
+            if (tb + 4 >= seg_len) {  // warp-uniform: the remaining row slots stay zero
+#pragma unroll
+                for (int t = tb + 4; t < 32; ++t) pr[t] = 0.f;
+                break;
+            }
+        }
+        const float dw = warp_transpose_sum32(pr);  // lane t: dOut . X_t
+        const float wt = lane < seg_len ? __ldg(w + seg * seg_len + lane) : 0.f;
+        const float dot = warp_sum(wt * dw);
+        if (lane < seg_len) dscore[seg * seg_len + lane] = wt * (dw - dot);
+    }
+}
+
 int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, const float* w, const float* dout, int ldo,
                 float* dscore, cudaStream_t stream) {
     if (n_seg == 0) return 0;
@@ -244,6 +303,14 @@ int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, con
     const long long groups = (n_seg + kDsSegs - 1) / kDsSegs;
     const int blocks = static_cast<int>(std::min<long long>(groups, 148 * 8));
     ProfScope ps("pool_dscore", static_cast<int>(n_seg), seg_len, D, stream);
+    if (seg_len <= 32 && D <= 512) {
+        const int wblocks = static_cast<int>(std::min<long long>((n_seg + 7) / 8, 148 * 8));
+        pool_dscore_warp_kernel<<<wblocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(X), lda, D, n_seg, seg_len, w, dout, ldo,
+                                                             dscore);
+        ++g_launches;
+        NR_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     pool_dscore_kernel<<<blocks, 256, sizeof(float) * kDsSegs * seg_len, stream>>>(
         static_cast<const __nv_bfloat16*>(X), lda, D, n_seg, seg_len, w, dout, ldo, dscore);
     ++g_launches;
