@@ -42,31 +42,44 @@ int cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, in
     return 0;
 }
 
-// fp32 rows [n_seq][T][D] (arbitrary element strides) -> bf16 rows [n_seq*T x ld] with a ones column at D
-__global__ void rows_to_bf16_kernel(const float* __restrict__ src, long long n_rows, int T, int D, long long s_seq,
-                                    long long s_tok, long long s_col, __nv_bfloat16* __restrict__ dst, int ld) {
-    const long long total = n_rows * ld;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / ld;
-        const int c = static_cast<int>(i - r * ld);
+// fp32 rows [n_seq][T][D] (arbitrary element strides) -> bf16 rows [n_seq*T x ld] with a ones column at D.
+// One thread per 8-column chunk column, a block walks kRowsThreads / chunks rows per iteration (no division in the loop).
+constexpr int kRowsThreads = 320;
+__global__ void __launch_bounds__(kRowsThreads) rows_to_bf16_kernel(const float* __restrict__ src, long long n_rows, int T, int D,
+                                                                  long long s_seq, long long s_tok, long long s_col,
+                                                                  __nv_bfloat16* __restrict__ dst, int ld) {
+    const int chunks = ld >> 3;
+    const int rows_per_it = kRowsThreads / chunks;
+    const int rl = threadIdx.x / chunks, c = threadIdx.x - rl * chunks;
+    if (rl >= rows_per_it) return;
+    const int col = c * 8;
+    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_it + rl; r < n_rows;
+         r += static_cast<long long>(gridDim.x) * rows_per_it) {
         const long long seq = r / T;
         const long long tok = r - seq * T;
-        float v = 0.f;
-        if (c < D) v = src[seq * s_seq + tok * s_tok + c * s_col];
-        else if (c == D) v = 1.0f;
-        dst[i] = __float2bfloat16_rn(v);
+        const float* sp = src + seq * s_seq + tok * s_tok;
+        float v[8];
+        if (s_col == 1 && col + 8 <= D && ((reinterpret_cast<uintptr_t>(sp + col) & 15) == 0)) {
+            const float4 a = *reinterpret_cast<const float4*>(sp + col), b = *reinterpret_cast<const float4*>(sp + col + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = col + j < D ? sp[(col + j) * s_col] : (col + j == D ? 1.0f : 0.f);
+        }
+        *reinterpret_cast<uint4*>(dst + r * ld + col) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
 }
 int rows_to_bf16(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col,
                  void* dst, int ld, cudaStream_t stream) {
     const long long n = n_seq * T;
     if (n == 0) return 0;
-    NR_REQUIRE(ld >= D + 1, "rows_to_bf16: pitch %d too small for D=%d plus the ones column", ld, D);
-    const int blocks = static_cast<int>(std::min<long long>((n * ld + 255) / 256, 148 * 16));
+    NR_REQUIRE(ld >= D + 1 && ld % 8 == 0 && ld / 8 <= kRowsThreads, "rows_to_bf16: pitch %d for D=%d plus the ones column", ld, D);
+    const int rows_per_it = kRowsThreads / (ld / 8);
+    const int blocks = static_cast<int>(std::min<long long>((n + rows_per_it - 1) / rows_per_it, 148 * 6));
     ProfScope ps("rows_to_bf16", static_cast<int>(n), D, ld, stream);
-    rows_to_bf16_kernel<<<blocks, 256, 0, stream>>>(src, n, T, D, s_seq, s_tok, s_col, static_cast<__nv_bfloat16*>(dst),
-                                                    ld);
+    rows_to_bf16_kernel<<<blocks, kRowsThreads, 0, stream>>>(src, n, T, D, s_seq, s_tok, s_col, static_cast<__nv_bfloat16*>(dst),
+                                                             ld);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -357,15 +357,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float* drow = p.D + static_cast<size_t>(valid ? grow : 0) * p.ldd;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
             const int nch = (p.Nb + 31) >> 5;
+            const bool vec4 = (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0;
             for (int ch = 0; ch < nch; ++ch) {
                 float x[32];
                 tmem_ld32(taddr + ch * 32, x);
                 tmem_ld_wait();
                 if (!valid) continue;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 32; j += 4) {  // 16-byte vector reductions: 4x fewer L2 atomic operations
                     const int col = ch * 32 + j;
-                    if (col < p.Nb) red_add_f32(drow + col, x[j]);
+                    if (vec4 && col + 4 <= p.Nb) {
+                        red_add_v4_f32(drow + col, x[j], x[j + 1], x[j + 2], x[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (col + i < p.Nb) red_add_f32(drow + col + i, x[j + i]);
+                    }
                 }
             }
         }
