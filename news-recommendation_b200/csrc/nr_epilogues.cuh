@@ -197,7 +197,7 @@ struct EpiStore {
 // Additive-attention pooling (reference additive.py:35-53) fused behind  pre = X.Wa^T:
 //   score_r = sum_c tanh(pre_rc + ba_c) * qv_c ; w = softmax over the segment ; out_s = sum_r w_r X_r
 // Requires n_slices == 1 and rows_per_tile = (segments per tile) * seg_len.
-// scratch floats: [0,256) partial scores (half*128 + row) | [256,384) weights | [512,768) bias | [768,1024) query
+// scratch floats: [0,384) partial scores (part*128 + row) | [384,512) weights | [512,768) bias | [768,1024) query
 // ------------------------------------------------------------------------------------------------
 struct EpiPool {
     static constexpr int kScratchBytes = 4096;
@@ -262,18 +262,25 @@ struct EpiPool {
                 }
             });
         float* s_part = c.scratch;
-        float* s_w = c.scratch + 256;
+        float* s_w = c.scratch + 384;
+        static_assert(kEpiParts <= 3, "EpiPool scratch layout");
+        auto row_score = [&](int r) {
+            float t = s_part[r];
+#pragma unroll
+            for (int pp = 1; pp < kEpiParts; ++pp) t += s_part[pp * 128 + r];
+            return t;
+        };
         s_part[c.half * 128 + c.r] = score;
         epi_bar_sync();
         if (c.half == 0) {
             float w = 0.f;
             if (c.valid) {
                 const int s0 = (c.r / seg_len) * seg_len;
-                const float mine = s_part[c.r] + s_part[128 + c.r];
+                const float mine = row_score(c.r);
                 float m = -INFINITY;
-                for (int t = 0; t < seg_len; ++t) m = fmaxf(m, s_part[s0 + t] + s_part[128 + s0 + t]);
+                for (int t = 0; t < seg_len; ++t) m = fmaxf(m, row_score(s0 + t));
                 float sum = 0.f;
-                for (int t = 0; t < seg_len; ++t) sum += __expf(s_part[s0 + t] + s_part[128 + s0 + t] - m);
+                for (int t = 0; t < seg_len; ++t) sum += __expf(row_score(s0 + t) - m);
                 w = __fdividef(__expf(mine - m), sum);
                 if (w_out != nullptr) w_out[c.grow] = w;
             }

@@ -10,19 +10,21 @@
 //  gemm_tn : D[Ma x Nb] += A[Kr x Ma]^T . B[Kr x Nb]  (both MN-major; weight gradients, Kr = all tokens)
 //            split over Kr across CTAs, fp32 red.global.add epilogue.
 //
-// Warp roles of gemm_nt (320 threads per CTA, CTAs launched as pairs): warps 0-7 epilogue (TMEM lane quarter =
-// warp & 3; the two warps of a quarter split the accumulator columns -- with 4 warps the row-per-thread epilogue was
-// latency bound at ~20 % issue utilisation, ncu profiles/), warp 8 TMA producer, warp 9 TMEM allocator and, in the
-// leader CTA, MMA issuer.
+// Warp roles of gemm_nt (kGemmThreads per CTA, CTAs launched as pairs): warps 0..kEpiWarps-1 epilogue (TMEM lane
+// quarter = warp & 3; the kEpiParts warps of a quarter split the accumulator columns -- with 4 warps the row-per-thread
+// epilogue was latency bound at ~20 % issue utilisation, ncu profiles/), then the TMA producer warp and the warp that
+// allocates TMEM and, in the leader CTA, issues the MMAs.
 // gemm_tn keeps 192 threads (4 epilogue warps, one-shot epilogue).
 #pragma once
 #include "nr_common.cuh"
 
 namespace nr {
 
-constexpr int kGemmThreads = 320;   // gemm_nt
 constexpr int kTnThreads = 192;     // gemm_tn
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 8;                    // gemm_nt epilogue warps: 4 TMEM lane quarters x kEpiParts column parts
+constexpr int kEpiParts = kEpiWarps / 4;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGemmThreads = kEpiThreads + 64;  // + TMA producer warp + MMA warp
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                     // bf16 elements per 128-byte swizzle row
 constexpr int kAStageBytes = kTileM * 128;      // 16 KB
@@ -57,7 +59,7 @@ struct EpiCtx {
     int col0;     // first output column of this CTA's slice
     int ncols;    // valid output columns in the slice
     int tid;      // 0..255 within the epilogue group
-    int half;     // 0 / 1: which of the two warps of this TMEM lane quarter
+    int half;     // 0 .. kEpiParts-1: which of the warps of this TMEM lane quarter (column part)
     int ch0, ch1; // this thread's range of 32-column chunks
     float* scratch;  // Epi::kScratchBytes of shared memory private to the epilogue group
     int it;          // how many tiles this CTA has finished before this one (double-buffer parity)
@@ -71,13 +73,13 @@ struct EpiInit {
     int num_tiles;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 // the two column halves run different chunk counts: barriers inside a chunk loop are per half
-__device__ __forceinline__ void epi_bar_sync_half(int half) { asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory"); }
-__device__ __forceinline__ void epi_chunk_range(int ncols, int half, int& ch0, int& ch1) {
-    const int nch = (ncols + 31) >> 5, mid = (nch + 1) >> 1;
-    ch0 = half ? mid : 0;
-    ch1 = half ? nch : mid;
+
+__device__ __forceinline__ void epi_chunk_range(int ncols, int part, int& ch0, int& ch1) {
+    const int nch = (ncols + 31) >> 5, base = nch / kEpiParts, rem = nch - base * kEpiParts;
+    ch0 = part * base + min(part, rem);
+    ch1 = ch0 + base + (part < rem ? 1 : 0);
 }
 
 struct TmemAcc {
@@ -139,7 +141,7 @@ __device__ __forceinline__ void epi_chunks(const Acc& acc, const EpiCtx& c, Pre&
 // Measured alone (tools/stbench.cu): 5.7 TB/s vs 2.6 (2 x STG.128) / 5.0 (STG.256); inside the GEMM the row-per-thread
 // stores sat in the LSU queue and stalled the warps on their source registers (ncu, profiles/).
 constexpr int kTileStoreBufs = 2;                                  // staging tiles per warp (2 KB each)
-constexpr int kTileStoreBytes = 8 * kTileStoreBufs * 2048 + 1024;  // 8 warps + alignment slack
+constexpr int kTileStoreBytes = kEpiWarps * kTileStoreBufs * 2048 + 1024;  // + alignment slack
 struct WarpTileStore {
     uint8_t* buf;  // this warp's kTileStoreBufs x 2 KB (1024-byte aligned)
     int nput;
@@ -237,7 +239,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     };
 
-    if (warp == 8 && lane == 0) {
+    if (warp == kEpiWarps && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < p.stages; ++i) {
@@ -250,7 +252,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tempty[i], 2 * (kEpiThreads / 32));
         }
         fence_barrier_init();
-    } else if (warp == 9) {
+    } else if (warp == kEpiWarps + 1) {
         tmem_alloc_pair(tmem_slot, 512);
     }
     tc_fence_before();
@@ -259,7 +261,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kEpiWarps) {
         // ===================== TMA producer (both CTAs; uniform loops, one elected lane issues) =====================
         const uint32_t bfull_l = mapa_shared(bfull, 0);
         if (elect_one()) {
@@ -291,7 +293,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
         }
         if (tmr != nullptr && lane == 0) tmr[0] = tw_a;
-    } else if (warp == 9) {
+    } else if (warp == kEpiWarps + 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         // The whole warp runs the loops (uniform control flow) and one elected lane issues: under an `if (lane == 0)`
         // the compiler wraps every tcgen05 instruction in a uniform-register waterfall loop, and together with the
@@ -335,7 +337,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (tmr != nullptr && lane == 0) { tmr[1] = tw_a; tmr[2] = tw_b; tmr[7] = tw_c; tmr[8] = tw_d; }
         }
     } else {
-        // ===================== epilogue warps 0..7 (both CTAs, own TMEM rows) =====================
+        // ===================== epilogue warps 0..kEpiWarps-1 (both CTAs, own TMEM rows) =====================
         const int tile_step = 2 * ptile_step;
         const EpiInit ei{col0, ncols, static_cast<int>(threadIdx.x), scratch, 2 * ptile0 + static_cast<int>(rank), p.num_m_tiles};
         epi.init(ei, tile_step);
@@ -372,7 +374,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // nobody leaves (or frees TMEM) while the partner may still read its shared memory / signal it
-    if (warp == 9) tmem_dealloc_pair(tmem_base, 512);
+    if (warp == kEpiWarps + 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // Debug backend (triage only, NR_DEBUG_SIMT_GEMM=1): plain SIMT accumulate + the SAME epilogue functors.
