@@ -26,6 +26,21 @@ def test_tcgen05_linear_bf16_out(kw):
     assert r["nan"] == 0 and r["rel"] < 3e-3, r
 
 
+@pytest.mark.parametrize("kw", [
+    dict(M=1, N=900, K=300),                # one tile: the peer CTA of the pair works on a phantom (zero-filled) tile
+    dict(M=128 * 2 + 1, N=300, K=200),      # odd number of 128-row tiles, two weight slices
+    dict(M=128 * 5, N=20, K=300),           # narrower than one 32-column chunk: no TMA-store chunk at all
+    dict(M=300, N=33, K=64),                # one full chunk + a 1-column tail through the row-per-thread path
+    dict(M=300, N=257, K=300),              # two slices, the second one 16 MMA columns wide
+    dict(M=4000, N=240, K=16),              # a single k-step
+    dict(M=4000, N=512, K=65),              # K tail of one element in the second k-chunk
+])
+def test_tcgen05_linear_edge_shapes(kw):
+    """CTA-pair scheduling, slice splitting and the TMA-store / row-per-thread boundary at awkward shapes."""
+    r = G.check_linear(**kw)
+    assert r["nan"] == 0 and r["rel"] < 3e-3, r
+
+
 def test_tcgen05_linear_fp32_out_k900():
     r = G.check_linear(M=777, N=300, K=900, out_bf16=0)
     assert r["nan"] == 0 and r["rel"] < 1e-5, r
@@ -56,7 +71,8 @@ def test_attention_core(kw):
     assert r["ones_col"] and r["fwd_rel"] < 1e-3 and r["bwd_rel"] < 1e-3, r
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(N=9, S=50), dict(N=50, S=4, D=400)])
+@pytest.mark.parametrize("kw", [dict(), dict(N=9, S=50), dict(N=50, S=4, D=400), dict(N=1, S=20), dict(N=13, S=32, D=296),
+                                dict(N=700, S=20, q=64)])
 def test_additive_attention(kw):
     r = G.check_additive(**kw)
     assert r["fwd_rel"] < 1e-5, r
