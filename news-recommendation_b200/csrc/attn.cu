@@ -20,7 +20,11 @@ extern int g_launches;
 
 namespace {
 
-constexpr int kPitch = 40;  // bf16 elements per tile row (80 B: 16-byte aligned, ldmatrix conflict-free)
+constexpr int kPitch = 40;   // bf16 elements per tile row (80 B: 16-byte aligned, ldmatrix conflict-free), generic kernels
+constexpr int kPitch24 = 24; // fixed-shape d_k = 20 kernels: 48-byte rows (also conflict-free: 8 rows x 16 B hit 8 distinct bank
+                             // quads); the second k-step over d_k is then an m16n8k8 MMA over columns 16..23 (20..23 stay zero).
+                             // 40 % less shared memory per tile -> 4 instead of 3 resident CTAs (backward), 6 instead of 5 (forward):
+                             // the kernels are latency bound (25-36 % issue-active, ncu profiles/), residency is what they lack.
 
 __device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -36,6 +40,15 @@ __device__ __forceinline__ void ldsm_x2(uint32_t* r, const void* p) {
 __device__ __forceinline__ void ldsm_x2_t(uint32_t* r, const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
 }
+__device__ __forceinline__ void ldsm_x1(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r[0]) : "r"(smem_u32(p)));
+}
+// m16n8k8: A (16 x 8) = 2 registers, B (8 x 8) = 1 register
+__device__ __forceinline__ void mma_bf16_k8(float* c, const uint32_t* a, const uint32_t* b) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(b[0]));
+}
 __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint32_t* b) {
     // not volatile: a pure register operation, the compiler may interleave independent MMAs with the softmax arithmetic
     asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -46,6 +59,13 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint
 // A fragment (16 x 16) of a row-major [row][k] tile:           rows row0.., k columns k0..
 __device__ __forceinline__ void load_a(uint32_t* a, const __nv_bfloat16* tile, int pitch, int row0, int k0, int lane) {
     ldsm_x4(a, tile + (row0 + (lane & 15)) * pitch + k0 + ((lane >> 4) << 3));
+}
+// 16 x 8 A fragment / 8 x 8 B fragment (B[k][n] = tile[n][k]) of the m16n8k8 tail step
+__device__ __forceinline__ void load_a8(uint32_t* a, const __nv_bfloat16* tile, int pitch, int row0, int k0, int lane) {
+    ldsm_x2(a, tile + (row0 + (lane & 15)) * pitch + k0);
+}
+__device__ __forceinline__ void load_b8(uint32_t* b, const __nv_bfloat16* tile, int pitch, int n0, int k0, int lane) {
+    ldsm_x1(b, tile + (n0 + (lane & 7)) * pitch + k0);
 }
 // A fragment of A = M^T where M is stored row-major [k][m]:      m rows m0.., k columns k0..
 __device__ __forceinline__ void load_a_t(uint32_t* a, const __nv_bfloat16* tile, int pitch, int m0, int k0, int lane) {
@@ -142,7 +162,7 @@ template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // global rows [T][dk] at g (pitch ld, elements)  ->  tile rows.  piece = bytes per copy (8 / 4 / 2).
-__device__ __forceinline__ void tile_load(__nv_bfloat16* tile, const __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane, int nthr = 32) {
+__device__ __forceinline__ void tile_load(__nv_bfloat16* tile, const __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane, int nthr = 32, int pitch = kPitch) {
     const int epp = piece >> 1;        // elements per piece
     const int ppr = dk / epp;          // pieces per row
     const float inv = 1.0f / static_cast<float>(ppr);
@@ -150,14 +170,14 @@ __device__ __forceinline__ void tile_load(__nv_bfloat16* tile, const __nv_bfloat
     for (int i = lane; i < n; i += nthr) {
         const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
         const int c = (i - r * ppr) * epp;
-        __nv_bfloat16* dst = tile + r * kPitch + c;
+        __nv_bfloat16* dst = tile + r * pitch + c;
         const __nv_bfloat16* src = g + static_cast<size_t>(r) * ld + c;
         if (piece == 8) cp_async8(dst, src);
         else if (piece == 4) cp_async4(dst, src);
         else *dst = *src;
     }
 }
-__device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane, int nthr = 32) {
+__device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane, int nthr = 32, int pitch = kPitch) {
     const int epp = piece >> 1;
     const int ppr = dk / epp;
     const float inv = 1.0f / static_cast<float>(ppr);
@@ -165,7 +185,7 @@ __device__ __forceinline__ void tile_store(const __nv_bfloat16* tile, __nv_bfloa
     for (int i = lane; i < n; i += nthr) {
         const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
         const int c = (i - r * ppr) * epp;
-        const __nv_bfloat16* src = tile + r * kPitch + c;
+        const __nv_bfloat16* src = tile + r * pitch + c;
         __nv_bfloat16* dst = g + static_cast<size_t>(r) * ld + c;
         if (piece == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
         else if (piece == 4) *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
@@ -184,7 +204,7 @@ struct PieceMap {
     int row[kMaxP];
     int col[kMaxP];
 };
-__device__ __forceinline__ bool make_piece_map(PieceMap& m, int T, int dk, int piece, int ld, int lane) {
+__device__ __forceinline__ bool make_piece_map(PieceMap& m, int T, int dk, int piece, int ld, int lane, int pitch = kPitch) {
     const int epp = piece >> 1, ppr = dk / epp, n = T * ppr;
     m.n = 0;
     m.total = n;
@@ -195,7 +215,7 @@ __device__ __forceinline__ bool make_piece_map(PieceMap& m, int T, int dk, int p
         const int i = lane + 32 * k;
         const int r = i / ppr, c = (i - r * ppr) * epp;
         m.src[k] = r * ld + c;
-        m.dst[k] = r * kPitch + c;
+        m.dst[k] = r * pitch + c;
         m.row[k] = r;
         m.col[k] = c;
         if (i < n) m.n = k + 1;
@@ -250,7 +270,8 @@ __device__ __forceinline__ void tile_store_dropout_map(const __nv_bfloat16* tile
 
 // context tile -> global with the dropout mask applied on the fly (one counter hash per 4 aligned columns)
 __device__ __forceinline__ void tile_store_dropout(const __nv_bfloat16* tile, __nv_bfloat16* g, int ld, int T, int dk, int piece, int lane,
-                                                   long long row0, int col0, uint64_t seed, uint32_t thresh, float scale, int nthr = 32) {
+                                                   long long row0, int col0, uint64_t seed, uint32_t thresh, float scale, int nthr = 32,
+                                                   int pitch = kPitch) {
     const int epp = piece >> 1;
     const int ppr = dk / epp;
     const float inv = 1.0f / static_cast<float>(ppr);
@@ -258,7 +279,7 @@ __device__ __forceinline__ void tile_store_dropout(const __nv_bfloat16* tile, __
     for (int i = lane; i < n; i += nthr) {
         const int r = static_cast<int>((static_cast<float>(i) + 0.5f) * inv);
         const int c = (i - r * ppr) * epp;
-        const __nv_bfloat16* src = tile + r * kPitch + c;
+        const __nv_bfloat16* src = tile + r * pitch + c;
         __nv_bfloat16* dst = g + static_cast<size_t>(r) * ld + c;
         const int gc = col0 + c;
         const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row0 + r) * ld + gc) >> 2);
@@ -298,19 +319,22 @@ __host__ __device__ inline int piece_bytes(int dk, int ld_a, int ld_b, int d) {
 // 3 warps per SM resident (0.28 ms for 4 % of the tokens).  Tiles are loaded/stored by all threads, phases are separated
 // by __syncthreads instead of __syncwarp.
 template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH, bool COOP>
-__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 6 : 5) : (COOP ? 3 : 1))) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
                                                                   int T_, int heads_, int dk_, __nv_bfloat16* __restrict__ ctx,
                                                                   int ld_ctx, float p, uint64_t seed) {
     constexpr int NTJ = TP / 8, MT = TP / 16;
+    constexpr int PT = (CDK == 20) ? kPitch24 : kPitch;  // tile row pitch
+    constexpr bool K8T = (CDK == 20);                    // last k-step over d_k is an m16n8k8 (columns 16..23)
+    constexpr int KS16 = K8T ? KSD - 1 : KSD;
     const int T = CT > 0 ? CT : T_, heads = CH > 0 ? CH : heads_, dk = CDK > 0 ? CDK : dk_;
-    // A tile holds exactly T rows (pitch kPitch).  Fragment loads of rows >= T run into the neighbouring tile or the
+    // A tile holds exactly T rows (pitch PT).  Fragment loads of rows >= T run into the neighbouring tile or the
     // zeroed slack behind the last one: finite bytes that only ever meet zero probabilities / unused output rows.
-    const int TILE = T * kPitch;
+    const int TILE = T * PT;
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int d = heads * dk;
     static_assert(!COOP || (WPS == TP / 16 && !FAST), "cooperative CTAs: one warp per 16-row block, generic copy loops");
-    for (int i = tid; i < ((COOP ? 1 : WPS) * STG * 3 * TILE + (TP - T) * kPitch) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    for (int i = tid; i < ((COOP ? 1 : WPS) * STG * 3 * TILE + (TP - T) * PT) / 2; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
     __syncthreads();
     __nv_bfloat16* wbase = sm + (COOP ? 0 : warp) * STG * 3 * TILE;
     const int ctid = COOP ? tid : lane, cnt = COOP ? WPS * 32 : 32;  // who copies a task's tiles
@@ -325,8 +349,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhs
     const int gw = COOP ? blockIdx.x : blockIdx.x * WPS + warp;
     PieceMap lmap, smap;
     if (FAST) {
-        make_piece_map(lmap, T, dk, piece, ld, lane);
-        make_piece_map(smap, T, dk, piece, ld_ctx, lane);
+        make_piece_map(lmap, T, dk, piece, ld, lane, PT);
+        make_piece_map(smap, T, dk, piece, ld_ctx, lane, PT);
     }
     constexpr bool fast = FAST;
     const uint32_t wbase_s = smem_u32(wbase);
@@ -343,9 +367,9 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhs
                 tile_load_map(t0s + 4 * TILE, src + 2 * d, lmap, piece);
             } else {
                 __nv_bfloat16* t0 = wbase + stage * 3 * TILE;
-                tile_load(t0, src, ld, T, dk, piece, ctid, cnt);
-                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt);
-                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt);
+                tile_load(t0, src, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt, PT);
             }
         }
         cp_commit();
@@ -372,15 +396,26 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhs
 #pragma unroll
             for (int nt = 0; nt < NTJ; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < KSD; ++ks) {
+            for (int ks = 0; ks < KS16; ++ks) {
                 uint32_t a[4];
-                load_a(a, q, kPitch, mt * 16, ks * 16, lane);
+                load_a(a, q, PT, mt * 16, ks * 16, lane);
 #pragma unroll
                 for (int nt = 0; nt < NTJ; ++nt) {
                     if (nt >= ntj) break;
                     uint32_t b[2];
-                    load_b(b, k, kPitch, nt * 8, ks * 16, lane);
+                    load_b(b, k, PT, nt * 8, ks * 16, lane);
                     mma_bf16(s[nt], a, b);
+                }
+            }
+            if constexpr (K8T) {
+                uint32_t a[2];
+                load_a8(a, q, PT, mt * 16, KS16 * 16, lane);
+#pragma unroll
+                for (int nt = 0; nt < NTJ; ++nt) {
+                    if (nt >= ntj) break;
+                    uint32_t b[1];
+                    load_b8(b, k, PT, nt * 8, KS16 * 16, lane);
+                    mma_bf16_k8(s[nt], a, b);
                 }
             }
             softmax_rows<NTJ>(s, T, t4, ntj, sc);
@@ -398,7 +433,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhs
 #pragma unroll
                 for (int nd = 0; nd < NTD; ++nd) {
                     uint32_t b[2];
-                    load_b_t(b, v, kPitch, kj * 16, nd * 8, lane);
+                    load_b_t(b, v, PT, kj * 16, nd * 8, lane);
                     mma_bf16(o[nd], a, b);
                 }
             }
@@ -414,7 +449,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhs
                     const int r = mt * 16 + g + hf * 8;
                     if (r >= T) continue;
                     const float v0 = o[nd][2 * hf], v1 = pair ? o[nd][2 * hf + 1] : 0.f;
-                    *reinterpret_cast<uint32_t*>(q + r * kPitch + col) = pack_bf16x2(v0, v1);
+                    *reinterpret_cast<uint32_t*>(q + r * PT + col) = pack_bf16x2(v0, v1);
                 }
             }
         }
@@ -424,9 +459,9 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhs
             if (p > 0.f) tile_store_dropout_map(q, out + h * dk, smap, piece, ld_ctx, seq * T, h * dk, seed, thresh, dscale);
             else tile_store_map(q, out + h * dk, smap, piece);
         } else if (p > 0.f) {
-            tile_store_dropout(q, out + h * dk, ld_ctx, T, dk, piece, ctid, seq * T, h * dk, seed, thresh, dscale, cnt);
+            tile_store_dropout(q, out + h * dk, ld_ctx, T, dk, piece, ctid, seq * T, h * dk, seed, thresh, dscale, cnt, PT);
         } else {
-            tile_store(q, out + h * dk, ld_ctx, T, dk, piece, ctid, cnt);
+            tile_store(q, out + h * dk, ld_ctx, T, dk, piece, ctid, cnt, PT);
         }
         if (h == 0) {  // ones column + zero tail of the padded context rows
             for (int i = ctid; i < T * (ld_ctx - d); i += cnt) {
@@ -444,13 +479,16 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 5 : (COOP ? 3 : 1))) mhs
 // backward
 // ------------------------------------------------------------------------------------------------
 template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH, bool COOP>
-__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (COOP ? 3 : 1))) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
                                                                   const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
                                                                   long long n_seq, int T_, int heads_, int dk_,
                                                                   __nv_bfloat16* __restrict__ dqkv, int ld_d) {
     constexpr int NTJ = TP / 8, MT = TP / 16, SP = TP + 8;
+    constexpr int PT = (CDK == 20) ? kPitch24 : kPitch;
+    constexpr bool K8T = (CDK == 20);
+    constexpr int KS16 = K8T ? KSD - 1 : KSD;
     const int T = CT > 0 ? CT : T_, heads = CH > 0 ? CH : heads_, dk = CDK > 0 ? CDK : dk_;
-    const int TILE = T * kPitch;  // packed rows, see the forward kernel
+    const int TILE = T * PT;  // packed rows, see the forward kernel
     extern __shared__ __align__(16) __nv_bfloat16 sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     const int d = heads * dk;
@@ -473,9 +511,9 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhs
     const int gw = COOP ? blockIdx.x : blockIdx.x * WPS + warp;
     PieceMap lmap, gmap, smap;
     if (FAST) {
-        make_piece_map(lmap, T, dk, piece, ld, lane);
-        make_piece_map(gmap, T, dk, piece, ld_dctx, lane);
-        make_piece_map(smap, T, dk, piece, ld_d, lane);
+        make_piece_map(lmap, T, dk, piece, ld, lane, PT);
+        make_piece_map(gmap, T, dk, piece, ld_dctx, lane, PT);
+        make_piece_map(smap, T, dk, piece, ld_d, lane, PT);
     }
     constexpr bool fast = FAST;
     const uint32_t wbase_s = smem_u32(wbase);
@@ -494,10 +532,10 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhs
                 tile_load_map(t0s + 6 * TILE, gsrc, gmap, piece);
             } else {
                 __nv_bfloat16* t0 = wbase + stage * 4 * TILE;
-                tile_load(t0, src, ld, T, dk, piece, ctid, cnt);
-                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt);
-                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt);
-                tile_load(t0 + 3 * TILE, gsrc, ld_dctx, T, dk, piece, ctid, cnt);
+                tile_load(t0, src, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + 3 * TILE, gsrc, ld_dctx, T, dk, piece, ctid, cnt, PT);
             }
         }
         cp_commit();
@@ -533,18 +571,32 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhs
                 dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
             }
 #pragma unroll
-            for (int ks = 0; ks < KSD; ++ks) {
+            for (int ks = 0; ks < KS16; ++ks) {
                 uint32_t aq[4], ag[4];
-                load_a(aq, q, kPitch, mt * 16, ks * 16, lane);
-                load_a(ag, gg, kPitch, mt * 16, ks * 16, lane);
+                load_a(aq, q, PT, mt * 16, ks * 16, lane);
+                load_a(ag, gg, PT, mt * 16, ks * 16, lane);
 #pragma unroll
                 for (int nt = 0; nt < NTJ; ++nt) {
                     if (nt >= ntj) break;
                     uint32_t bk[2], bv[2];
-                    load_b(bk, k, kPitch, nt * 8, ks * 16, lane);
-                    load_b(bv, v, kPitch, nt * 8, ks * 16, lane);
+                    load_b(bk, k, PT, nt * 8, ks * 16, lane);
+                    load_b(bv, v, PT, nt * 8, ks * 16, lane);
                     mma_bf16(s[nt], aq, bk);    // S  = Q K^T
                     mma_bf16(dp[nt], ag, bv);   // dA = dCtx V^T
+                }
+            }
+            if constexpr (K8T) {
+                uint32_t aq[2], ag[2];
+                load_a8(aq, q, PT, mt * 16, KS16 * 16, lane);
+                load_a8(ag, gg, PT, mt * 16, KS16 * 16, lane);
+#pragma unroll
+                for (int nt = 0; nt < NTJ; ++nt) {
+                    if (nt >= ntj) break;
+                    uint32_t bk[1], bv[1];
+                    load_b8(bk, k, PT, nt * 8, KS16 * 16, lane);
+                    load_b8(bv, v, PT, nt * 8, KS16 * 16, lane);
+                    mma_bf16_k8(s[nt], aq, bk);
+                    mma_bf16_k8(dp[nt], ag, bv);
                 }
             }
             softmax_rows<NTJ>(s, T, t4, ntj, sc);
@@ -585,7 +637,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhs
 #pragma unroll
                 for (int nd = 0; nd < NTD; ++nd) {
                     uint32_t b[2];
-                    load_b_t(b, k, kPitch, kj * 16, nd * 8, lane);
+                    load_b_t(b, k, PT, kj * 16, nd * 8, lane);
                     mma_bf16(dq[nd], a, b);
                 }
             }
@@ -629,8 +681,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhs
 #pragma unroll
                 for (int nd = 0; nd < NTD; ++nd) {
                     uint32_t bq[2], bg[2];
-                    load_b_t(bq, q, kPitch, ki * 16, nd * 8, lane);
-                    load_b_t(bg, gg, kPitch, ki * 16, nd * 8, lane);
+                    load_b_t(bq, q, PT, ki * 16, nd * 8, lane);
+                    load_b_t(bg, gg, PT, ki * 16, nd * 8, lane);
                     mma_bf16(dkk[nd], ad, bq);
                     mma_bf16(dvv[nd], ap, bg);
                 }
@@ -644,8 +696,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhs
                 for (int hf = 0; hf < 2; ++hf) {
                     const int r = mt * 16 + g + hf * 8;
                     if (r >= T) continue;
-                    *reinterpret_cast<uint32_t*>(k + r * kPitch + col) = pack_bf16x2(dkk[nd][2 * hf], pair ? dkk[nd][2 * hf + 1] : 0.f);
-                    *reinterpret_cast<uint32_t*>(v + r * kPitch + col) = pack_bf16x2(dvv[nd][2 * hf], pair ? dvv[nd][2 * hf + 1] : 0.f);
+                    *reinterpret_cast<uint32_t*>(k + r * PT + col) = pack_bf16x2(dkk[nd][2 * hf], pair ? dkk[nd][2 * hf + 1] : 0.f);
+                    *reinterpret_cast<uint32_t*>(v + r * PT + col) = pack_bf16x2(dvv[nd][2 * hf], pair ? dvv[nd][2 * hf + 1] : 0.f);
                 }
             }
         }
@@ -654,8 +706,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? 3 : (COOP ? 3 : 1))) mhs
             tile_store_map(k, gout + d + h * dk, smap, piece);
             tile_store_map(v, gout + 2 * d + h * dk, smap, piece);
         } else {
-            tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, ctid, cnt);
-            tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, ctid, cnt);
+            tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
+            tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
         }
         phase_sync();
         stage = (stage + 1) % STG;
@@ -668,9 +720,10 @@ int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     const long long tasks = n_seq * heads;
     NR_REQUIRE(tasks < (1ll << 31), "mhsa: too many (sequence, head) tasks");
-    const size_t tile = sizeof(__nv_bfloat16) * T * kPitch;
+    constexpr int PT = (CDK == 20) ? kPitch24 : kPitch;
+    const size_t tile = sizeof(__nv_bfloat16) * T * PT;
     const int sets = COOP ? 1 : WPS;  // tile sets per CTA: one per warp, or one shared by the cooperative CTA
-    const size_t smem_f = sets * STG * 3 * tile + sizeof(__nv_bfloat16) * (TP - T) * kPitch;
+    const size_t smem_f = sets * STG * 3 * tile + sizeof(__nv_bfloat16) * (TP - T) * PT;
     const size_t smem_b = sets * (STG * 4 * tile + sizeof(__nv_bfloat16) * 2 * TP * (TP + 8));
     const size_t smem = bwd ? smem_b : smem_f;
     NR_REQUIRE(smem <= 227 * 1024, "mhsa: tile set of %zu bytes exceeds shared memory", smem);
