@@ -557,6 +557,29 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
         const __nv_bfloat16* gg = v + TILE;
         __nv_bfloat16* gout = dqkv + seq * T * static_cast<long long>(ld_d);
         // ---- phase A (row blocks i): P, dS -> smem (bf16); dQ straight to global ----
+        // The K / V fragments do not depend on the row block: with two row blocks per task (T <= 32) they are loaded
+        // once and kept in registers (the kernel is bound by the shared-memory instruction queue, ncu: stall_mio).
+        constexpr bool HOIST = (MT == 2) && !COOP;
+        uint32_t hk[HOIST ? KS16 : 1][HOIST ? NTJ : 1][2], hv[HOIST ? KS16 : 1][HOIST ? NTJ : 1][2];
+        uint32_t hk8[HOIST && K8T ? NTJ : 1][1], hv8[HOIST && K8T ? NTJ : 1][1];
+        if constexpr (HOIST) {
+#pragma unroll
+            for (int ks = 0; ks < KS16; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NTJ; ++nt) {
+                    if (nt >= ntj) break;
+                    load_b(hk[ks][nt], k, PT, nt * 8, ks * 16, lane);
+                    load_b(hv[ks][nt], v, PT, nt * 8, ks * 16, lane);
+                }
+            if constexpr (K8T) {
+#pragma unroll
+                for (int nt = 0; nt < NTJ; ++nt) {
+                    if (nt >= ntj) break;
+                    load_b8(hk8[nt], k, PT, nt * 8, KS16 * 16, lane);
+                    load_b8(hv8[nt], v, PT, nt * 8, KS16 * 16, lane);
+                }
+            }
+        }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             if (mt * 16 >= T) continue;
@@ -578,11 +601,16 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
 #pragma unroll
                 for (int nt = 0; nt < NTJ; ++nt) {
                     if (nt >= ntj) break;
-                    uint32_t bk[2], bv[2];
-                    load_b(bk, k, PT, nt * 8, ks * 16, lane);
-                    load_b(bv, v, PT, nt * 8, ks * 16, lane);
-                    mma_bf16(s[nt], aq, bk);    // S  = Q K^T
-                    mma_bf16(dp[nt], ag, bv);   // dA = dCtx V^T
+                    if constexpr (HOIST) {
+                        mma_bf16(s[nt], aq, hk[ks][nt]);    // S  = Q K^T
+                        mma_bf16(dp[nt], ag, hv[ks][nt]);   // dA = dCtx V^T
+                    } else {
+                        uint32_t bk[2], bv[2];
+                        load_b(bk, k, PT, nt * 8, ks * 16, lane);
+                        load_b(bv, v, PT, nt * 8, ks * 16, lane);
+                        mma_bf16(s[nt], aq, bk);
+                        mma_bf16(dp[nt], ag, bv);
+                    }
                 }
             }
             if constexpr (K8T) {
@@ -592,11 +620,16 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
 #pragma unroll
                 for (int nt = 0; nt < NTJ; ++nt) {
                     if (nt >= ntj) break;
-                    uint32_t bk[1], bv[1];
-                    load_b8(bk, k, PT, nt * 8, KS16 * 16, lane);
-                    load_b8(bv, v, PT, nt * 8, KS16 * 16, lane);
-                    mma_bf16_k8(s[nt], aq, bk);
-                    mma_bf16_k8(dp[nt], ag, bv);
+                    if constexpr (HOIST) {
+                        mma_bf16_k8(s[nt], aq, hk8[nt]);
+                        mma_bf16_k8(dp[nt], ag, hv8[nt]);
+                    } else {
+                        uint32_t bk[1], bv[1];
+                        load_b8(bk, k, PT, nt * 8, KS16 * 16, lane);
+                        load_b8(bv, v, PT, nt * 8, KS16 * 16, lane);
+                        mma_bf16_k8(s[nt], aq, bk);
+                        mma_bf16_k8(dp[nt], ag, bv);
+                    }
                 }
             }
             softmax_rows<NTJ>(s, T, t4, ntj, sc);
