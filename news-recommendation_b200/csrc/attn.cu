@@ -319,7 +319,7 @@ __host__ __device__ inline int piece_bytes(int dk, int ld_a, int ld_b, int d) {
 // 3 warps per SM resident (0.28 ms for 4 % of the tokens).  Tiles are loaded/stored by all threads, phases are separated
 // by __syncthreads instead of __syncwarp.
 template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH, bool COOP>
-__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 7 : 5) : (COOP ? 3 : 1))) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (COOP ? 3 : 1))) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
                                                                   int T_, int heads_, int dk_, __nv_bfloat16* __restrict__ ctx,
                                                                   int ld_ctx, float p, uint64_t seed) {
     constexpr int NTJ = TP / 8, MT = TP / 16;
@@ -760,7 +760,7 @@ int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int
     const size_t smem_b = sets * (STG * 4 * tile + sizeof(__nv_bfloat16) * 2 * TP * (TP + 8));
     const size_t smem = bwd ? smem_b : smem_f;
     NR_REQUIRE(smem <= 227 * 1024, "mhsa: tile set of %zu bytes exceeds shared memory", smem);
-    const int per_sm = std::max<int>(1, std::min<size_t>(COOP ? 3 : (bwd ? 6 : 7), (224 * 1024) / (smem + 1024)));
+    const int per_sm = std::max<int>(1, std::min<size_t>(COOP ? 3 : (bwd ? 6 : 8), (224 * 1024) / (smem + 1024)));
     const int grid = static_cast<int>(std::min<long long>(ceil_div(static_cast<int>(std::min<long long>(tasks, 1 << 30)), COOP ? 1 : WPS),
                                                           static_cast<long long>(num_sms()) * per_sm));
     if (!bwd) {
