@@ -46,14 +46,15 @@ class FlatGradients:
                 uniq.append(p)
         self.params = uniq
         self.world = world
-        total = sum(p.numel() for p in self.params)
+        pad4 = lambda n: (n + 3) // 4 * 4  # every view starts on a 16-byte boundary (the kernels reduce with 16-byte vectors)
+        total = sum(pad4(p.numel()) for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            off += pad4(n)
 
     def zero(self):
         self.flat.zero_()

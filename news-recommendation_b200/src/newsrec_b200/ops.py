@@ -65,7 +65,7 @@ def grad_sink(p):
     """The parameter's own gradient storage if the kernels can accumulate into it directly, else None."""
     g = getattr(p, "grad", None)
     if g is None or not p.requires_grad or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device \
-            or g.shape != p.shape:
+            or g.shape != p.shape or g.data_ptr() % 16 != 0:  # 16-byte vector reductions (red.global.add.v4.f32)
         return None
     return g
 

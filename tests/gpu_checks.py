@@ -311,20 +311,25 @@ def check_nrms_direct_grad_accumulation(B=8, Cn=5, H=50, T=20, V=500, seed=6):
         torch.nn.functional.cross_entropy(model_a(slots(cand_t), slots(clicked_t)), label).backward()
         torch.nn.functional.cross_entropy(model_b(slots(cand_t), slots(clicked_t)), label).backward()
     torch.cuda.synchronize()
-    worst = 0.0
-    for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
-        scale = float(pa.grad.abs().max()) + 1e-12
-        worst = max(worst, float((pa.grad - pb.grad).abs().max()) / scale)
+    def worst_rel(ma, mb):
+        # W_K.bias has an analytically zero gradient (softmax shift invariance): what both paths hold there is fp32
+        # accumulation noise in atomic order.  Every difference is therefore measured against the tensor's own scale
+        # floored at 1e-3 of the largest gradient in the model.
+        floor = 1e-3 * max(float(p.grad.abs().max()) for p in ma.parameters())
+        w = 0.0
+        for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+            scale = max(float(pa.grad.abs().max()), floor)
+            w = max(w, float((pa.grad - pb.grad).abs().max()) / scale)
+        return w
+
+    worst = worst_rel(model_a, model_b)
     # a third backward with the persistent workspaces must start from cleared accumulators
     flat.zero()
     model_a.zero_grad(set_to_none=True)
     torch.nn.functional.cross_entropy(model_a(slots(cand_t), slots(clicked_t)), label).backward()
     torch.nn.functional.cross_entropy(model_b(slots(cand_t), slots(clicked_t)), label).backward()
     torch.cuda.synchronize()
-    again = 0.0
-    for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
-        scale = float(pa.grad.abs().max()) + 1e-12
-        again = max(again, float((pa.grad - pb.grad).abs().max()) / scale)
+    again = worst_rel(model_a, model_b)
     return {"direct_vs_returned_rel_maxabs": worst, "after_zero_rel_maxabs": again,
             "grads_are_flat_views": all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in model_b.parameters())}
 
