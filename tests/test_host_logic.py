@@ -150,6 +150,28 @@ def _ddp_worker(rank, world, port, q):
     torch.distributed.destroy_process_group()
 
 
+def test_flat_gradient_views_start_on_16_byte_boundaries():
+    """The kernels accumulate into .grad with 16-byte vector reductions: every view of the flat buffer must be aligned,
+    whatever the parameter sizes are (odd sizes get padding behind them)."""
+    import torch
+    from newsrec_b200 import ddp
+    from newsrec_b200.ops import grad_sink
+    ps = [torch.nn.Parameter(torch.randn(*shape)) for shape in ((5, 3), (7,), (2, 2), (1,), (9, 300))]
+    fg = ddp.FlatGradients(ps, 1)
+    for p in ps:
+        assert p.grad.data_ptr() % 16 == 0 and p.grad.is_contiguous() and p.grad.shape == p.shape
+        assert grad_sink(p) is p.grad
+    # views do not overlap: writing one leaves the others zero
+    fg.zero()
+    ps[1].grad.fill_(1.0)
+    assert float(fg.flat.sum()) == 7.0 and all(float(p.grad.abs().sum()) == 0.0 for i, p in enumerate(ps) if i != 1)
+    # a parameter without usable gradient storage is not a sink
+    q = torch.nn.Parameter(torch.randn(4))
+    assert grad_sink(q) is None
+    q.grad = torch.zeros(8)[::2]
+    assert grad_sink(q) is None
+
+
 def test_flat_gradient_all_reduce_equals_single_process_mean_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
