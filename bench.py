@@ -139,8 +139,8 @@ def kernel_work(name):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in
 # profiles/ncu_r01_kernel_summary.csv (batch 512 shapes only; other shapes report null)
 NCU_DRAM_BYTES = {
-    "mhsa_core_bwd[28160,20,300]": 1.468930e9 + 1.042096e9,   # fixed-shape kernel, profiles/ncu_r01_attention_final.csv
-    "mhsa_core_fwd[28160,20,300]": 1.185283e9 + 0.360153e9,
+    "mhsa_core_bwd[28160,20,300]": 1.483482e9 + 1.050252e9,   # 48-byte-tile kernels, profiles/ncu_r01_attention_final.csv
+    "mhsa_core_fwd[28160,20,300]": 1.055464e9 + 0.329299e9,
     "gemm_store[563200,900,300]": 0.443694e9 + 0.979511e9,
     "gemm_additive_pool[563200,200,300]": 0.374886e9 + 0.030811e9,
     "gemm_additive_dpre[563200,200,300]": 0.344909e9 + 0.191328e9,
