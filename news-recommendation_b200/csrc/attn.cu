@@ -96,9 +96,11 @@ __device__ __forceinline__ float drop_mult(uint64_t seed, uint32_t thresh, float
 // Row-block softmax on the S fragments of one 16-row m-tile.  s[nt][4] holds (row g: c0,c1 ; row g+8: c2,c3)
 // for key columns nt*8 + 2t, +1.  Input scores are pre-scaled into the log2 domain.  Returns P in place.
 template <int NTJ>
-__device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4, int ntj, float sc) {
+__device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4, int ntj, float sc, bool dead1 = false) {
     // raw scores in, probabilities out; `sc` = log2(e)/sqrt(d_k) is folded into the exp2 argument.
     // Only the last live n-tile can contain key columns >= T; tiles >= ntj are dead (skipped everywhere).
+    // dead1: rows g+8 of this 16-row block are all >= T (compile-time for the fixed shapes): their probabilities are
+    // forced to zero without computing anything (for T = 20 that is half of the second row block).
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NTJ; ++nt) {
@@ -108,14 +110,14 @@ __device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4, int n
             for (int e = 0; e < 2; ++e) {
                 const bool ok = nt * 8 + 2 * t4 + e < T;
                 s[nt][e] = ok ? s[nt][e] : -INFINITY;
-                s[nt][2 + e] = ok ? s[nt][2 + e] : -INFINITY;
+                if (!dead1) s[nt][2 + e] = ok ? s[nt][2 + e] : -INFINITY;
             }
         }
         m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        if (!dead1) m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
     }
     m0 = quad_max(m0) * sc;
-    m1 = quad_max(m1) * sc;
+    if (!dead1) m1 = quad_max(m1) * sc;
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < NTJ; ++nt) {
@@ -123,22 +125,31 @@ __device__ __forceinline__ void softmax_rows(float (*s)[4], int T, int t4, int n
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             s[nt][e] = exp2f(fmaf(s[nt][e], sc, -m0));
-            s[nt][2 + e] = exp2f(fmaf(s[nt][2 + e], sc, -m1));
             l0 += s[nt][e];
-            l1 += s[nt][2 + e];
+            if (!dead1) {
+                s[nt][2 + e] = exp2f(fmaf(s[nt][2 + e], sc, -m1));
+                l1 += s[nt][2 + e];
+            } else {
+                s[nt][2 + e] = 0.f;
+            }
         }
     }
     l0 = quad_sum(l0);
-    l1 = quad_sum(l1);
     const float i0 = 1.f / (l0 + 1e-8f * exp2f(-m0));  // == exp(S)/(sum exp(S) + 1e-8) of the reference
-    const float i1 = 1.f / (l1 + 1e-8f * exp2f(-m1));
+    float i1 = 0.f;
+    if (!dead1) {
+        l1 = quad_sum(l1);
+        i1 = 1.f / (l1 + 1e-8f * exp2f(-m1));
+    }
 #pragma unroll
     for (int nt = 0; nt < NTJ; ++nt) {
         if (nt >= ntj) break;
         s[nt][0] *= i0;
         s[nt][1] *= i0;
-        s[nt][2] *= i1;
-        s[nt][3] *= i1;
+        if (!dead1) {
+            s[nt][2] *= i1;
+            s[nt][3] *= i1;
+        }
     }
 }
 
@@ -418,7 +429,8 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (C
                     mma_bf16_k8(s[nt], a, b);
                 }
             }
-            softmax_rows<NTJ>(s, T, t4, ntj, sc);
+            const bool dead1 = CT > 0 && mt * 16 + 8 >= CT;  // folds after unrolling
+            softmax_rows<NTJ>(s, T, t4, ntj, sc, dead1);
             float o[NTD][4];
 #pragma unroll
             for (int nd = 0; nd < NTD; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
@@ -632,18 +644,24 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
                     }
                 }
             }
-            softmax_rows<NTJ>(s, T, t4, ntj, sc);
+            const bool dead1 = CT > 0 && mt * 16 + 8 >= CT;  // rows g+8 of this block are all >= T (folds after unrolling)
+            softmax_rows<NTJ>(s, T, t4, ntj, sc, dead1);
             float del0 = 0.f, del1 = 0.f;
 #pragma unroll
             for (int nt = 0; nt < NTJ; ++nt) {
+                if (nt >= ntj) break;
                 del0 += s[nt][0] * dp[nt][0] + s[nt][1] * dp[nt][1];
-                del1 += s[nt][2] * dp[nt][2] + s[nt][3] * dp[nt][3];
+                if (!dead1) del1 += s[nt][2] * dp[nt][2] + s[nt][3] * dp[nt][3];
             }
             del0 = quad_sum(del0);
-            del1 = quad_sum(del1);
-            const bool r0ok = mt * 16 + g < T, r1ok = mt * 16 + g + 8 < T;
+            if (!dead1) del1 = quad_sum(del1);
+            const bool r0ok = mt * 16 + g < T, r1ok = !dead1 && mt * 16 + g + 8 < T;
 #pragma unroll
             for (int nt = 0; nt < NTJ; ++nt) {
+                if (nt >= ntj) {  // dead key columns: never stored (the scratch stays zero there), zero dS fragments for dQ
+                    dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+                    continue;
+                }
                 // rows >= T carry garbage (zero Q rows give a uniform softmax): force them to zero, they are
                 // k-indices of the phase-B products
                 const float p0 = r0ok ? s[nt][0] : 0.f, p1 = r0ok ? s[nt][1] : 0.f;
@@ -654,9 +672,11 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
                 dp[nt][3] = p3 * (dp[nt][3] - del1) * rs;
                 const int col = nt * 8 + 2 * t4;
                 *reinterpret_cast<uint32_t*>(ps + (mt * 16 + g) * SP + col) = pack_bf16x2(p0, p1);
-                *reinterpret_cast<uint32_t*>(ps + (mt * 16 + g + 8) * SP + col) = pack_bf16x2(p2, p3);
                 *reinterpret_cast<uint32_t*>(ds + (mt * 16 + g) * SP + col) = pack_bf16x2(dp[nt][0], dp[nt][1]);
-                *reinterpret_cast<uint32_t*>(ds + (mt * 16 + g + 8) * SP + col) = pack_bf16x2(dp[nt][2], dp[nt][3]);
+                if (!dead1) {  // dead rows are never written by any task of this kernel: they keep their initial zeros
+                    *reinterpret_cast<uint32_t*>(ps + (mt * 16 + g + 8) * SP + col) = pack_bf16x2(p2, p3);
+                    *reinterpret_cast<uint32_t*>(ds + (mt * 16 + g + 8) * SP + col) = pack_bf16x2(dp[nt][2], dp[nt][3]);
+                }
             }
             // dQ = dS K   (A = dS fragments straight from registers, B[k=j][n=d] = K[j][d])
 #pragma unroll
