@@ -458,6 +458,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (C
                 const bool pair = col + 1 < dk;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
+                    if (CT > 0 && mt * 16 + hf * 8 >= CT) continue;  // whole half-block past T: folds after unrolling
                     const int r = mt * 16 + g + hf * 8;
                     if (r >= T) continue;
                     const float v0 = o[nd][2 * hf], v1 = pair ? o[nd][2 * hf + 1] : 0.f;
@@ -700,6 +701,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
                 if (col >= dk) continue;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
+                    if (CT > 0 && mt * 16 + hf * 8 >= CT) continue;  // whole half-block past T: folds after unrolling
                     const int r = mt * 16 + g + hf * 8;
                     if (r >= T) continue;
                     __nv_bfloat16* o = gout + static_cast<size_t>(r) * ld_d + h * dk + col;
@@ -747,6 +749,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
                 const bool pair = col + 1 < dk;  // odd d_k: keep the zero padding column intact
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
+                    if (CT > 0 && mt * 16 + hf * 8 >= CT) continue;  // whole half-block past T: folds after unrolling
                     const int r = mt * 16 + g + hf * 8;
                     if (r >= T) continue;
                     *reinterpret_cast<uint32_t*>(k + r * PT + col) = pack_bf16x2(dkk[nd][2 * hf], pair ? dkk[nd][2 * hf + 1] : 0.f);
