@@ -145,6 +145,9 @@ def main(argv=None):
     ap.add_argument("--no-dropin", action="store_true", help="keep the reference's own model/config packages (CPU smoke runs)")
     ap.add_argument("--backend", default=None, help="torch.distributed backend (default: nccl with CUDA, else gloo)")
     ap.add_argument("--seed", type=int, default=0, help="seed of the sharded sampler's permutations")
+    ap.add_argument("--set", action="append", default=[], metavar="KNOB=VALUE",
+                    help="override a knob of the selected <MODEL_NAME>Config before the trainer is imported (repeatable), "
+                         "e.g. --set batch_size=512 --set num_workers=8")
     args = ap.parse_args(argv)
 
     rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
@@ -160,9 +163,14 @@ def main(argv=None):
         os.environ.setdefault("TQDM_DISABLE", "1")
 
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # .../news-recommendation_b200/src
+    from newsrec_b200 import ddp  # noqa: F401  (resolved now: --no-dropin takes the package's directory off the path below)
     sys.path.insert(0, os.path.abspath(args.reference_src))
     if not args.no_dropin:
         sys.path.insert(0, here)  # model.*, config shadow the reference's
+    else:
+        # the reference's `model` is a namespace package (no __init__.py): a regular package of the same name anywhere
+        # on the path would win over it, so the drop-in's directory must not be on the path at all
+        sys.path[:] = [q for q in sys.path if os.path.abspath(q or os.getcwd()) != here]
     apply_compat_shims()
 
     import torch
@@ -174,6 +182,17 @@ def main(argv=None):
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
 
     import importlib
+    if args.set:
+        import ast
+        cfgmod = importlib.import_module("config")
+        cfg = getattr(cfgmod, f"{cfgmod.model_name}Config")
+        for item in args.set:
+            key, _, val = item.partition("=")
+            try:
+                val = ast.literal_eval(val)
+            except (ValueError, SyntaxError):
+                pass  # keep the string
+            setattr(cfg, key, val)
     train = importlib.import_module("train")
     patch_trainer(train, rank, world, args.seed)
     try:

@@ -107,3 +107,30 @@ def test_launcher_shards_and_all_reduces_like_one_process(tmp_path):
         opt.step()
     assert torch.allclose(model.weight.detach().flatten(), torch.tensor(out[0]["w"]), atol=1e-5)
     assert torch.allclose(model.bias.detach(), torch.tensor(out[0]["b"]), atol=1e-5)
+
+
+REFERENCE_SRC = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE_SRC, "train.py")), reason="reference checkout not present")
+def test_launcher_drives_the_unmodified_reference_trainer_on_cpu(tmp_path):
+    """The reference's own train.py + dataset.py + CPU model (--no-dropin), two gloo ranks under torchrun, on synthetic
+    parsed-MIND files: shards differ per rank, the loader is re-created on exhaustion, only rank 0 writes TensorBoard."""
+    import subprocess
+    tmp = str(tmp_path)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_synth_mind.py"), tmp, "24", "60", "2"], check=True,
+                   stdout=subprocess.DEVNULL)
+    env = dict(os.environ, PYTHONPATH=SRC, CUDA_VISIBLE_DEVICES="", MODEL_NAME="NRMS", OMP_NUM_THREADS="4")
+    port = 29700 + (os.getpid() % 90)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), "-m", "newsrec_b200.launch", "--reference-src", REFERENCE_SRC, "--no-dropin", "--backend", "gloo",
+           "--set", "batch_size=4", "--set", "num_workers=0", "--set", "num_epochs=1", "--set", "num_batches_show_loss=2"]
+    r = subprocess.run(cmd, cwd=tmp, env=env, capture_output=True, text=True, timeout=600)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "Load training dataset with size 24." in out
+    losses = [ln for ln in out.splitlines() if "current loss" in ln]
+    assert len(losses) >= 2 * 3  # both ranks report at batches 2, 4, 6
+    assert out.count("Training data exhausted") >= 2  # each rank's 12-sample shard runs out after 3 batches of 4
+    runs = os.listdir(os.path.join(tmp, "runs", "NRMS"))
+    assert len(runs) == 1  # rank 0 alone created a TensorBoard run directory
