@@ -130,8 +130,17 @@ typedef struct {
     float* w;                 /* [n_seq*T] additive-attention weights                               */
     float* out;               /* [n_seq][d] fp32                                                    */
     int* bad_id_flag;         /* device int, set if an id is out of range                           */
+    /* fused front end (ids variant, shapes nr_mhsa_fused_supported() accepts; all three NULL = unfused kernel sequence):
+     * gather -> Q|K|V -> attention run as ONE kernel, X / Q|K|V stay on chip (they are written to X_bf16 / QKV_bf16
+     * only when those pointers are non-NULL, i.e. when a backward pass will read them), and the context leaves as a
+     * bf16 hi plane (C_bf16) plus a bf16 lo plane (C_lo_bf16): the pooled sum uses hi + lo. */
+    const void* wqkv_heads_bf16; /* [heads*64][ldx]: per head the rows W_Q[h] | W_K[h] | W_V[h] | zero rows up to 64 */
+    const float* bqkv_heads;     /* [heads*64] biases in the same order                                */
+    void* C_lo_bf16;             /* [n_seq*T][ldx]                                                      */
 } nr_mhsa_encoder_fwd_args;
 int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream);
+/* 1 if the fused front end handles (tokens per title, model width, heads): the reference's news level, T = 20, d_k = 20 */
+int nr_mhsa_fused_supported(int T, int d, int heads);
 
 typedef struct {
     long long n_seq;

@@ -117,6 +117,8 @@ int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits,
     return dot_score_bwd(cand, user, dlogits, B, C, D, dcand, duser, S(stream));
 }
 
+int nr_mhsa_fused_supported(int T, int d, int heads) { return mhsa_fused_supported(T, d, heads); }
+
 int nr_accumulate_ext_grad(float* ext, int rows, int ld, int D, float* dW, float* db, void* stream) {
     NR_REQUIRE(ext && dW && rows >= 0 && D >= 1, "nr_accumulate_ext_grad: null operand");
     return accumulate_ext_grad(ext, rows, ld, D, dW, db, S(stream));
@@ -136,13 +138,26 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
     NR_REQUIRE(a != nullptr, "nr_mhsa_encoder_fwd: null args");
     NR_PROPAGATE(check_mhsa_shape(a->n_seq, a->T, a->d, a->heads, a->q, a->ldx, a->ld3));
     NR_REQUIRE((a->ids != nullptr) != (a->dense != nullptr), "nr_mhsa_encoder_fwd: exactly one of ids / dense");
-    NR_REQUIRE(a->wqkv_bf16 && a->bqkv && a->wa_bf16 && a->ba && a->qv && a->X_bf16 && a->QKV_bf16 && a->C_bf16 && a->w &&
-                   a->out, "nr_mhsa_encoder_fwd: null operand");
+    const bool fused = a->ids != nullptr && a->wqkv_heads_bf16 != nullptr && a->bqkv_heads != nullptr && a->C_lo_bf16 != nullptr &&
+                       mhsa_fused_supported(a->T, a->d, a->heads);
+    NR_REQUIRE(a->wa_bf16 && a->ba && a->qv && a->C_bf16 && a->w && a->out, "nr_mhsa_encoder_fwd: null operand");
+    NR_REQUIRE(fused || (a->wqkv_bf16 && a->bqkv && a->X_bf16 && a->QKV_bf16), "nr_mhsa_encoder_fwd: null operand");
     NR_REQUIRE(a->p_drop >= 0.f && a->p_drop < 1.f, "nr_mhsa_encoder_fwd: dropout p=%f", a->p_drop);
     if (a->n_seq == 0) return 0;
     const int M = static_cast<int>(a->n_seq * a->T);
     const cudaStream_t st = S(stream);
     prof_context(a->ids != nullptr ? "news.fwd" : "user.fwd");
+    if (fused) {
+        // one kernel: gather -> Q|K|V -> attention (news_encoder.py:38-43); then the pooling GEMM on the hi plane with
+        // the pooled sum over hi + lo (additive.py:35-53)
+        NR_REQUIRE(a->table_bf16 && a->bad_id_flag && a->V >= 1, "nr_mhsa_encoder_fwd: table / bad_id_flag missing");
+        NR_PROPAGATE(mhsa_fused_fwd(a->ids, a->n_seq, a->T, a->table_bf16, a->V, a->d, a->heads, a->ldx, a->ld3, a->wqkv_heads_bf16,
+                                    a->bqkv_heads, DropoutCfg{a->p_drop, a->seed}, DropoutCfg{a->p_drop, a->seed ^ 0x5bd1e995u},
+                                    a->X_bf16, a->QKV_bf16, a->C_bf16, a->C_lo_bf16, a->bad_id_flag, st));
+        NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
+                                        a->w, st, a->C_lo_bf16));
+        return 0;
+    }
     if (a->ids != nullptr) {
         NR_REQUIRE(a->table_bf16 && a->bad_id_flag && a->V >= 1, "nr_mhsa_encoder_fwd: table / bad_id_flag missing");
         NR_PROPAGATE(gather_rows(a->ids, M, a->T, a->table_bf16, a->V, a->d, a->ldx, a->X_bf16, a->ldx, 0,

@@ -29,7 +29,9 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return t_err; }
 int read_device_error(int* out4) {
-    return (int)cudaMemcpyFromSymbol(out4, g_dev_error, sizeof(int) * 4);
+    const int rc = (int)cudaMemcpyFromSymbol(out4, g_dev_error, sizeof(int) * 4);
+    if (rc != 0 || out4[0] != 0) return rc;
+    return read_fused_device_error(out4);  // the fused encoder kernels keep their own record (fused_fwd.cu)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,7 +492,7 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
 }
 
 int gemm_additive_pool(const void* X, int M, int lda, int D, const void* Wa, int q, int ldw, const float* ba,
-                       const float* qv, int seg_len, float* out, int ldo, float* w_out, cudaStream_t stream) {
+                       const float* qv, int seg_len, float* out, int ldo, float* w_out, cudaStream_t stream, const void* X_lo) {
     if (M == 0) return 0;
     NR_REQUIRE(seg_len >= 1 && seg_len <= kTileM && M % seg_len == 0, "additive_pool: M=%d seg_len=%d", M, seg_len);
     NR_REQUIRE(q <= 256 && (D % 2) == 0 && (ldo % 2) == 0, "additive_pool: q=%d D=%d ldo=%d unsupported", q, D, ldo);
@@ -502,6 +504,7 @@ int gemm_additive_pool(const void* X, int M, int lda, int D, const void* Wa, int
     e.bias = ba;
     e.qv = qv;
     e.X = static_cast<const __nv_bfloat16*>(X);
+    e.X_lo = static_cast<const __nv_bfloat16*>(X_lo);
     e.lda = lda;
     e.D = D;
     e.seg_len = seg_len;

@@ -204,6 +204,7 @@ struct EpiPool {
     const float* bias;
     const float* qv;
     const __nv_bfloat16* X;  // the GEMM's A operand (rows x lda), re-read (L2 hits) for the weighted sum
+    const __nv_bfloat16* X_lo;  // optional second plane (same pitch): the pooled rows are X + X_lo (hi/lo bf16 pair)
     int lda;
     int D;        // pooled width (even)
     int seg_len;
@@ -304,6 +305,13 @@ struct EpiPool {
             wsum_rows<10>(xp, pitch16, sw, t, a);
             wsum_rows<4>(xp, pitch16, sw, t, a);
             wsum_rows<1>(xp, pitch16, sw, t, a);
+            if (X_lo != nullptr) {  // low plane of a hi/lo pair: same weights, same accumulators
+                const uint4* xl = reinterpret_cast<const uint4*>(X_lo + static_cast<size_t>(r0) * lda) + ck;
+                t = 0;
+                wsum_rows<10>(xl, pitch16, sw, t, a);
+                wsum_rows<4>(xl, pitch16, sw, t, a);
+                wsum_rows<1>(xl, pitch16, sw, t, a);
+            }
             float* o = out + static_cast<size_t>(r0 / seg_len) * ldo + ck * 8;
             if (ck * 8 + 8 <= D && (ldo & 3) == 0) {
                 *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);

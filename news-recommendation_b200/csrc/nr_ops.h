@@ -23,8 +23,10 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
                int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream);
 
 // additive-attention pooling: out[seg][D] = sum_r softmax_seg(tanh(X Wa^T + ba) . qv)_r X_r ; w_out[rows]
+// X_lo (may be null): a second bf16 plane with X = X_hi + X_lo; the scores use X_hi, the pooled sum both planes.
 int gemm_additive_pool(const void* X, int M, int lda, int D, const void* Wa, int q, int ldw, const float* ba,
-                       const float* qv, int seg_len, float* out, int ldo, float* w_out, cudaStream_t stream);
+                       const float* qv, int seg_len, float* out, int ldo, float* w_out, cudaStream_t stream,
+                       const void* X_lo = nullptr);
 
 // dPre = dscore * qv * (1 - tanh^2(X Wa^T + ba)) -> bf16 [M x ld_dpre]; dqv += sum_r dscore_r tanh(..)
 int gemm_additive_dpre(const void* X, int M, int lda, int D, const void* Wa, int q, int ldw, const float* ba,
@@ -74,6 +76,15 @@ int relu_bwd_to_bf16(const float* dy, const float* relu_out, long long n, int N,
 int embedding_f32_fwd(const long long* ids, long long n, const float* table, int V, int D, float* out, int* bad_id_flag,
                       cudaStream_t stream);
 int embedding_f32_bwd(const long long* ids, long long n, const float* dout, int D, float* dtable, cudaStream_t stream);
+
+// ---- fused NRMS news-encoder front end (fused_fwd.cu): ids -> gather -> Q|K|V -> attention -> context hi/lo planes -----
+// w_heads bf16 [heads*64][ldx]: per head the rows W_Q[h] | W_K[h] | W_V[h] | zero rows up to 64; b_heads fp32 [heads*64].
+// X / QKV may be null (inference): they are only written for the backward kernels.
+int mhsa_fused_supported(int T, int d, int heads);
+int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* table, int V, int d, int heads, int ldx, int ld3,
+                   const void* w_heads, const float* b_heads, DropoutCfg drop_x, DropoutCfg drop_c, void* X, void* QKV, void* C_hi,
+                   void* C_lo, int* bad_id_flag, cudaStream_t stream);
+int read_fused_device_error(int* out4);
 
 int num_sms();
 

@@ -24,6 +24,7 @@ class MhsaEncoderFwdArgs(C.Structure):
         ("wqkv_bf16", _vp), ("bqkv", _vp), ("wa_bf16", _vp), ("ba", _vp), ("qv", _vp),
         ("p_drop", _f), ("seed", _ull),
         ("X_bf16", _vp), ("QKV_bf16", _vp), ("C_bf16", _vp), ("w", _vp), ("out", _vp), ("bad_id_flag", _vp),
+        ("wqkv_heads_bf16", _vp), ("bqkv_heads", _vp), ("C_lo_bf16", _vp),
     ]
 
 
@@ -113,6 +114,7 @@ SIGNATURES = {
     "nr_accumulate_ext_grad": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "nr_dot_score_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nr_mhsa_encoder_fwd": (_i, [C.POINTER(MhsaEncoderFwdArgs), _vp]),
+    "nr_mhsa_fused_supported": (_i, [_i, _i, _i]),
     "nr_mhsa_encoder_bwd_workspace": (_ll, [_ll, _i, _i, _i]),
     "nr_mhsa_encoder_bwd": (_i, [C.POINTER(MhsaEncoderBwdArgs), _vp]),
     "nr_cnn_encoder_fwd": (_i, [C.POINTER(CnnEncoderFwdArgs), _vp]),

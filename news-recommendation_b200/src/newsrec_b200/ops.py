@@ -95,6 +95,19 @@ def mhsa_operands(cache: OperandCache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, q
     return cache.get(prefix, (Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv), build)
 
 
+def pack_head_blocks(Wq, bq, Wk, bk, Wv, bv, heads, ldx, rows_per_head=64):
+    """Per-head weight blocks of the fused front end: rows W_Q[h] | W_K[h] | W_V[h] | zero rows up to `rows_per_head`
+    (head h owns output features [h*d_k, (h+1)*d_k) of each projection, multihead_self.py:53-58).  Layout plumbing only."""
+    d = Wq.shape[0]
+    dk = d // heads
+    W = torch.zeros((heads, rows_per_head, d), dtype=torch.float32, device=Wq.device)
+    b = torch.zeros((heads, rows_per_head), dtype=torch.float32, device=Wq.device)
+    for i, (Wm, bm) in enumerate(((Wq, bq), (Wk, bk), (Wv, bv))):
+        W[:, i * dk:(i + 1) * dk] = Wm.float().view(heads, dk, d)
+        b[:, i * dk:(i + 1) * dk] = bm.float().view(heads, dk)
+    return cast_pad(W.view(heads * rows_per_head, d), ldx), b.view(-1).contiguous()
+
+
 def table_operand(cache: OperandCache, name, weight):
     ldx = ru8(weight.shape[1] + 1)
     return cache.get(name, (weight,), lambda w: cast_pad(w, ldx))
@@ -134,8 +147,13 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
             a.dense_s_seq, a.dense_s_tok, a.dense_s_col = dense.stride()
             table = None
         n_tok = n_seq * T
-        X = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
-        QKV = torch.empty((n_tok, ld3), dtype=torch.bfloat16, device=dev)
+        need_bwd = any(ctx.needs_input_grad)
+        # the fused front end (gather -> Q|K|V -> attention in one kernel) covers the reference's news level shapes
+        fused = ids is not None and os.environ.get("NEWSREC_NO_FUSED") is None and bool(lib.nr_mhsa_fused_supported(T, d, heads))
+        X = QKV = C_lo = None
+        if need_bwd or not fused:  # X / Q|K|V only exist in HBM when a backward pass (or the unfused sequence) reads them
+            X = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
+            QKV = torch.empty((n_tok, ld3), dtype=torch.bfloat16, device=dev)
         Cx = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
         w = torch.empty((n_tok,), dtype=torch.float32, device=dev)
         out = torch.empty((n_seq, d), dtype=torch.float32, device=dev)
@@ -143,10 +161,16 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         a.n_seq, a.T, a.d, a.heads, a.q, a.ldx, a.ld3 = n_seq, T, d, heads, q, ldx, ld3
         a.wqkv_bf16, a.bqkv, a.wa_bf16, a.ba, a.qv = _p(ops["wqkv"]), _p(ops["bqkv"]), _p(ops["wa"]), _p(ops["ba"]), _p(ops["qv"])
         a.p_drop, a.seed = float(p_drop), seed
+        if fused:
+            hb = cache.get(prefix + ".heads", (Wq, bq, Wk, bk, Wv, bv),
+                           lambda Wq, bq, Wk, bk, Wv, bv: pack_head_blocks(Wq, bq, Wk, bk, Wv, bv, heads, ldx))
+            C_lo = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
+            a.wqkv_heads_bf16, a.bqkv_heads, a.C_lo_bf16 = _p(hb[0]), _p(hb[1]), _p(C_lo)
         a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.out = _p(X), _p(QKV), _p(Cx), _p(w), _p(out)
         a.bad_id_flag = _p(bad_flag)
         check(lib.nr_mhsa_encoder_fwd(C.byref(a), _stream()), "nr_mhsa_encoder_fwd")
-        ctx.save_for_backward(X, QKV, Cx, w, ids if ids is not None else torch.empty(0, device=dev))
+        if need_bwd:
+            ctx.save_for_backward(X, QKV, Cx, w, ids if ids is not None else torch.empty(0, device=dev))
         ctx.meta = dict(n_seq=n_seq, T=T, d=d, q=q, heads=heads, p_drop=float(p_drop), seed=seed, ops=ops,
                         has_ids=ids is not None, V=emb_w.shape[0] if ids is not None else 0,
                         dense_shape=None if dense is None else tuple(dense.shape),

@@ -78,12 +78,31 @@ class _RoundGrad(torch.autograd.Function):
         return _round_bf16(g)
 
 
+class _RoundHiLo(torch.autograd.Function):
+    """value -> bf16 hi + bf16 lo pair (about 16 mantissa bits) forward; gradient -> bf16 on the way back."""
+
+    @staticmethod
+    def forward(ctx, x):
+        hi = _round_bf16(x)
+        return hi + _round_bf16(x - hi)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _round_bf16(g)
+
+
 @dataclass(frozen=True)
 class Contract:
     bf16: bool = False
+    hilo: bool = False     # fused news front end (csrc/fused_fwd.cu): V and the context are hi/lo bf16 pairs
 
     def act(self, x):      # an activation the kernels store in bf16 (and whose grad they store in bf16)
         return _RoundBoth.apply(x) if self.bf16 else x
+
+    def act_hilo(self, x):  # an activation the fused kernels keep as a hi/lo bf16 pair (plain bf16 on the unfused path)
+        if self.bf16 and self.hilo:
+            return _RoundHiLo.apply(x)
+        return self.act(x)
 
     def operand(self, x):  # a parameter / input converted to a bf16 tensor-core operand; grad stays fp32
         return _RoundFwd.apply(x) if self.bf16 else x
@@ -94,6 +113,49 @@ class Contract:
 
 EXACT = Contract(False)
 BF16 = Contract(True)
+BF16_FUSED = Contract(True, True)
+
+
+# --------------------------------------------------------------------------- #
+# dropout: NumPy restatement of the kernels' counter hash (csrc/nr_common.cuh dropout_bits4,
+# nr_epilogues.cuh Dropout::mask4).  The reference draws its masks from torch's global RNG
+# (news_encoder.py:38,43), which no kernel can reproduce; train-mode parity is therefore checked by
+# giving the ORACLE the kernel's masks: element (row, col) of a matrix with pitch ld belongs to group
+# (row*ld + col) >> 2 and is kept iff 16-bit lane (col & 3) of hash(seed, group) >= round(p * 65536).
+# --------------------------------------------------------------------------- #
+def dropout_bits4(seed: int, group):
+    import numpy as np
+    M32 = np.uint64(0xFFFFFFFF)
+    group = np.asarray(group, dtype=np.uint64)
+    s_lo, s_hi = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    g_lo, g_hi = group & M32, group >> np.uint64(32)
+    with np.errstate(over="ignore"):
+        x = ((g_lo ^ s_lo) + g_hi * np.uint64(0x85EBCA6B) + s_hi * np.uint64(0x165667B1)) & M32
+        x = (x * np.uint64(0x9E3779B1)) & M32
+        x ^= x >> np.uint64(15)
+        x = (x * np.uint64(0x85EBCA77)) & M32
+        x ^= x >> np.uint64(13)
+        y = (x * np.uint64(0xC2B2AE3D) + s_hi) & M32
+        y ^= y >> np.uint64(16)
+        y = (y * np.uint64(0x27D4EB2F)) & M32
+        y ^= y >> np.uint64(15)
+    return (y << np.uint64(32)) | x
+
+
+def dropout_mask(seed: int, p: float, n_rows: int, n_cols: int, ld: int, row0: int = 0, col0: int = 0):
+    """fp32 (n_rows, n_cols) multipliers (0 or 1/(1-p)) of rows [row0, row0+n_rows), columns [col0, col0+n_cols)."""
+    import numpy as np
+    if p <= 0.0:
+        return torch.ones(n_rows, n_cols)
+    assert ld % 4 == 0
+    thresh = int(np.float32(p) * np.float32(65536.0) + np.float32(0.5))
+    rows = (np.arange(n_rows, dtype=np.uint64) + np.uint64(row0))[:, None]
+    cols = (np.arange(n_cols, dtype=np.uint64) + np.uint64(col0))[None, :]
+    flat = rows * np.uint64(ld) + cols
+    bits = dropout_bits4(seed, flat >> np.uint64(2))
+    lane = (bits >> (np.uint64(16) * (flat & np.uint64(3)))) & np.uint64(0xFFFF)
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return torch.from_numpy(np.where(lane >= thresh, scale, np.float32(0.0)).astype(np.float32))
 
 
 # --------------------------------------------------------------------------- #
@@ -119,7 +181,7 @@ def scaled_dot_product_attention(Q, K, V, c: "Contract" = None):
     return torch.matmul(attn, V)
 
 
-def multihead_self_attention(x, p, prefix, heads, c: Contract = EXACT):
+def multihead_self_attention(x, p, prefix, heads, c: Contract = EXACT, ctx_mask=None):
     """src/model/general/attention/multihead_self.py:46-76 (Q=K=V=x, length=None).
 
     x: (N, T, d).  W_Q/W_K/W_V are nn.Linear(d, d) WITH bias (:35-37); there is no
@@ -131,14 +193,17 @@ def multihead_self_attention(x, p, prefix, heads, c: Contract = EXACT):
 
     def proj(name):
         w = c.operand(p[f"{prefix}.W_{name}.weight"])
-        return c.act(F.linear(x, w) + p[f"{prefix}.W_{name}.bias"])
+        y = F.linear(x, w) + p[f"{prefix}.W_{name}.bias"]
+        return c.act_hilo(y) if name == "V" else c.act(y)  # fused path: V enters P.V as a hi/lo pair
 
     def split(t):  # (N,T,d) -> (N,h,T,d_k)   (:53-58)
         return t.view(N, T, heads, d_k).transpose(1, 2)
 
     ctx = scaled_dot_product_attention(split(proj("Q")), split(proj("K")), split(proj("V")), c)
     ctx = ctx.transpose(1, 2).contiguous().view(N, T, d)  # (:74-76)
-    return c.act(ctx)
+    if ctx_mask is not None:  # train mode: dropout on the context (NRMS/news_encoder.py:43) with an injected mask
+        ctx = ctx * ctx_mask
+    return c.act_hilo(ctx)
 
 
 def additive_attention(x, p, prefix, c: Contract = EXACT):
@@ -150,7 +215,8 @@ def additive_attention(x, p, prefix, c: Contract = EXACT):
     w.r.t. the pre-activation is stored bf16.
     """
     w = c.operand(p[f"{prefix}.linear.weight"])
-    pre = c.grad(F.linear(x, w) + p[f"{prefix}.linear.bias"])
+    xs = c.operand(x) if (c.bf16 and c.hilo) else x  # hi/lo input: the score GEMM reads the hi plane, the pooled sum both
+    pre = c.grad(F.linear(xs, w) + p[f"{prefix}.linear.bias"])
     temp = torch.tanh(pre)
     weights = F.softmax(torch.matmul(temp, p[f"{prefix}.attention_query_vector"]), dim=1)
     return torch.bmm(weights.unsqueeze(1), x).squeeze(1)
@@ -180,10 +246,19 @@ def title_cnn(x, weight, bias, c: Contract = EXACT):
 # --------------------------------------------------------------------------- #
 # NRMS  (reference: src/model/NRMS/**)
 # --------------------------------------------------------------------------- #
-def nrms_news_encoder(title, p, heads, c: Contract = EXACT, prefix="news_encoder"):
-    """src/model/NRMS/news_encoder.py:27-48 in eval mode (dropout off, :38-45)."""
+def nrms_news_encoder(title, p, heads, c: Contract = EXACT, prefix="news_encoder", drop=None):
+    """src/model/NRMS/news_encoder.py:27-48.  drop=None: eval mode (dropout off, :38-45).
+    drop=dict(p, seed, ld, row0): train mode with the kernels' masks -- embedding rows under hash(seed) (:38),
+    context under hash(seed ^ 0x5bd1e995) (:43); rows are numbered row0.. in the order of `title`."""
     x = embedding(title, p[f"{prefix}.word_embedding.weight"], c)
-    x = multihead_self_attention(x, p, f"{prefix}.multihead_self_attention", heads, c)
+    ctx_mask = None
+    if drop is not None and drop["p"] > 0:
+        N, T, d = x.shape
+        mx = dropout_mask(drop["seed"], drop["p"], N * T, d, drop["ld"], drop.get("row0", 0)).view(N, T, d)
+        ctx_mask = dropout_mask(drop["seed"] ^ 0x5bd1e995, drop["p"], N * T, d, drop["ld"], drop.get("row0", 0)).view(N, T, d)
+        x = c.act(x * mx.to(x.dtype))  # the gathered rows are stored bf16 after the 1/(1-p) scaling
+        ctx_mask = ctx_mask.to(x.dtype)
+    x = multihead_self_attention(x, p, f"{prefix}.multihead_self_attention", heads, c, ctx_mask)
     return additive_attention(x, p, f"{prefix}.additive_attention", c)
 
 
@@ -194,12 +269,17 @@ def nrms_user_encoder(clicked_vec, p, heads, c: Contract = EXACT, prefix="user_e
     return additive_attention(x, p, f"{prefix}.additive_attention", c)
 
 
-def nrms_forward(cand_title, clicked_title, p, heads, c: Contract = EXACT):
-    """src/model/NRMS/__init__.py:19-48.  cand_title (B,C,T), clicked_title (B,H,T) int64."""
+def nrms_forward(cand_title, clicked_title, p, heads, c: Contract = EXACT, c_news: Contract = None, drop=None):
+    """src/model/NRMS/__init__.py:19-48.  cand_title (B,C,T), clicked_title (B,H,T) int64.
+    c_news: storage contract of the news encoder when it differs from the user encoder's (fused front end).
+    drop: see nrms_news_encoder; rows are numbered as the drop-in packs them (browsed block, then candidates)."""
     B, C, T = cand_title.shape
     H = clicked_title.shape[1]
-    cand = nrms_news_encoder(cand_title.reshape(B * C, T), p, heads, c).view(B, C, -1)
-    clicked = nrms_news_encoder(clicked_title.reshape(B * H, T), p, heads, c).view(B, H, -1)
+    cn = c if c_news is None else c_news
+    d_clicked = None if drop is None else dict(drop, row0=0)
+    d_cand = None if drop is None else dict(drop, row0=B * H * T)
+    cand = nrms_news_encoder(cand_title.reshape(B * C, T), p, heads, cn, drop=d_cand).view(B, C, -1)
+    clicked = nrms_news_encoder(clicked_title.reshape(B * H, T), p, heads, cn, drop=d_clicked).view(B, H, -1)
     user = nrms_user_encoder(clicked, p, heads, c)
     return dot_product_click_predictor(cand, user)
 

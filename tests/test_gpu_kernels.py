@@ -82,3 +82,16 @@ def test_additive_attention(kw):
 def test_dot_product_click_predictor():
     r = G.check_dot_score()
     assert r["fwd_rel"] < 1e-6 and r["dc_rel"] < 1e-6 and r["du_rel"] < 1e-6, r
+
+
+@pytest.mark.parametrize("kw", [dict(n_seq=13), dict(n_seq=6), dict(n_seq=1), dict(n_seq=1000, V=5000),
+                                dict(n_seq=13, p_drop=0.2), dict(n_seq=777, V=3000, p_drop=0.2, seed=0xDEADBEEFCAFE)])
+def test_fused_news_front_end(kw):
+    """One-kernel gather -> Q|K|V -> attention: X bit exact against the unfused gather (same masks), context against the
+    oracle under the fused storage contract <= 1e-3 (measured ~1e-4: bf16 rounding flips of Q / K / P), pooled vector too."""
+    r = G.check_fused_front(**kw)
+    assert r["x_bit_exact"] and r["bad_flag"] == 0 and r["ctx_hi_ones_col"], r
+    assert r.get("x_vs_masked_oracle_exact", True), r
+    assert r["qkv_rel"] < 3e-3, r                       # the two GEMMs may round a bf16 result differently
+    assert r["ctx_vs_oracle_fused_contract"] < 1e-3, r
+    assert r["out_vs_oracle"] < 1e-3 and r["w_sums_to_one"] < 1e-5, r
