@@ -131,9 +131,10 @@ typedef struct {
     float* out;               /* [n_seq][d] fp32                                                    */
     int* bad_id_flag;         /* device int, set if an id is out of range                           */
     /* fused front end (ids variant, shapes nr_mhsa_fused_supported() accepts; all three NULL = unfused kernel sequence):
-     * gather -> Q|K|V -> attention run as ONE kernel, X / Q|K|V stay on chip (they are written to X_bf16 / QKV_bf16
-     * only when those pointers are non-NULL, i.e. when a backward pass will read them), and the context leaves as a
-     * bf16 hi plane (C_bf16) plus a bf16 lo plane (C_lo_bf16): the pooled sum uses hi + lo. */
+     * gather -> Q|K|V -> attention run as ONE kernel; the gathered rows are written to X_bf16 only when that pointer is
+     * non-NULL (a backward pass will read them), Q|K|V never leaves the chip (QKV_bf16 must be NULL; the backward
+     * recomputes it from X), and the context leaves as a bf16 hi plane (C_bf16) plus a bf16 lo plane (C_lo_bf16): the
+     * pooled sum uses hi + lo. */
     const void* wqkv_heads_bf16; /* [heads*64][ldx]: per head the rows W_Q[h] | W_K[h] | W_V[h] | zero rows up to 64 */
     const float* bqkv_heads;     /* [heads*64] biases in the same order                                */
     void* C_lo_bf16;             /* [n_seq*T][ldx]                                                      */
@@ -167,6 +168,9 @@ typedef struct {
     float* ddense;                       /* [n_seq*T][d] (=) input gradient (dense variant)              */
     void* workspace;
     long long workspace_bytes;
+    /* QKV_bf16 == NULL (the fused forward keeps Q|K|V on chip): recomputed here from X_bf16 with these operands */
+    const void* wqkv_bf16;               /* [3d][ldx]                                                    */
+    const float* bqkv;                   /* [3d]                                                         */
 } nr_mhsa_encoder_bwd_args;
 long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q);
 int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream);
@@ -237,7 +241,8 @@ int nr_linear_rows_bwd(const float* dy, const float* relu_out, long long n, int 
 /* ---- fp32 embedding lookups (LSTUR category / user embeddings, src/model/LSTUR/news_encoder.py:47-53) ---- */
 int nr_embedding_f32_fwd(const long long* ids, long long n, const float* table, int V, int D, float* out,
                          int* bad_id_flag, void* stream);
-int nr_embedding_f32_bwd(const long long* ids, long long n, const float* dout, int D, float* dtable, void* stream);
+/* ids outside [1, V) contribute nothing (row 0 = padding_idx; out-of-range ids are flagged by the forward lookup) */
+int nr_embedding_f32_bwd(const long long* ids, long long n, const float* dout, int V, int D, float* dtable, void* stream);
 
 /* ---- reference: NAML ElementEncoder  relu(Linear(embedding(id)))  (src/model/NAML/news_encoder.py:40-47) --- */
 int nr_element_encoder_fwd(const long long* ids, long long n, const void* table_bf16, int V, int E, int lde,
@@ -245,7 +250,7 @@ int nr_element_encoder_fwd(const long long* ids, long long n, const void* table_
                            void* stream);
 int nr_element_encoder_bwd(const long long* ids, long long n, const float* dout, const float* out, int F, void* dY_bf16,
                            int ldf, const void* E_bf16, int E, int lde, const void* WT_bf16, float* dW_ext,
-                           float* dtable, void* stream);
+                           float* dtable, int V, void* stream);
 
 /* ---- reference: LSTUR UserEncoder -- pack_padded_sequence + nn.GRU, last hidden state -----------------
  * (src/model/LSTUR/user_encoder.py:16-45).  Gate order r, z, n; user b consumes the FIRST len[b] positions of

@@ -142,6 +142,7 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
                        mhsa_fused_supported(a->T, a->d, a->heads);
     NR_REQUIRE(a->wa_bf16 && a->ba && a->qv && a->C_bf16 && a->w && a->out, "nr_mhsa_encoder_fwd: null operand");
     NR_REQUIRE(fused || (a->wqkv_bf16 && a->bqkv && a->X_bf16 && a->QKV_bf16), "nr_mhsa_encoder_fwd: null operand");
+    NR_REQUIRE(!fused || a->QKV_bf16 == nullptr, "nr_mhsa_encoder_fwd: the fused front end never writes Q|K|V (pass QKV_bf16 = NULL)");
     NR_REQUIRE(a->p_drop >= 0.f && a->p_drop < 1.f, "nr_mhsa_encoder_fwd: dropout p=%f", a->p_drop);
     if (a->n_seq == 0) return 0;
     const int M = static_cast<int>(a->n_seq * a->T);
@@ -151,9 +152,9 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
         // one kernel: gather -> Q|K|V -> attention (news_encoder.py:38-43); then the pooling GEMM on the hi plane with
         // the pooled sum over hi + lo (additive.py:35-53)
         NR_REQUIRE(a->table_bf16 && a->bad_id_flag && a->V >= 1, "nr_mhsa_encoder_fwd: table / bad_id_flag missing");
-        NR_PROPAGATE(mhsa_fused_fwd(a->ids, a->n_seq, a->T, a->table_bf16, a->V, a->d, a->heads, a->ldx, a->ld3, a->wqkv_heads_bf16,
+        NR_PROPAGATE(mhsa_fused_fwd(a->ids, a->n_seq, a->T, a->table_bf16, a->V, a->d, a->heads, a->ldx, a->wqkv_heads_bf16,
                                     a->bqkv_heads, DropoutCfg{a->p_drop, a->seed}, DropoutCfg{a->p_drop, a->seed ^ 0x5bd1e995u},
-                                    a->X_bf16, a->QKV_bf16, a->C_bf16, a->C_lo_bf16, a->bad_id_flag, st));
+                                    a->X_bf16, a->C_bf16, a->C_lo_bf16, a->bad_id_flag, st));
         NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
                                         a->w, st, a->C_lo_bf16));
         return 0;
@@ -182,7 +183,7 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
 long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q) {
     const long long rows = n_seq * T;
     const long long ldx = (d + 1 + 7) & ~7, ld3 = (3 * d + 15) & ~15, ldq = (q + 15) & ~15;
-    return align256(rows * 4) + align256(rows * ldq * 2) + align256(rows * ldx * 2) + align256(rows * ld3 * 2) + 256;
+    return align256(rows * 4) + align256(rows * ldq * 2) + align256(rows * ldx * 2) + 2 * align256(rows * ld3 * 2) + 256;
 }
 
 int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
@@ -191,9 +192,11 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     NR_REQUIRE(a->ldq % 8 == 0 && a->ldq >= a->q, "nr_mhsa_encoder_bwd: ldq=%d", a->ldq);
     NR_REQUIRE(a->ldx == ((a->d + 8) & ~7) && a->ld3 == ((3 * a->d + 15) & ~15) && a->ldq == ((a->q + 15) & ~15),
                "nr_mhsa_encoder_bwd: pitches must be canonical: ldx=round_up(d+1,8), ld3=round_up(3d,16), ldq=round_up(q,16)");
-    NR_REQUIRE(a->wqkvT_bf16 && a->wa_bf16 && a->waT_bf16 && a->ba && a->qv && a->X_bf16 && a->QKV_bf16 && a->C_bf16 &&
+    NR_REQUIRE(a->wqkvT_bf16 && a->wa_bf16 && a->waT_bf16 && a->ba && a->qv && a->X_bf16 && a->C_bf16 &&
                    a->w && a->dout && a->dWqkv_ext && a->dWa_ext && a->dqv && a->workspace,
                "nr_mhsa_encoder_bwd: null operand");
+    NR_REQUIRE(a->QKV_bf16 != nullptr || (a->wqkv_bf16 != nullptr && a->bqkv != nullptr),
+               "nr_mhsa_encoder_bwd: Q|K|V was not saved (fused forward): pass wqkv_bf16 / bqkv so that it can be recomputed from X");
     NR_REQUIRE((a->ids != nullptr) ? (a->demb != nullptr) : (a->ddense != nullptr),
                "nr_mhsa_encoder_bwd: missing input-gradient buffer");
     NR_REQUIRE(a->workspace_bytes >= nr_mhsa_encoder_bwd_workspace(a->n_seq, a->T, a->d, a->q),
@@ -210,8 +213,15 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     void* dC = ws;
     ws += align256(rows * a->ldx * 2);
     void* dQKV = ws;
+    ws += align256(rows * a->ld3 * 2);
 
     prof_context(a->ids != nullptr ? "news.bwd" : "user.bwd");
+    const void* QKV = a->QKV_bf16;
+    if (QKV == nullptr) {  // the fused forward keeps Q|K|V on chip: recompute it from the saved rows (multihead_self.py:53-58)
+        NR_PROPAGATE(gemm_store(a->X_bf16, M, a->ldx, a->wqkv_bf16, 3 * a->d, a->ldx, a->d, 1, 0, 128, a->bqkv, 0, ws, a->ld3, 1,
+                                kIdentity, 0, kNoDrop, -1, 0, st));
+        QKV = ws;
+    }
     // --- additive pooling backward ---
     NR_PROPAGATE(pool_dscore(a->C_bf16, a->ldx, a->d, a->n_seq, a->T, a->w, a->dout, a->d, dscore, st));
     NR_PROPAGATE(gemm_additive_dpre(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, dscore, dpre, a->ldq,
@@ -222,12 +232,13 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     NR_PROPAGATE(gemm_tn_accumulate(dpre, M, a->q, a->ldq, a->C_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWa_ext,
                                     a->ldx, st));
     // --- attention backward ---
-    NR_PROPAGATE(mhsa_core_bwd(a->QKV_bf16, a->ld3, dC, a->ldx, a->n_seq, a->T, a->heads, a->d / a->heads, dQKV, a->ld3, st));
+    NR_PROPAGATE(mhsa_core_bwd(QKV, a->ld3, dC, a->ldx, a->n_seq, a->T, a->heads, a->d / a->heads, dQKV, a->ld3, st));
     // --- projection backward: weights (+bias through the ones column of X), then the input ---
     NR_PROPAGATE(gemm_tn_accumulate(dQKV, M, 3 * a->d, a->ld3, a->X_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWqkv_ext,
                                     a->ldx, st));
     if (a->ids != nullptr) {
-        NR_PROPAGATE(gemm_scatter_emb(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, a->ids, a->demb, a->d,
+        NR_REQUIRE(a->V >= 1, "nr_mhsa_encoder_bwd: V=%d", a->V);
+        NR_PROPAGATE(gemm_scatter_emb(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, a->ids, a->demb, a->V, a->d,
                                       kIdentity, DropoutCfg{a->p_drop, a->seed}, a->ldx, st));
     } else {
         NR_PROPAGATE(gemm_store(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, nullptr, 0, a->ddense, a->d,

@@ -93,7 +93,7 @@ int nr_cnn_encoder_bwd(const nr_cnn_encoder_bwd_args* a, void* stream) {
     // embedding gradient: dX[r] = sum_s' W_(2-s')^T dY[r + s' - 1], scattered to the token ids
     const RowMapCfg to_compact = {Tp, 1, T, T, 0};
     NR_PROPAGATE(gemm_scatter_emb(dYp, Mp, a->ldf, a->wconvT_bf16, a->d, a->ldf, a->F, 3, a->d, (128 / Tp) * Tp, a->ids, a->demb,
-                                  a->d, to_compact, DropoutCfg{a->p_drop, a->seed}, a->ldx, st));
+                                  a->V, a->d, to_compact, DropoutCfg{a->p_drop, a->seed}, a->ldx, st));
     return 0;
 }
 
@@ -137,9 +137,9 @@ int nr_embedding_f32_fwd(const long long* ids, long long n, const float* table, 
     NR_REQUIRE(ids && table && out && bad_id_flag && D >= 1, "nr_embedding_f32_fwd: null operand");
     return embedding_f32_fwd(ids, n, table, V, D, out, bad_id_flag, S(stream));
 }
-int nr_embedding_f32_bwd(const long long* ids, long long n, const float* dout, int D, float* dtable, void* stream) {
-    NR_REQUIRE(ids && dout && dtable, "nr_embedding_f32_bwd: null operand");
-    return embedding_f32_bwd(ids, n, dout, D, dtable, S(stream));
+int nr_embedding_f32_bwd(const long long* ids, long long n, const float* dout, int V, int D, float* dtable, void* stream) {
+    NR_REQUIRE(ids && dout && dtable && V >= 1, "nr_embedding_f32_bwd: null operand or V=%d", V);
+    return embedding_f32_bwd(ids, n, dout, V, D, dtable, S(stream));
 }
 
 // ---- NAML ElementEncoder: relu(Linear(embedding(id)))  (reference NAML/news_encoder.py:40-47) ----------------
@@ -154,15 +154,15 @@ int nr_element_encoder_fwd(const long long* ids, long long n, const void* table_
                       S(stream));
 }
 int nr_element_encoder_bwd(const long long* ids, long long n, const float* dout, const float* out, int F, void* dY_bf16, int ldf,
-                           const void* E_bf16, int E, int lde, const void* WT_bf16, float* dW_ext, float* dtable, void* stream) {
+                           const void* E_bf16, int E, int lde, const void* WT_bf16, float* dW_ext, float* dtable, int V, void* stream) {
     NR_REQUIRE(ids && dout && out && dY_bf16 && E_bf16 && WT_bf16 && dW_ext && dtable && ldf == ru8(F + 1) && lde == ru8(E + 1) &&
-                   E % 4 == 0 && n < (1ll << 31), "nr_element_encoder_bwd: bad argument");
+                   E % 4 == 0 && n < (1ll << 31) && V >= 1, "nr_element_encoder_bwd: bad argument");
     if (n == 0) return 0;
     prof_context("element.bwd");
     NR_PROPAGATE(relu_bwd_to_bf16(dout, out, n, F, F, dY_bf16, ldf, S(stream)));
     NR_PROPAGATE(gemm_tn_accumulate(dY_bf16, static_cast<int>(n), F, ldf, E_bf16, static_cast<int>(n), E + 1, lde, 0, E + 1, 0, dW_ext,
                                     lde, S(stream)));
-    return gemm_scatter_emb(dY_bf16, static_cast<int>(n), ldf, WT_bf16, E, ldf, F, 1, 0, 128, ids, dtable, E, kIdentity, kNoDrop, lde,
+    return gemm_scatter_emb(dY_bf16, static_cast<int>(n), ldf, WT_bf16, E, ldf, F, 1, 0, 128, ids, dtable, V, E, kIdentity, kNoDrop, lde,
                             S(stream));
 }
 

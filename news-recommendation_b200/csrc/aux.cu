@@ -405,14 +405,14 @@ __global__ void emb_f32_fwd_kernel(const long long* __restrict__ ids, long long 
         for (int c = lane; c < D; c += 32) out[i * D + c] = table[id * D + c];
     }
 }
-__global__ void emb_f32_bwd_kernel(const long long* __restrict__ ids, long long n, const float* __restrict__ dout, int D,
+__global__ void emb_f32_bwd_kernel(const long long* __restrict__ ids, long long n, const float* __restrict__ dout, int V, int D,
                                    float* __restrict__ dtable) {
     const int lane = threadIdx.x & 31;
     const long long w0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
     const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     for (long long i = w0; i < n; i += nw) {
         const long long id = ids[i];
-        if (id == 0) continue;  // padding_idx
+        if (id <= 0 || id >= V) continue;  // padding_idx; out-of-range ids were flagged by the forward lookup
         for (int c = lane; c < D; c += 32) red_add_f32(dtable + id * D + c, dout[i * D + c]);
     }
 }
@@ -426,11 +426,11 @@ int embedding_f32_fwd(const long long* ids, long long n, const float* table, int
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
-int embedding_f32_bwd(const long long* ids, long long n, const float* dout, int D, float* dtable, cudaStream_t stream) {
+int embedding_f32_bwd(const long long* ids, long long n, const float* dout, int V, int D, float* dtable, cudaStream_t stream) {
     if (n == 0) return 0;
     ProfScope ps("embedding_f32_bwd", static_cast<int>(n), D, 0, stream);
     const int blocks = static_cast<int>(std::min<long long>((n + 7) / 8, 148 * 8));
-    emb_f32_bwd_kernel<<<blocks, 256, 0, stream>>>(ids, n, dout, D, dtable);
+    emb_f32_bwd_kernel<<<blocks, 256, 0, stream>>>(ids, n, dout, V, D, dtable);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -5,14 +5,20 @@
 //
 // in ONE persistent kernel: the gathered rows, Q|K|V, the scores and the probabilities never leave the SM.  What reaches HBM
 // is the context C (as a bf16 hi plane + a bf16 lo plane: C is the operand of the pooling GEMM and the precise input of the
-// pooled sum) and, only when the caller asks for them (training: the backward kernels read them), X and the bf16 Q|K|V rows.
+// pooled sum) and, only when the caller asks for it (training: the backward kernels read it), the gathered rows X.
+// Q|K|V is never written: the backward recomputes it from X.
 //
 // One CTA per SM, 14 warps:
-//   warps 0-7   epilogue / softmax: two groups of four (one warp per TMEM lane quarter); group g owns heads h = g (mod 2)
+//   warps 0-7   epilogue / softmax: two groups of four (one warp per TMEM lane quarter); group g owns the head PAIRS
+//               (2j, 2j+1) with j = g (mod 2): a pair is 80 bytes of a context row, the granularity at which every warp
+//               hands its 32 rows to TMA stores (row-per-thread 8-byte global stores cost one LSU sector cycle per lane:
+//               ~190k cycles per tile, 7x the whole rest of the kernel, in the first version)
 //   warps 8-11  gather: table rows -> registers -> (dropout) -> the SWIZZLE_128B A-operand tile X (row-contiguous 16-byte
 //               pieces, 512 B of one row per warp instruction)
 //   warp  12    TMA producer: streams the per-head weight block W_h = [W_Q[h] | W_K[h] | W_V[h] | 0] (64 rows) through a ring
-//   warp  13    tcgen05 issuer (software pipelined over heads:  QKV(h) | S(h-1) | PV(h-2))
+//   warp  13    tcgen05 issuer: a small dependency-driven scheduler over three kinds of work -- Q|K|V of the next head
+//               (in head order, paced by the weight ring), scores and P.V of each group's next head (as soon as the
+//               operands that group produces are ready)
 //
 // A tile is 128 accumulator rows = 6 whole titles of 20 tokens (+8 dead rows), so the per-title attention is the block
 // diagonal of ONE 128 x 128 x 32 score MMA per head; each row reads only its own 20 score columns (a 64-column TMEM window per
@@ -41,13 +47,14 @@ int read_fused_device_error(int* out4) {
 namespace fused {
 
 constexpr int kThreads = 14 * 32;
-constexpr int kWStages = 6;
+constexpr int kWStages = 4;
 constexpr int kNB = 64;                 // weight rows of one head block: 3 * d_k padded to a multiple of 16
 constexpr int kNV = 48;                 // N of the P.V product: [V_hi (d_k) | pad to 24 | V_lo (d_k) | pad]
 constexpr int kVLo = 24;                // first column of V_lo inside the V tile / the context accumulator
 constexpr int kXChunk = 128 * 128;      // one 64-column k-chunk of the X tile
 constexpr int kWStage = kNB * 128;
 constexpr int kTile = 128 * 128;        // a [128][64] bf16 operand tile
+constexpr int kStageBuf = 32 * 80;      // one warp's staging tile of one context plane: 32 rows x (2 heads x 20 columns) bf16
 
 struct FwdParams {
     const long long* ids;
@@ -65,10 +72,14 @@ struct FwdParams {
     float scale;
     uint64_t seed_x, seed_c;
     __nv_bfloat16* X;     // [M][ldx] or null
-    __nv_bfloat16* QKV;   // [M][ld3] or null
     __nv_bfloat16* C_hi;  // [M][ldx]
     __nv_bfloat16* C_lo;  // [M][ldx]
     int* bad_flag;
+};
+// TMA maps of the two context planes (dense boxes): [plane][0/1 = head pair / odd last head + ones column][0/1 = 32-row box /
+// the shorter box of the last lane quarter]
+struct CtxMaps {
+    CUtensorMap m[2][2][2];
 };
 
 struct Smem {
@@ -76,6 +87,7 @@ struct Smem {
     uint8_t* w;      // kWStages stages of 8 KB
     uint8_t* qk;     // 2 tiles: Q in elements [0,32), K in [32,64) of every row
     uint8_t* v;      // 2 tiles: V_hi in elements [0,d_k), V_lo in [24, 24+d_k)
+    uint8_t* stage;  // 8 warps x 2 planes x kStageBuf
     float* bias;
     uint64_t* bars;
     uint32_t* tmem_slot;
@@ -85,7 +97,7 @@ enum Bar { X_FULL = 0, X_EMPTY = 1, W_FULL = 2, W_EMPTY = 2 + kWStages, QKV_FULL
            NUM_BARS = O_EMPTY + 2 };
 
 __host__ __device__ inline size_t smem_bytes(int heads, int kch) {
-    return 1024 + static_cast<size_t>(kch) * kXChunk + kWStages * kWStage + 4 * kTile + ((heads * kNB * 4 + 1023) & ~1023) + 1024;
+    return 1024 + static_cast<size_t>(kch) * kXChunk + kWStages * kWStage + 4 * kTile + 16 * kStageBuf + ((heads * kNB * 4 + 1023) & ~1023) + 1024;
 }
 
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
@@ -93,15 +105,22 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 
+// heads of group g inside a tile, in processing order: pairs (2j, 2j+1), j = g, g+2, ...
+__device__ __forceinline__ int first_head(int g) { return 2 * g; }
+__device__ __forceinline__ int next_head(int h, int H) { return (!(h & 1) && h + 1 < H) ? h + 1 : ((h >> 1) + 2) * 2; }
+__device__ __forceinline__ int group_of(int h) { return (h >> 1) & 1; }
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // epilogue / softmax role of one warp: TMEM lane quarter QD of group g
 // ---------------------------------------------------------------------------------------------------------------------------
 template <int T, int DK, int QD>
-__device__ __forceinline__ void epilogue_role(const FwdParams& p, const Smem& sm, uint32_t tmem_base, int g, int lane) {
+__device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps& maps, const Smem& sm, uint32_t tmem_base, int g,
+                                              int lane) {
     using G = Geo<T>;
     using W = Win<T, QD>;
-    static_assert(DK % 4 == 0 && DK <= kVLo && 3 * DK <= kNB && kVLo + DK <= kNV, "head width");
+    static_assert(DK % 4 == 0 && DK <= kVLo && 3 * DK <= kNB && kVLo + DK <= kNV && 2 * DK * 2 * 32 <= kStageBuf, "head width");
     constexpr int H2 = DK / 2;  // packed words per head row
+    constexpr int kBoxRows = (G::kRows - 32 * QD) < 32 ? (G::kRows - 32 * QD) : 32;  // used rows of this lane quarter
     const int r = 32 * QD + lane;
     int t = r / T;
     if (t > G::kTPT - 1) t = G::kTPT - 1;  // dead rows ride with the last title (their results are never stored)
@@ -112,15 +131,20 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const Smem& sm
     const uint32_t s_t = tmem_base + lane_base + 128 + g * 128;
     const uint32_t o_t = tmem_base + lane_base + 384 + g * 64;
     const int H = p.heads;
-    const int hg = g == 0 ? (H + 1) >> 1 : H >> 1;  // heads of this group per tile
     uint64_t* bars = sm.bars;
+    uint8_t* st_hi = sm.stage + (g * 4 + QD) * 2 * kStageBuf;  // this warp's staging tiles
+    uint8_t* st_lo = st_hi + kStageBuf;
+    const CUtensorMap* m_hi = &maps.m[0][0][kBoxRows < 32 ? 1 : 0];
+    const CUtensorMap* m_lo = &maps.m[1][0][kBoxRows < 32 ? 1 : 0];
+    const CUtensorMap* m_hi_last = &maps.m[0][1][kBoxRows < 32 ? 1 : 0];
+    const CUtensorMap* m_lo_last = &maps.m[1][1][kBoxRows < 32 ? 1 : 0];
+    const int tail_cols = p.ldx - p.d;  // ones column + zero pad behind the last head
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    uint32_t k = 0;  // heads this group has processed (barrier phase)
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const long long grow = static_cast<long long>(tile) * G::kRows + r;
-        const bool valid = r < G::kRows && grow < p.M;
-        for (int h = g; h < H; h += 2) {
-            const uint32_t par = static_cast<uint32_t>(it * hg + (h >> 1)) & 1u;
+        for (int h = first_head(g); h < H; h = next_head(h, H), ++k) {
+            const uint32_t par = k & 1u;
             // ---- (a) Q|K|V accumulator -> + bias -> bf16 operand tiles -------------------------------------------------------
             f_wait(&bars[QKV_FULL + g], par, 331);
             tc_fence_after();
@@ -130,7 +154,7 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const Smem& sm
                 tmem_ld32(acc_t + 32, acc + 32);
                 tmem_ld_wait();
                 tc_fence_before();
-                warp_arrive(&bars[QKV_EMPTY + g], lane);  // the issuer may start Q|K|V of head h + 2
+                warp_arrive(&bars[QKV_EMPTY + g], lane);  // the issuer may start Q|K|V of this group's next head
                 const float* b = sm.bias + h * kNB;
 #pragma unroll
                 for (int j = 0; j < 3 * DK; j += 4) {
@@ -147,22 +171,14 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const Smem& sm
                     const float2 f = unpack_bf16x2(vh[i]);
                     vl[i] = pack_bf16x2(v0 - f.x, v1 - f.y);
                 }
-                // the tiles of this group are free: step (c) of head h - 2 waited for its P.V MMA (and with it S(h - 2))
+                // the tiles of this group are free: step (c) of its previous head waited for that head's P.V MMA (and with it
+                // the score MMA)
                 sts_row20(qk_tile, r, 0, qw);
                 sts_row20(qk_tile, r, 32, kw);
                 sts_row20(v_tile, r, 0, vh);
                 sts_row20(v_tile, r, kVLo, vl);
                 fence_proxy_async();
                 warp_arrive(&bars[QK_READY + g], lane);
-                if (p.QKV != nullptr && valid) {  // bf16 Q|K|V rows for the backward kernels
-                    __nv_bfloat16* o = p.QKV + grow * p.ld3 + h * DK;
-#pragma unroll
-                    for (int i = 0; i < H2; i += 2) {
-                        stg64(o + 2 * i, qw[i], qw[i + 1]);
-                        stg64(o + p.d + 2 * i, kw[i], kw[i + 1]);
-                        stg64(o + 2 * p.d + 2 * i, vh[i], vh[i + 1]);
-                    }
-                }
             }
             // ---- (b) scores -> exp-softmax (multihead_self.py:16-20) -> P as the bf16 A operand in TMEM ---------------------
             f_wait(&bars[S_FULL + g], par, 332);
@@ -215,7 +231,7 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const Smem& sm
                 tc_fence_before();
                 warp_arrive(&bars[P_READY + g], lane);
             }
-            // ---- (c) context accumulator -> hi + lo parts -> dropout -> bf16 hi / lo planes ---------------------------------
+            // ---- (c) context accumulator -> hi + lo parts -> dropout -> staging tiles -> TMA store per head pair -------------
             f_wait(&bars[O_FULL + g], par, 333);
             tc_fence_after();
             {
@@ -225,36 +241,60 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const Smem& sm
                 tmem_ld_wait();
                 tc_fence_before();
                 warp_arrive(&bars[O_EMPTY + g], lane);
-                if (valid) {
-                    __nv_bfloat16* ch = p.C_hi + grow * p.ldx + h * DK;
-                    __nv_bfloat16* cl = p.C_lo + grow * p.ldx + h * DK;
+                const bool single = !(h & 1) && h + 1 >= H;  // odd head count: the last head travels with the ones column
+                const int pitch = single ? (DK + tail_cols) * 2 : 4 * DK;  // bytes per staging row
+                if (!(h & 1)) {  // first head of a pair: the TMA stores of the previous pair have read the staging tiles
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
+                uint8_t* row_hi = st_hi + lane * pitch + (h & 1) * (2 * DK);
+                uint8_t* row_lo = st_lo + lane * pitch + (h & 1) * (2 * DK);
 #pragma unroll
-                    for (int q4 = 0; q4 < DK; q4 += 4) {
-                        float c4[4];
+                for (int q4 = 0; q4 < DK; q4 += 4) {
+                    float c4[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) c4[j] = o[q4 + j] + o[kVLo + q4 + j];
-                        if (p.thresh != 0u) {
-                            float mk[4];
-                            drop4(p.seed_c, p.thresh, p.scale, grow, p.ldx, h * DK + q4, mk);
+                    for (int j = 0; j < 4; ++j) c4[j] = o[q4 + j] + o[kVLo + q4 + j];
+                    if (p.thresh != 0u) {
+                        float mk[4];
+                        drop4(p.seed_c, p.thresh, p.scale, grow, p.ldx, h * DK + q4, mk);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) c4[j] *= mk[j];
-                        }
-                        const uint32_t h0 = pack_bf16x2(c4[0], c4[1]), h1 = pack_bf16x2(c4[2], c4[3]);
-                        const float2 f0 = unpack_bf16x2(h0), f1 = unpack_bf16x2(h1);
-                        stg64(ch + q4, h0, h1);
-                        stg64(cl + q4, pack_bf16x2(c4[0] - f0.x, c4[1] - f0.y), pack_bf16x2(c4[2] - f1.x, c4[3] - f1.y));
+                        for (int j = 0; j < 4; ++j) c4[j] *= mk[j];
+                    }
+                    const uint32_t h0 = pack_bf16x2(c4[0], c4[1]), h1 = pack_bf16x2(c4[2], c4[3]);
+                    const float2 f0 = unpack_bf16x2(h0), f1 = unpack_bf16x2(h1);
+                    *reinterpret_cast<uint2*>(row_hi + 2 * q4) = make_uint2(h0, h1);
+                    *reinterpret_cast<uint2*>(row_lo + 2 * q4) =
+                        make_uint2(pack_bf16x2(c4[0] - f0.x, c4[1] - f0.y), pack_bf16x2(c4[2] - f1.x, c4[3] - f1.y));
+                }
+                if (single) {  // ones column (1.0 in the hi plane) + zero pad
+                    for (int j = 0; j < tail_cols; ++j) {
+                        reinterpret_cast<__nv_bfloat16*>(row_hi)[DK + j] = __float2bfloat16_rn(j == 0 ? 1.0f : 0.f);
+                        reinterpret_cast<__nv_bfloat16*>(row_lo)[DK + j] = __float2bfloat16_rn(0.f);
+                    }
+                }
+                if ((h & 1) || single) {  // pair complete: rows beyond M are clipped by the tensor map, dead rows by the box
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && kBoxRows > 0) {
+                        const int col0 = (h & ~1) * DK;
+                        const int row0 = static_cast<int>(static_cast<long long>(tile) * G::kRows + 32 * QD);
+                        tma_store_2d(single ? m_hi_last : m_hi, st_hi, col0, row0);
+                        tma_store_2d(single ? m_lo_last : m_lo, st_lo, col0, row0);
+                        bulk_commit();
                     }
                 }
             }
         }
     }
+    if (lane == 0) bulk_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------------
 template <int T, int DK>
-__global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const FwdParams p) {
+__global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW,
+                                                                      const __grid_constant__ CtxMaps maps, const FwdParams p) {
     using G = Geo<T>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -263,7 +303,8 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
     sm.w = sm.x + p.kch * kXChunk;
     sm.qk = sm.w + kWStages * kWStage;
     sm.v = sm.qk + 2 * kTile;
-    sm.bias = reinterpret_cast<float*>(sm.v + 2 * kTile);
+    sm.stage = sm.v + 2 * kTile;
+    sm.bias = reinterpret_cast<float*>(sm.stage + 16 * kStageBuf);
     sm.bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.bias) + ((p.heads * kNB * 4 + 1023) & ~1023));
     sm.tmem_slot = reinterpret_cast<uint32_t*>(sm.bars + NUM_BARS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
     // must be finite zeros for the whole kernel; nothing below ever writes them
     {
         uint4* z = reinterpret_cast<uint4*>(base);
-        const int n16 = static_cast<int>(reinterpret_cast<uint8_t*>(sm.bias) - base) >> 4;
+        const int n16 = static_cast<int>(sm.stage - base) >> 4;
         for (int i = threadIdx.x; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
         for (int i = threadIdx.x; i < H * kNB; i += kThreads) sm.bias[i] = p.bias[i];
     }
@@ -308,17 +349,18 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
     if (warp < 8) {
         const int g = warp >> 2;
         switch (warp & 3) {
-            case 0: epilogue_role<T, DK, 0>(p, sm, tmem_base, g, lane); break;
-            case 1: epilogue_role<T, DK, 1>(p, sm, tmem_base, g, lane); break;
-            case 2: epilogue_role<T, DK, 2>(p, sm, tmem_base, g, lane); break;
-            default: epilogue_role<T, DK, 3>(p, sm, tmem_base, g, lane); break;
+            case 0: epilogue_role<T, DK, 0>(p, maps, sm, tmem_base, g, lane); break;
+            case 1: epilogue_role<T, DK, 1>(p, maps, sm, tmem_base, g, lane); break;
+            case 2: epilogue_role<T, DK, 2>(p, maps, sm, tmem_base, g, lane); break;
+            default: epilogue_role<T, DK, 3>(p, maps, sm, tmem_base, g, lane); break;
         }
     } else if (warp < 12) {
-        // ===================== gather: table rows -> (dropout) -> X tile (+ the X / ones-column rows in HBM) =====================
+        // ===================== gather: table rows -> (dropout) -> X tile (+ the X rows in HBM) =====================
         const int gw = warp - 8;
         const int chunks = p.ldx >> 3;                 // 16-byte pieces of a table row
         const int smem_pieces = p.kch * 8;             // pieces that exist in the X tile
         const uint32_t x_s = smem_u32(sm.x);
+        const bool tail_here = (H & 1) == 0;           // even head count: nobody else writes the ones column of the context
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             f_wait(&bars[X_EMPTY], static_cast<uint32_t>(it & 1) ^ 1u, 321);
@@ -370,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
                             reinterpret_cast<uint4*>(p.X)[gr * chunks + pc] = make_uint4(w[0], w[1], w[2], w[3]);
                         }
                     }
-                    if (lane < p.ldx - p.d) {  // ones column + zero tail of the context planes
+                    if (tail_here && lane < p.ldx - p.d) {  // ones column + zero tail of the context planes
                         p.C_hi[gr * p.ldx + p.d + lane] = __float2bfloat16_rn(lane == 0 ? 1.0f : 0.f);
                         p.C_lo[gr * p.ldx + p.d + lane] = __float2bfloat16_rn(0.f);
                     }
@@ -396,77 +438,100 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
                 }
         }
     } else {
-        // ===================== tcgen05 issuer =====================
+        // ===================== tcgen05 issuer: dependency-driven over Q|K|V (head order) and each group's S / P.V =====================
         const uint32_t idesc_qkv = make_idesc_bf16(128, kNB, 0, 0);
         const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
         const uint32_t idesc_pv = make_idesc_bf16(128, kNV, 0, 1);
         constexpr int KS_S = (DK + 15) / 16;  // k-steps of the score product (Q / K are zero padded to 32 elements)
         const uint32_t x_s = smem_u32(sm.x), w_s = smem_u32(sm.w), qk_s = smem_u32(sm.qk), v_s = smem_u32(sm.v);
-        const int hg0 = (H + 1) >> 1, hg1 = H >> 1;
+        auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {  // warp-uniform non-blocking test
+            return __shfl_sync(0xffffffffu, mbar_test_wait(bar, parity) ? 1 : 0, 0) != 0;
+        };
         int st = 0;
         uint32_t ph = 0;
+        uint32_t cq0 = 0u, cq1 = 0u;                 // Q|K|V projections issued per group (barrier phases); scalars: a run-time
+        uint32_t cs[2] = {0u, 0u}, cp[2] = {0u, 0u};  // indexed array would live in local memory (cs / cp are indexed by the unrolled g)
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             f_wait(&bars[X_FULL], static_cast<uint32_t>(it & 1), 311);
             tc_fence_after();
-            for (int step = 0; step < H + 2; ++step) {
-                if (step < H) {  // ---- Q|K|V of head `step`
-                    const int h = step, g = h & 1;
-                    const uint32_t par = static_cast<uint32_t>(it * (g ? hg1 : hg0) + (h >> 1)) & 1u;
-                    f_wait(&bars[QKV_EMPTY + g], par ^ 1u, 312);
-                    tc_fence_after();
-                    const uint32_t d_t = tmem_base + g * kNB;
-                    for (int kc = 0; kc < p.kch; ++kc) {
-                        f_wait(&bars[W_FULL + st], ph, 313);
+            int q_next = 0;                                  // next head to project
+            int s_next[2] = {first_head(0), first_head(1)};  // per group: next head whose scores / P.V are due
+            int p_next[2] = {first_head(0), first_head(1)};
+            uint64_t t_idle = 0;
+            while (p_next[0] < H || p_next[1] < H) {
+                bool progressed = false;
+                if (q_next < H) {  // ---- Q|K|V of head q_next
+                    const int h = q_next, g = group_of(h);
+                    if (ready(&bars[QKV_EMPTY + g], ((g ? cq1 : cq0) & 1u) ^ 1u)) {
                         tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t da = make_sw128_desc(x_s + kc * kXChunk, 0, 1024);
-                            const uint64_t db = make_sw128_desc(w_s + st * kWStage, 0, 1024);
-                            const int nk = (kc == p.kch - 1) ? p.ksteps_last : 4;
+                        const uint32_t d_t = tmem_base + g * kNB;
+                        for (int kc = 0; kc < p.kch; ++kc) {
+                            f_wait(&bars[W_FULL + st], ph, 313);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t da = make_sw128_desc(x_s + kc * kXChunk, 0, 1024);
+                                const uint64_t db = make_sw128_desc(w_s + st * kWStage, 0, 1024);
+                                const int nk = (kc == p.kch - 1) ? p.ksteps_last : 4;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (k < nk) umma_bf16(d_t, da + 2 * k, db + 2 * k, idesc_qkv, (kc | k) ? 1u : 0u);
-                            umma_commit(&bars[W_EMPTY + st]);
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < nk) umma_bf16(d_t, da + 2 * k, db + 2 * k, idesc_qkv, (kc | k) ? 1u : 0u);
+                                umma_commit(&bars[W_EMPTY + st]);
+                            }
+                            __syncwarp();
+                            if (++st == kWStages) { st = 0; ph ^= 1u; }
+                        }
+                        if (elect_one()) {
+                            umma_commit(&bars[QKV_FULL + g]);
+                            if (h == H - 1) umma_commit(&bars[X_EMPTY]);  // the gather warps may refill X for the next tile
                         }
                         __syncwarp();
-                        if (++st == kWStages) { st = 0; ph ^= 1u; }
+                        if (g) ++cq1; else ++cq0;
+                        ++q_next;
+                        progressed = true;
                     }
-                    if (elect_one()) {
-                        umma_commit(&bars[QKV_FULL + g]);
-                        if (h == H - 1) umma_commit(&bars[X_EMPTY]);  // the gather warps may refill X for the next tile
-                    }
-                    __syncwarp();
                 }
-                if (step >= 1 && step <= H) {  // ---- scores of head `step - 1`
-                    const int h = step - 1, g = h & 1;
-                    const uint32_t par = static_cast<uint32_t>(it * (g ? hg1 : hg0) + (h >> 1)) & 1u;
-                    f_wait(&bars[QK_READY + g], par, 314);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t da = make_sw128_desc(qk_s + g * kTile, 0, 1024);
-                        const uint64_t db = make_sw128_desc(qk_s + g * kTile + 64, 0, 1024);  // K lives in elements [32, 64)
 #pragma unroll
-                        for (int k = 0; k < KS_S; ++k)
-                            umma_bf16(tmem_base + 128 + g * 128, da + 2 * k, db + 2 * k, idesc_s, k ? 1u : 0u);
-                        umma_commit(&bars[S_FULL + g]);
+                for (int g = 0; g < 2; ++g) {
+                    // ---- scores of this group's next head (its Q|K|V MMAs were issued: s_next < q_next in head order)
+                    if (s_next[g] < H && s_next[g] < q_next && ready(&bars[QK_READY + g], cs[g] & 1u)) {
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t da = make_sw128_desc(qk_s + g * kTile, 0, 1024);
+                            const uint64_t db = make_sw128_desc(qk_s + g * kTile + 64, 0, 1024);  // K lives in elements [32, 64)
+#pragma unroll
+                            for (int k = 0; k < KS_S; ++k)
+                                umma_bf16(tmem_base + 128 + g * 128, da + 2 * k, db + 2 * k, idesc_s, k ? 1u : 0u);
+                            umma_commit(&bars[S_FULL + g]);
+                        }
+                        __syncwarp();
+                        ++cs[g];
+                        s_next[g] = next_head(s_next[g], H);
+                        progressed = true;
                     }
-                    __syncwarp();
+                    // ---- P.V of this group's next head: A = P (bf16, TMEM), B = [V_hi | V_lo] (MN-major)
+                    if (p_next[g] < H && cp[g] < cs[g] && ready(&bars[P_READY + g], cp[g] & 1u) &&
+                        ready(&bars[O_EMPTY + g], (cp[g] & 1u) ^ 1u)) {
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t db = make_sw128_desc(v_s + g * kTile, 8192, 1024);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)  // 16 key rows per k-step: +2048 bytes in B, +8 packed columns in A
+                                umma_bf16_ts(tmem_base + 384 + g * 64, tmem_base + 128 + g * 128 + 8 * k, db + 128 * k, idesc_pv,
+                                             k ? 1u : 0u);
+                            umma_commit(&bars[O_FULL + g]);
+                        }
+                        __syncwarp();
+                        ++cp[g];
+                        p_next[g] = next_head(p_next[g], H);
+                        progressed = true;
+                    }
                 }
-                if (step >= 2) {  // ---- P.V of head `step - 2`: A = P (bf16, TMEM), B = [V_hi | V_lo] (MN-major)
-                    const int h = step - 2, g = h & 1;
-                    const uint32_t par = static_cast<uint32_t>(it * (g ? hg1 : hg0) + (h >> 1)) & 1u;
-                    f_wait(&bars[P_READY + g], par, 315);
-                    f_wait(&bars[O_EMPTY + g], par ^ 1u, 316);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t db = make_sw128_desc(v_s + g * kTile, 8192, 1024);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)  // 16 key rows per k-step: +2048 bytes in B, +8 packed columns in A
-                            umma_bf16_ts(tmem_base + 384 + g * 64, tmem_base + 128 + g * 128 + 8 * k, db + 128 * k, idesc_pv,
-                                         k ? 1u : 0u);
-                        umma_commit(&bars[O_FULL + g]);
-                    }
-                    __syncwarp();
+                if (progressed) {
+                    t_idle = 0;
+                } else {  // nothing was ready: bounded like every other wait of this kernel
+                    if (t_idle == 0) t_idle = globaltimer_ns();
+                    else if (globaltimer_ns() - t_idle > 4000000000ull) f_timeout(317, static_cast<uint32_t>(q_next));
                 }
             }
         }
@@ -486,15 +551,15 @@ int mhsa_fused_supported(int T, int d, int heads) {
     return (T == 20 && heads >= 1 && heads <= 16 && d == heads * 20 && d <= 320) ? 1 : 0;
 }
 
-int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* table, int V, int d, int heads, int ldx, int ld3,
-                   const void* w_heads, const float* b_heads, DropoutCfg drop_x, DropoutCfg drop_c, void* X, void* QKV, void* C_hi,
-                   void* C_lo, int* bad_id_flag, cudaStream_t stream) {
+int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* table, int V, int d, int heads, int ldx,
+                   const void* w_heads, const float* b_heads, DropoutCfg drop_x, DropoutCfg drop_c, void* X, void* C_hi, void* C_lo,
+                   int* bad_id_flag, cudaStream_t stream) {
     using namespace fused;
     NR_REQUIRE(mhsa_fused_supported(T, d, heads), "mhsa_fused_fwd: unsupported shape T=%d d=%d heads=%d", T, d, heads);
-    NR_REQUIRE(ldx % 8 == 0 && ldx >= d + 1 && ldx <= 512 && (QKV == nullptr || (ld3 % 4 == 0 && ld3 >= 3 * d)),
-               "mhsa_fused_fwd: pitches ldx=%d ld3=%d", ldx, ld3);
+    NR_REQUIRE(ldx % 8 == 0 && ldx >= d + 1 && ldx <= 512, "mhsa_fused_fwd: pitch ldx=%d", ldx);
+    NR_REQUIRE(n_seq * T < (1ll << 31), "mhsa_fused_fwd: too many tokens");
     if (n_seq == 0) return 0;
-    constexpr int TT = 20;
+    constexpr int TT = 20, DK = 20;
     FwdParams p;
     memset(&p, 0, sizeof(p));
     p.ids = ids;
@@ -507,7 +572,6 @@ int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* tab
     p.ksteps_last = ceil_div(d - (p.kch - 1) * 64, 16);
     p.d = d;
     p.ldx = ldx;
-    p.ld3 = ld3;
     p.bias = b_heads;
     p.sc = 1.4426950408889634f / sqrtf(static_cast<float>(d / heads));
     NR_REQUIRE(drop_x.p == drop_c.p, "mhsa_fused_fwd: one dropout probability for both sites");
@@ -516,22 +580,34 @@ int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* tab
     p.seed_x = drop_x.seed;
     p.seed_c = drop_c.seed;
     p.X = static_cast<__nv_bfloat16*>(X);
-    p.QKV = static_cast<__nv_bfloat16*>(QKV);
     p.C_hi = static_cast<__nv_bfloat16*>(C_hi);
     p.C_lo = static_cast<__nv_bfloat16*>(C_lo);
     p.bad_flag = bad_id_flag;
     CUtensorMap tmW;
     NR_PROPAGATE(make_tmap_bf16_2d(&tmW, w_heads, static_cast<int64_t>(heads) * kNB, d, ldx, 64, kNB));
+    // context planes: dense boxes of one head pair (or the odd last head + ones column) x the rows of one lane quarter
+    CtxMaps maps;
+    const int last_rows = Geo<TT>::kRows - 96;  // used rows of the last lane quarter
+    const int single_cols = DK + (ldx - d);
+    NR_REQUIRE((heads & 1) == 0 || (single_cols * 2) % 16 == 0, "mhsa_fused_fwd: odd head count needs (d_k + ldx - d) * 2 %% 16 == 0");
+    for (int pl = 0; pl < 2; ++pl) {
+        void* base = pl == 0 ? C_hi : C_lo;
+        for (int rb = 0; rb < 2; ++rb) {
+            const int rows = rb == 0 ? 32 : (last_rows > 0 ? last_rows : 32);
+            NR_PROPAGATE(make_tmap_bf16_2d(&maps.m[pl][0][rb], base, p.M, ldx, ldx, 2 * DK, rows, 0));
+            NR_PROPAGATE(make_tmap_bf16_2d(&maps.m[pl][1][rb], base, p.M, ldx, ldx, (heads & 1) ? single_cols : 2 * DK, rows, 0));
+        }
+    }
     const size_t smem = smem_bytes(heads, p.kch);
     NR_REQUIRE(smem <= 232448, "mhsa_fused_fwd: %zu bytes of shared memory", smem);
     static bool attr_set = false;
     if (!attr_set) {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_fused_fwd_kernel<TT, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_fused_fwd_kernel<TT, DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
     }
     const int grid = std::min(p.num_tiles, num_sms());
     ProfScope ps("mhsa_fused_fwd", static_cast<int>(n_seq), T, d, stream);
-    mhsa_fused_fwd_kernel<TT, 20><<<grid, kThreads, smem, stream>>>(tmW, p);
+    mhsa_fused_fwd_kernel<TT, DK><<<grid, kThreads, smem, stream>>>(tmW, maps, p);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -170,7 +170,9 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
     NR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
     NR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16B aligned", base);
     NR_REQUIRE((ld_elems * 2) % 16 == 0, "TMA row pitch %lld elements is not a multiple of 16 bytes", (long long)ld_elems);
-    NR_REQUIRE(box_cols * 2 <= swizzle_bytes && (swizzle_bytes == 128 || swizzle_bytes == 64) && box_rows <= 256 && box_rows >= 1,
+    NR_REQUIRE(((swizzle_bytes == 128 || swizzle_bytes == 64) ? box_cols * 2 <= swizzle_bytes
+                                                               : (swizzle_bytes == 0 && (box_cols * 2) % 16 == 0 && box_cols <= 256)) &&
+                   box_rows <= 256 && box_rows >= 1,
                "bad TMA box %d x %d (swizzle %d)", box_cols, box_rows, swizzle_bytes);
     NR_REQUIRE(rows >= 1 && cols >= 1, "empty tensor for TMA (%lld x %lld)", (long long)rows, (long long)cols);
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -178,7 +180,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
     cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%dx%d)",
@@ -578,16 +581,17 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
 }
 
 int gemm_scatter_emb(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
-                     int rows_per_tile, const long long* ids, float* demb, int D, RowMapCfg rm, DropoutCfg drop,
+                     int rows_per_tile, const long long* ids, float* demb, int V, int D, RowMapCfg rm, DropoutCfg drop,
                      int drop_ld, cudaStream_t stream) {
     if (M == 0) return 0;
-    NR_REQUIRE(N == D && D % 4 == 0, "scatter_emb: N=%d D=%d", N, D);
+    NR_REQUIRE(N == D && D % 4 == 0 && V >= 1, "scatter_emb: N=%d D=%d V=%d", N, D, V);
     GemmNTPlan plan;
     NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0,
                               EpiScatter::kScratchBytes, 0));
     EpiScatter e;
     e.ids = ids;
     e.demb = demb;
+    e.V = V;
     e.D = D;
     e.rm = to_rm(rm);
     e.drop = to_drop(drop);

@@ -91,6 +91,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a mis-programmed pipeline traps after ~4 s instead of hanging the GPU.
 #ifdef NR_OWNS_WATCHDOG
 __device__ __noinline__ void mbar_timeout(int code, uint32_t aux) {
@@ -374,7 +386,8 @@ __device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t group)
 // host: TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency)
 // ----------------------------------------------------------------------------------------------
 // 2-D bf16 tensor [rows][cols] with row pitch ld (elements), box = [box_cols(<=64) x box_rows];
-// swizzle_bytes = 128 (operand tiles, box_cols <= 64) or 64 (epilogue store tiles, box_cols <= 32).
+// swizzle_bytes = 128 (operand tiles, box_cols <= 64), 64 (epilogue store tiles, box_cols <= 32) or 0 (dense row-major
+// box, rows of box_cols * 2 bytes, a multiple of 16).
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_cols,
                       int box_rows, int swizzle_bytes = 128);
 

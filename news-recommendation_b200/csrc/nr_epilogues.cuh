@@ -548,6 +548,8 @@ struct EpiScatter {
     static constexpr int kScratchBytes = 16;
     const long long* ids;  // [rows] token ids (row-mapped through rm for the padded CNN layout)
     float* demb;           // [V][D] fp32
+    int V;                 // rows of demb: ids outside [1, V) contribute nothing (the forward gather flags them, the reference
+                           // raises IndexError; an unchecked id here would be an out-of-bounds atomic into a neighbouring gradient)
     int D;
     RowMap rm;             // maps the GEMM row to the token index in ids
     Dropout drop;
@@ -561,7 +563,8 @@ struct EpiScatter {
         long long trow;
         int t;
         const bool v = rm.map(c.grow, trow, t) && c.valid;
-        const long long id = v ? ids[trow] : 0;
+        long long id = v ? ids[trow] : 0;
+        if (id < 0 || id >= V) id = 0;  // out of range: skipped like the padding row
         float* dst = demb + static_cast<size_t>(id) * D;
         epi_chunks(
             acc, c, [](int) {},

@@ -40,7 +40,7 @@ int gemm_pool_dinput(const void* dpre, int M, int ld_dpre, int q, const void* Wa
 
 // dEmb[ids[row]] += A . W^T  (embedding gradient; padding row 0 skipped) [* dropout of the gathered rows]
 int gemm_scatter_emb(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
-                     int rows_per_tile, const long long* ids, float* demb, int D, RowMapCfg rm, DropoutCfg drop,
+                     int rows_per_tile, const long long* ids, float* demb, int V, int D, RowMapCfg rm, DropoutCfg drop,
                      int drop_ld, cudaStream_t stream);
 
 // D[Ma x Nb] += A[:, :Ma]^T . B[rows + shift, b_col0 : b_col0 + Nb]   (fp32 accumulate into D, pitch ldd)
@@ -75,15 +75,15 @@ int relu_bwd_to_bf16(const float* dy, const float* relu_out, long long n, int N,
 // fp32 embedding lookup / scatter-add (padding row 0: value read as-is, gradient skipped)
 int embedding_f32_fwd(const long long* ids, long long n, const float* table, int V, int D, float* out, int* bad_id_flag,
                       cudaStream_t stream);
-int embedding_f32_bwd(const long long* ids, long long n, const float* dout, int D, float* dtable, cudaStream_t stream);
+int embedding_f32_bwd(const long long* ids, long long n, const float* dout, int V, int D, float* dtable, cudaStream_t stream);
 
 // ---- fused NRMS news-encoder front end (fused_fwd.cu): ids -> gather -> Q|K|V -> attention -> context hi/lo planes -----
 // w_heads bf16 [heads*64][ldx]: per head the rows W_Q[h] | W_K[h] | W_V[h] | zero rows up to 64; b_heads fp32 [heads*64].
-// X / QKV may be null (inference): they are only written for the backward kernels.
+// X may be null (inference): it is only written for the backward kernels.  Q|K|V never reaches HBM.
 int mhsa_fused_supported(int T, int d, int heads);
-int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* table, int V, int d, int heads, int ldx, int ld3,
-                   const void* w_heads, const float* b_heads, DropoutCfg drop_x, DropoutCfg drop_c, void* X, void* QKV, void* C_hi,
-                   void* C_lo, int* bad_id_flag, cudaStream_t stream);
+int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* table, int V, int d, int heads, int ldx,
+                   const void* w_heads, const float* b_heads, DropoutCfg drop_x, DropoutCfg drop_c, void* X, void* C_hi, void* C_lo,
+                   int* bad_id_flag, cudaStream_t stream);
 int read_fused_device_error(int* out4);
 
 int num_sms();

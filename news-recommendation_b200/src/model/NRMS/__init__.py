@@ -60,6 +60,4 @@ class NRMS(torch.nn.Module):
 
     def check_ids(self):
         """Raises IndexError (like the reference's CPU embedding) if any token id was out of range.  Syncs."""
-        f = self.news_encoder._bad_flag
-        if f is not None and int(f.item()) != 0:
-            raise IndexError("token id out of range for word_embedding")
+        self.news_encoder._flag.raise_if_set("word_embedding")

@@ -6,6 +6,7 @@ import torch.nn as nn
 from model.general.attention.additive import AdditiveAttention
 from model.general.attention.multihead_self import MultiHeadSelfAttention
 from newsrec_b200 import require_cuda
+from newsrec_b200.guard import BadIdFlag
 from newsrec_b200.ops import MhsaPoolEncoderFn, OperandCache
 
 
@@ -20,12 +21,11 @@ class NewsEncoder(nn.Module):
         self.multihead_self_attention = MultiHeadSelfAttention(config.word_embedding_dim, config.num_attention_heads)
         self.additive_attention = AdditiveAttention(config.query_vector_dim, config.word_embedding_dim)
         self._cache = OperandCache()
-        self._bad_flag = None
+        self._flag = BadIdFlag()
 
     def bad_id_flag(self, dev):
-        if self._bad_flag is None or self._bad_flag.device != dev:
-            self._bad_flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        return self._bad_flag
+        """Device int the gather sets for an id outside [0, num_words); polled without a sync on every call (guard.py)."""
+        return self._flag.get(dev)
 
     def encode_ids(self, ids):
         """ids: int64 (n_titles, num_words_title) on the device -> (n_titles, word_embedding_dim)."""

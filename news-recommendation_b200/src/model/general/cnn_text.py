@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from newsrec_b200 import require_cuda
+from newsrec_b200.guard import BadIdFlag  # noqa: F401  (re-exported: the CNN model packages import it from here)
 from newsrec_b200.ops import OperandCache
 from newsrec_b200.ops_cnn import CnnPoolEncoderFn
 
@@ -10,22 +11,6 @@ from newsrec_b200.ops_cnn import CnnPoolEncoderFn
 def make_title_cnn(num_filters, window_size, word_embedding_dim):
     """Parameter container with the reference's shapes: weight (F, 1, window, d), bias (F)."""
     return nn.Conv2d(1, num_filters, (window_size, word_embedding_dim), padding=(int((window_size - 1) / 2), 0))
-
-
-class BadIdFlag:
-    """Device-side 'token id out of range' flag shared by the gather kernels of one encoder."""
-
-    def __init__(self):
-        self._t = None
-
-    def get(self, dev):
-        if self._t is None or self._t.device != dev:
-            self._t = torch.zeros(1, dtype=torch.int32, device=dev)
-        return self._t
-
-    def raise_if_set(self, what="word_embedding"):
-        if self._t is not None and int(self._t.item()) != 0:
-            raise IndexError(f"id out of range for {what}")
 
 
 def cnn_text_encode(ids, word_embedding, cnn, attention, p_drop, cache: OperandCache, prefix, flag: BadIdFlag):

@@ -38,6 +38,7 @@ class MhsaEncoderBwdArgs(C.Structure):
         ("X_bf16", _vp), ("QKV_bf16", _vp), ("C_bf16", _vp), ("w", _vp), ("dout", _vp),
         ("dWqkv_ext", _vp), ("dWa_ext", _vp), ("dqv", _vp), ("demb", _vp), ("ddense", _vp),
         ("workspace", _vp), ("workspace_bytes", _ll),
+        ("wqkv_bf16", _vp), ("bqkv", _vp),
     ]
 
 
@@ -123,9 +124,9 @@ SIGNATURES = {
     "nr_linear_rows_fwd": (_i, [_vp, _ll, _i, _ll, _ll, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp]),
     "nr_linear_rows_bwd": (_i, [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "nr_embedding_f32_fwd": (_i, [_vp, _ll, _vp, _i, _i, _vp, _vp, _vp]),
-    "nr_embedding_f32_bwd": (_i, [_vp, _ll, _vp, _i, _vp, _vp]),
+    "nr_embedding_f32_bwd": (_i, [_vp, _ll, _vp, _i, _i, _vp, _vp]),
     "nr_element_encoder_fwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "nr_element_encoder_bwd": (_i, [_vp, _ll, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "nr_element_encoder_bwd": (_i, [_vp, _ll, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "nr_gru_fwd": (_i, [C.POINTER(GruFwdArgs), _vp]),
     "nr_gru_bwd_workspace": (_ll, [_i, _i, _i, _i]),
     "nr_gru_bwd": (_i, [C.POINTER(GruBwdArgs), _vp]),

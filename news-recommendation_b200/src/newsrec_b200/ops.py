@@ -151,8 +151,9 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         # the fused front end (gather -> Q|K|V -> attention in one kernel) covers the reference's news level shapes
         fused = ids is not None and os.environ.get("NEWSREC_NO_FUSED") is None and bool(lib.nr_mhsa_fused_supported(T, d, heads))
         X = QKV = C_lo = None
-        if need_bwd or not fused:  # X / Q|K|V only exist in HBM when a backward pass (or the unfused sequence) reads them
+        if need_bwd or not fused:  # X only exists in HBM when a backward pass (or the unfused sequence) reads it
             X = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
+        if not fused:              # the fused front end keeps Q|K|V on chip; its backward recomputes it from X
             QKV = torch.empty((n_tok, ld3), dtype=torch.bfloat16, device=dev)
         Cx = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
         w = torch.empty((n_tok,), dtype=torch.float32, device=dev)
@@ -170,7 +171,8 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         a.bad_id_flag = _p(bad_flag)
         check(lib.nr_mhsa_encoder_fwd(C.byref(a), _stream()), "nr_mhsa_encoder_fwd")
         if need_bwd:
-            ctx.save_for_backward(X, QKV, Cx, w, ids if ids is not None else torch.empty(0, device=dev))
+            ctx.save_for_backward(X, QKV if QKV is not None else torch.empty(0, device=dev), Cx, w,
+                                  ids if ids is not None else torch.empty(0, device=dev))
         ctx.meta = dict(n_seq=n_seq, T=T, d=d, q=q, heads=heads, p_drop=float(p_drop), seed=seed, ops=ops,
                         has_ids=ids is not None, V=emb_w.shape[0] if ids is not None else 0,
                         dense_shape=None if dense is None else tuple(dense.shape),
@@ -220,7 +222,8 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         a.V = m["V"]
         a.wqkvT_bf16, a.wa_bf16, a.waT_bf16, a.ba, a.qv = _p(ops["wqkvT"]), _p(ops["wa"]), _p(ops["waT"]), _p(ops["ba"]), _p(ops["qv"])
         a.p_drop, a.seed = m["p_drop"], m["seed"]
-        a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.dout = _p(X), _p(QKV), _p(Cx), _p(w), _p(dout)
+        a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.dout = _p(X), (_p(QKV) if QKV.numel() else None), _p(Cx), _p(w), _p(dout)
+        a.wqkv_bf16, a.bqkv = _p(ops["wqkv"]), _p(ops["bqkv"])
         a.dWqkv_ext, a.dWa_ext, a.dqv = _p(dWqkv), _p(dWa), _p(dqv)
         a.demb, a.ddense = _p(demb), _p(ddense)
         a.workspace, a.workspace_bytes = _p(ws), ws_bytes

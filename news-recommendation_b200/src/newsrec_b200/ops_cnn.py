@@ -146,7 +146,7 @@ class EmbeddingF32Fn(torch.autograd.Function):
         V, D = ctx.shape
         dout = dout.contiguous().float()
         dt = torch.zeros((V, D), dtype=torch.float32, device=dout.device)
-        check(lib.nr_embedding_f32_bwd(_p(ids), ids.numel(), _p(dout), D, _p(dt), _stream()), "nr_embedding_f32_bwd")
+        check(lib.nr_embedding_f32_bwd(_p(ids), ids.numel(), _p(dout), V, D, _p(dt), _stream()), "nr_embedding_f32_bwd")
         return None, dt, None
 
 
@@ -186,5 +186,5 @@ class ElementEncoderFn(torch.autograd.Function):
         dW = torch.zeros((Fn, lde), dtype=torch.float32, device=dev)
         dt = torch.zeros((V, E), dtype=torch.float32, device=dev)
         check(lib.nr_element_encoder_bwd(_p(ids), n, _p(dout), _p(out), Fn, _p(dY), ldf, _p(Eb), E, lde, _p(ops["wT"]), _p(dW),
-                                         _p(dt), _stream()), "nr_element_encoder_bwd")
+                                         _p(dt), V, _stream()), "nr_element_encoder_bwd")
         return None, dt, dW[:, :E].contiguous(), dW[:, E].contiguous(), None, None, None

@@ -47,7 +47,9 @@ def oracle_forward(case, g, p, contract=O.EXACT):
     """Runs the oracle on a golden case's inputs.  Returns (logits, topic_loss or None)."""
     cand_t, clicked_t = t(g, "cand_title"), t(g, "clicked_title")
     if case == "nrms":
-        return O.nrms_forward(cand_t, clicked_t, p, 15, contract), None
+        # the news level runs through the fused front end (V / context as hi/lo pairs) whenever a bf16 contract is asked for
+        c_news = O.BF16_FUSED if contract.bf16 else contract
+        return O.nrms_forward(cand_t, clicked_t, p, 15, contract, c_news=c_news), None
     if case.startswith("naml"):
         cand = dict(title=cand_t, abstract=t(g, "cand_abstract"), category=t(g, "cand_category"),
                     subcategory=t(g, "cand_subcategory"))

@@ -274,7 +274,7 @@ def check_nrms_random(B=8, Cn=5, H=50, T=20, V=500, seed=5):
     model, sd = nrms_model_and_params(V, seed)
     model.eval()
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16)
+    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16, c_news=O.BF16_FUSED)
     O.click_loss(logits_o).backward()
     with torch.no_grad():
         logits_x = O.nrms_forward(cand_t, clicked_t, {k: v.detach() for k, v in p.items()}, 15, O.EXACT)
@@ -357,7 +357,7 @@ def check_nrms_eval_api(V=300, seed=9):
     titles = O.synth_titles(40, 20, V, 3)
     with torch.no_grad():
         nv = model.get_news_vector({"title": titles, "id": ["N%d" % i for i in range(40)]})
-        nv_o = O.nrms_news_encoder(titles, p, 15, O.BF16)
+        nv_o = O.nrms_news_encoder(titles, p, 15, O.BF16_FUSED)
         B, H = 4, 10
         stacked = torch.stack([nv[i * 4:(i + 1) * 4] for i in range(H)], dim=0).transpose(0, 1)  # (B,H,d) non-contiguous
         uv = model.get_user_vector(stacked)
