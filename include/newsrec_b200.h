@@ -40,6 +40,10 @@ void nr_debug_set_simt_gemm(int on);
  * for A data, [2] MMA issuer waiting for a free TMEM accumulator, [3] epilogue waiting for a finished accumulator,
  * [4] epilogue body, [5] kernel, [6] tiles, [7] MMA issue loops, [8] tcgen05.commit.  Null (default) switches the counters off. */
 void nr_debug_set_gemm_timing(void* dev_buf, int slots);
+/* TUNING ONLY (tools/fused_timing.py): dev_buf holds 148 x 32 int64; every fused front-end launch after this call writes,
+ * per CTA, cycle counters of its warp roles (epilogue groups [0..6], [8..14]; gather [16,17]; weight producer [20];
+ * tcgen05 issuer [24..29]).  Null (default) switches the counters off. */
+void nr_debug_set_fused_timing(void* dev_buf);
 /* Live per-kernel timing for bench.py: CUDA events on the launching stream around every kernel of this
  * library.  nr_profile_report writes JSON {"<context>/<op>[shape]": [launches, total_ms], ...}, returns its
  * length (or -1 if cap is too small) and clears the records.  Off by default. */

@@ -75,6 +75,7 @@ struct FwdParams {
     __nv_bfloat16* C_hi;  // [M][ldx]
     __nv_bfloat16* C_lo;  // [M][ldx]
     int* bad_flag;
+    long long* timing;    // tuning only (nr_debug_set_fused_timing): per CTA 32 cycle counters, see the roles
 };
 // TMA maps of the two context planes (dense boxes): [plane][0/1 = head pair / odd last head + ones column][0/1 = 32-row box /
 // the shorter box of the last lane quarter]
@@ -140,6 +141,19 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps&
     const CUtensorMap* m_lo_last = &maps.m[1][1][kBoxRows < 32 ? 1 : 0];
     const int tail_cols = p.ldx - p.d;  // ones column + zero pad behind the last head
 
+    // tuning counters (quarter 0 of each group): [g*8 + 0] wait Q|K|V, [1] step a, [2] wait scores, [3] step b, [4] wait context,
+    // [5] step c, [6] whole role
+    long long* tmr = (p.timing != nullptr && QD == 0 && lane == 0) ? p.timing + blockIdx.x * 32 + g * 8 : nullptr;
+    long long tw[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_role = tmr != nullptr ? clock64() : 0;
+    long long t_mark = t_role;
+    auto lap = [&](int slot) {
+        if (tmr != nullptr) {
+            const long long t = clock64();
+            tw[slot] += t - t_mark;
+            t_mark = t;
+        }
+    };
     uint32_t k = 0;  // heads this group has processed (barrier phase)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const long long grow = static_cast<long long>(tile) * G::kRows + r;
@@ -148,6 +162,7 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps&
             // ---- (a) Q|K|V accumulator -> + bias -> bf16 operand tiles -------------------------------------------------------
             f_wait(&bars[QKV_FULL + g], par, 331);
             tc_fence_after();
+            lap(0);
             {
                 float acc[kNB];
                 tmem_ld32(acc_t, acc);
@@ -181,8 +196,10 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps&
                 warp_arrive(&bars[QK_READY + g], lane);
             }
             // ---- (b) scores -> exp-softmax (multihead_self.py:16-20) -> P as the bf16 A operand in TMEM ---------------------
+            lap(1);
             f_wait(&bars[S_FULL + g], par, 332);
             tc_fence_after();
+            lap(2);
             {
                 float x[T];
                 {
@@ -232,8 +249,10 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps&
                 warp_arrive(&bars[P_READY + g], lane);
             }
             // ---- (c) context accumulator -> hi + lo parts -> dropout -> staging tiles -> TMA store per head pair -------------
+            lap(3);
             f_wait(&bars[O_FULL + g], par, 333);
             tc_fence_after();
+            lap(4);
             {
                 float o[kNV];
                 tmem_ld32(o_t, o);
@@ -284,9 +303,14 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps&
                     }
                 }
             }
+            lap(5);
         }
     }
     if (lane == 0) bulk_wait_all();
+    if (tmr != nullptr) {
+        for (int i = 0; i < 6; ++i) tmr[i] = tw[i];
+        tmr[6] = clock64() - t_role;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -361,9 +385,14 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
         const int smem_pieces = p.kch * 8;             // pieces that exist in the X tile
         const uint32_t x_s = smem_u32(sm.x);
         const bool tail_here = (H & 1) == 0;           // even head count: nobody else writes the ones column of the context
+        long long* tmr = (p.timing != nullptr && gw == 0 && lane == 0) ? p.timing + blockIdx.x * 32 + 16 : nullptr;  // [16] wait X free, [17] gather
+        long long tg_wait = 0, tg_work = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const long long tg0 = tmr != nullptr ? clock64() : 0;
             f_wait(&bars[X_EMPTY], static_cast<uint32_t>(it & 1) ^ 1u, 321);
+            const long long tg1 = tmr != nullptr ? clock64() : 0;
+            tg_wait += tg1 - tg0;
             const long long row0 = static_cast<long long>(tile) * G::kRows;
             for (int b = 0; b < 8; ++b) {
                 uint4 u[4][2];
@@ -420,15 +449,20 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
             }
             fence_proxy_async();
             warp_arrive(&bars[X_FULL], lane);
+            if (tmr != nullptr) tg_work += clock64() - tg1;
         }
+        if (tmr != nullptr) { tmr[0] = tg_wait; tmr[1] = tg_work; }
     } else if (warp == 12) {
         // ===================== TMA producer: per-head weight blocks, k-chunk by k-chunk =====================
         int st = 0;
         uint32_t ph = 0;
+        long long tp_wait = 0;  // [20] producer waiting for a free weight stage
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             for (int h = 0; h < H; ++h)
                 for (int kc = 0; kc < p.kch; ++kc) {
+                    const long long tp0 = p.timing != nullptr ? clock64() : 0;
                     f_wait(&bars[W_EMPTY + st], ph ^ 1u, 301);
+                    if (p.timing != nullptr) tp_wait += clock64() - tp0;
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&bars[W_FULL + st], kWStage);
                         tma_load_2d(sm.w + st * kWStage, &tmW, &bars[W_FULL + st], kc * 64, h * kNB);
@@ -437,6 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
                     if (++st == kWStages) { st = 0; ph ^= 1u; }
                 }
         }
+        if (p.timing != nullptr && lane == 0) p.timing[blockIdx.x * 32 + 20] = tp_wait;
     } else {
         // ===================== tcgen05 issuer: dependency-driven over Q|K|V (head order) and each group's S / P.V =====================
         const uint32_t idesc_qkv = make_idesc_bf16(128, kNB, 0, 0);
@@ -451,24 +486,33 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
         uint32_t ph = 0;
         uint32_t cq0 = 0u, cq1 = 0u;                 // Q|K|V projections issued per group (barrier phases); scalars: a run-time
         uint32_t cs[2] = {0u, 0u}, cp[2] = {0u, 0u};  // indexed array would live in local memory (cs / cp are indexed by the unrolled g)
+        // tuning counters: [24] wait X, [25] Q|K|V issue incl. weight waits, [26] weight waits alone, [27] idle polling, [28] role, [29] idle polls
+        long long tm_x = 0, tm_q = 0, tm_w = 0, tm_idle = 0, n_idle = 0;
+        const bool tmon = p.timing != nullptr;
+        const long long tm_role = tmon ? clock64() : 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const long long tx0 = tmon ? clock64() : 0;
             f_wait(&bars[X_FULL], static_cast<uint32_t>(it & 1), 311);
             tc_fence_after();
+            if (tmon) tm_x += clock64() - tx0;
             int q_next = 0;                                  // next head to project
             int s_next[2] = {first_head(0), first_head(1)};  // per group: next head whose scores / P.V are due
             int p_next[2] = {first_head(0), first_head(1)};
-            uint64_t t_idle = 0;
+            uint32_t idle_polls = 0;
             while (p_next[0] < H || p_next[1] < H) {
                 bool progressed = false;
+                const long long ti0 = tmon ? clock64() : 0;
                 if (q_next < H) {  // ---- Q|K|V of head q_next
                     const int h = q_next, g = group_of(h);
                     if (ready(&bars[QKV_EMPTY + g], ((g ? cq1 : cq0) & 1u) ^ 1u)) {
                         tc_fence_after();
                         const uint32_t d_t = tmem_base + g * kNB;
                         for (int kc = 0; kc < p.kch; ++kc) {
+                            const long long tw0 = tmon ? clock64() : 0;
                             f_wait(&bars[W_FULL + st], ph, 313);
                             tc_fence_after();
+                            if (tmon) tm_w += clock64() - tw0;
                             if (elect_one()) {
                                 const uint64_t da = make_sw128_desc(x_s + kc * kXChunk, 0, 1024);
                                 const uint64_t db = make_sw128_desc(w_s + st * kWStage, 0, 1024);
@@ -489,6 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
                         if (g) ++cq1; else ++cq0;
                         ++q_next;
                         progressed = true;
+                        if (tmon) tm_q += clock64() - ti0;
                     }
                 }
 #pragma unroll
@@ -528,12 +573,16 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
                     }
                 }
                 if (progressed) {
-                    t_idle = 0;
-                } else {  // nothing was ready: bounded like every other wait of this kernel
-                    if (t_idle == 0) t_idle = globaltimer_ns();
-                    else if (globaltimer_ns() - t_idle > 4000000000ull) f_timeout(317, static_cast<uint32_t>(q_next));
+                    idle_polls = 0;
+                } else {  // nothing was ready: bounded like every other wait of this kernel (~10^7 polls of >= 400 cycles)
+                    if (++idle_polls > 20000000u) f_timeout(317, static_cast<uint32_t>(q_next));
+                    if (tmon) { tm_idle += clock64() - ti0; ++n_idle; }
                 }
             }
+        }
+        if (tmon && lane == 0) {
+            long long* tmr = p.timing + blockIdx.x * 32 + 24;
+            tmr[0] = tm_x; tmr[1] = tm_q; tmr[2] = tm_w; tmr[3] = tm_idle; tmr[4] = clock64() - tm_role; tmr[5] = n_idle;
         }
     }
 
@@ -547,6 +596,9 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
 // ---------------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------------
+static long long* g_fused_timing = nullptr;
+void set_debug_fused_timing(void* dev_buf) { g_fused_timing = static_cast<long long*>(dev_buf); }
+
 int mhsa_fused_supported(int T, int d, int heads) {
     return (T == 20 && heads >= 1 && heads <= 16 && d == heads * 20 && d <= 320) ? 1 : 0;
 }
@@ -583,6 +635,7 @@ int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* tab
     p.C_hi = static_cast<__nv_bfloat16*>(C_hi);
     p.C_lo = static_cast<__nv_bfloat16*>(C_lo);
     p.bad_flag = bad_id_flag;
+    p.timing = g_fused_timing;
     CUtensorMap tmW;
     NR_PROPAGATE(make_tmap_bf16_2d(&tmW, w_heads, static_cast<int64_t>(heads) * kNB, d, ldx, 64, kNB));
     // context planes: dense boxes of one head pair (or the odd last head + ones column) x the rows of one lane quarter

@@ -33,10 +33,24 @@ def _stream():
 _seed_counter = [0x243F6A8885A308D3]
 
 
+def _seed_from(counter: int) -> int:
+    return (counter ^ (torch.initial_seed() & 0xFFFFFFFFFFFFFFFF) ^ (int(os.environ.get("RANK", "0")) << 48)) & 0xFFFFFFFFFFFFFFFF
+
+
 def next_seed() -> int:
     """Per-call dropout seed (counter based, mixed with torch's CPU seed so manual_seed() reproduces runs)."""
     _seed_counter[0] = (_seed_counter[0] * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-    return (_seed_counter[0] ^ (torch.initial_seed() & 0xFFFFFFFFFFFFFFFF) ^ (int(os.environ.get("RANK", "0")) << 48)) & 0xFFFFFFFFFFFFFFFF
+    return _seed_from(_seed_counter[0])
+
+
+def peek_seeds(n: int = 1):
+    """The next `n` values next_seed() will return, without advancing the counter (tests hand them to the oracle so
+    that it applies exactly the masks the kernels are going to draw)."""
+    c, out = _seed_counter[0], []
+    for _ in range(n):
+        c = (c * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
+        out.append(_seed_from(c))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------

