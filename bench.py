@@ -1,18 +1,26 @@
-"""bench.py -- impressions/sec, forward+backward, NRMS on MIND-shaped synthetic batches (BASELINE.json).
+"""bench.py -- impressions/sec, forward+backward, on MIND-shaped synthetic batches (BASELINE.json).
 
-    python bench.py --gpus 1 --steps 20 --warmup 5
+    python bench.py --gpus 1 --steps 20 --warmup 5                       # NRMS, BASELINE.json configs[1] (and [4] at N=8)
+    python bench.py --model NAML|LSTUR|TANR                              # configs[2], configs[3] (+ TANR)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 3 --warmup 1      # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps 3 --warmup 1                # the reference's CPU path (oracle port), same batch
 
-One "step" = zero_grad -> forward -> CrossEntropy(label 0) -> backward over one batch of B=512 impressions
-per GPU (1+K=5 candidates + 50 browsed titles of 20 tokens each = 55 news encodes + 1 user encode + 5
-scores), plus -- for N>1 -- the one NCCL gradient all-reduce.  The optimizer step is excluded: the
-metric is forward+backward.  Prints ONE JSON line on rank 0.
+One "step" = zero_grad -> forward -> CrossEntropy(label 0) -> backward over one batch of B=512 impressions per GPU
+(1+K=5 candidates + 50 browsed titles of 20 tokens each = 55 news encodes + 1 user encode + 5 scores), plus -- for N>1 --
+the one NCCL gradient all-reduce.  The optimizer step is excluded: the metric is forward+backward.
+Prints ONE JSON line on rank 0.
+
+  value    device-resident inputs (slot lists already in HBM)
+  e2e      the reference's own call, `model(candidate_news, clicked_news)` with the CPU slot lists a DataLoader yields
+           (src/train.py:202): host stacking into pinned memory + one H2D copy + device re-ordering inside forward, and a
+           device->host read of the loss every step -- what the unmodified train.py does with the drop-in
+  e2e_prefetch   (NRMS) the same with the NEXT batch staged on a copy stream by NRMS.prefetch (an API the reference lacks)
 """
 from __future__ import annotations
 
 import argparse
+import importlib
 import json
 import os
 import statistics
@@ -26,26 +34,68 @@ sys.path.insert(0, os.path.join(ROOT, "news-recommendation_b200", "src"))
 
 import torch  # noqa: E402
 
-V_WORDS, T_TITLE, H_HIST, K_NEG, D_MODEL, HEADS, Q_DIM = 70976, 20, 50, 4, 300, 15, 200
+V_WORDS, T_TITLE, T_ABS, H_HIST, K_NEG, D_MODEL, HEADS, Q_DIM = 70976, 20, 50, 50, 4, 300, 15, 200
+N_CAT, N_USERS = 275, 50001
 C_CAND = 1 + K_NEG
 N_NEWS = C_CAND + H_HIST
-# algorithmic work per impression (padding to MMA shapes is NOT counted), forward; x3 for fwd+bwd
-FLOP_FWD_PER_IMPRESSION = (N_NEWS * T_TITLE * 6 * D_MODEL ** 2 + N_NEWS * HEADS * 4 * T_TITLE ** 2 * (D_MODEL // HEADS)
-                           + N_NEWS * T_TITLE * 2 * D_MODEL * Q_DIM + N_NEWS * T_TITLE * (2 * Q_DIM + 2 * D_MODEL)
-                           + H_HIST * 6 * D_MODEL ** 2 + HEADS * 4 * H_HIST ** 2 * (D_MODEL // HEADS)
-                           + H_HIST * 2 * D_MODEL * Q_DIM + C_CAND * 2 * D_MODEL)
 
 
-def synth_slots(B, seed, device="cpu", pin=False):
-    """MIND-shaped ids exactly as default_collate hands them to the model: slot-major lists of {"title": (B,T)}.
-    Title length U{5..20} right-padded with 0; history length U{1..50}, LEFT-padded with all-zero news."""
+def flop_fwd_per_impression(model, F):
+    """Algorithmic forward FLOPs per impression (padding to MMA shapes is NOT counted); x3 for fwd+bwd."""
+    N, T, Ta, d, q, H, C = N_NEWS, T_TITLE, T_ABS, D_MODEL, Q_DIM, H_HIST, C_CAND
+    if model == "NRMS":
+        dk = d // HEADS
+        return (N * T * 6 * d * d + N * HEADS * 4 * T * T * dk + N * T * 2 * d * q + N * T * (2 * q + 2 * d)
+                + H * 6 * d * d + HEADS * 4 * H * H * dk + H * 2 * d * q + C * 2 * d)
+    conv = lambda L: N * L * 2 * 3 * d * F
+    pool = lambda L: N * L * (2 * F * q + 2 * q + 2 * F)
+    if model == "NAML":
+        return conv(T + Ta) + pool(T + Ta) + N * 2 * 2 * 100 * F + N * 4 * 2 * F * q + H * 2 * F * q
+    if model == "TANR":
+        return conv(T) + pool(T) + H * 2 * F * q + N * 2 * F * N_CAT
+    D = 3 * F  # LSTUR: GRU over the full history length (the synthetic lengths average H/2; the algorithmic figure is quoted at len = H)
+    return conv(T) + pool(T) + H * 2 * (3 * D * D) * 2
+
+
+def bytes_per_impression(model):
+    """Compulsory HBM traffic per impression, fwd+bwd: bf16 gather + fp32 embedding-gradient write + ids."""
+    tok = N_NEWS * (T_TITLE + (T_ABS if model == "NAML" else 0))
+    return tok * D_MODEL * 2 + tok * D_MODEL * 4 + tok * 8
+
+
+WORKLOADS = {
+    "NRMS": "NRMS bf16 fwd+bwd: batch={B}/GPU, title_len=20, history=50, K=4, 15 heads x d_k=20, d=300, V=70976",
+    "NAML": "NAML bf16 fwd+bwd: batch={B}/GPU, title(20)+abstract(50)+category+subcategory, CNN filters=400 window=3, history=50, K=4, d=300",
+    "LSTUR": "LSTUR(ini) bf16 fwd+bwd: batch={B}/GPU, CNN news encoder F=300 + GRU user encoder over history=50, K=4, d=300",
+    "TANR": "TANR bf16 fwd+bwd: batch={B}/GPU, CNN news encoder F=300 + additive user encoder + topic head, history=50, K=4",
+}
+FIELDS = {"NRMS": ("title",), "NAML": ("category", "subcategory", "title", "abstract"), "LSTUR": ("category", "subcategory", "title"),
+          "TANR": ("category", "title")}
+
+
+def synth_slots(model, B, seed, device="cpu", pin=False):
+    """MIND-shaped inputs exactly as default_collate hands them to the model: slot-major lists of dicts of (B, ...) int64.
+    Title length U{5..20} / abstract U{10..50} right-padded with 0; history length U{1..50}, LEFT-padded with all-zero news."""
     g = torch.Generator().manual_seed(seed)
-    ids = torch.randint(1, V_WORDS, (B, N_NEWS, T_TITLE), generator=g)
-    tl = torch.randint(5, T_TITLE + 1, (B, N_NEWS, 1), generator=g)
-    ids = ids * (torch.arange(T_TITLE).view(1, 1, -1) < tl)
-    hl = torch.randint(1, H_HIST + 1, (B, 1), generator=g)
-    keep = torch.arange(H_HIST).view(1, -1) >= (H_HIST - hl)
-    ids[:, C_CAND:] = ids[:, C_CAND:] * keep.unsqueeze(-1)
+
+    def text(T, lo):
+        ids = torch.randint(1, V_WORDS, (B, N_NEWS, T), generator=g)
+        ln = torch.randint(lo, T + 1, (B, N_NEWS, 1), generator=g)
+        return ids * (torch.arange(T).view(1, 1, -1) < ln)
+
+    hl = torch.randint(1, H_HIST + 1, (B,), generator=g)
+    keep = (torch.arange(H_HIST).view(1, -1) >= (H_HIST - hl.view(-1, 1)))  # (B, H)
+    data = {}
+    for f in FIELDS[model]:
+        if f == "title":
+            t = text(T_TITLE, 5)
+        elif f == "abstract":
+            t = text(T_ABS, 10)
+        else:
+            t = torch.randint(1, N_CAT, (B, N_NEWS), generator=g)
+        m = keep.view(B, H_HIST, *([1] * (t.dim() - 2)))
+        t[:, C_CAND:] = t[:, C_CAND:] * m
+        data[f] = t
 
     def mk(t):
         t = t.contiguous()
@@ -53,9 +103,12 @@ def synth_slots(B, seed, device="cpu", pin=False):
             return t.to(device)
         return t.pin_memory() if pin else t
 
-    cand = [{"title": mk(ids[:, j])} for j in range(C_CAND)]
-    clicked = [{"title": mk(ids[:, C_CAND + j])} for j in range(H_HIST)]
-    return cand, clicked
+    cand = [{f: mk(data[f][:, j]) for f in data} for j in range(C_CAND)]
+    clicked = [{f: mk(data[f][:, C_CAND + j]) for f in data} for j in range(H_HIST)]
+    extra = ()
+    if model == "LSTUR":
+        extra = (mk(torch.randint(1, N_USERS, (B,), generator=g)), hl.clone())  # (user ids, clicked_news_length on the host)
+    return extra, cand, clicked
 
 
 class ClockSampler:
@@ -114,7 +167,7 @@ def peaks():
 
 
 def kernel_work(name):
-    """Algorithmic FLOPs and compulsory HBM bytes of ONE launch, from the '<ctx>/<op>[a,b,c]' profile key."""
+    """Algorithmic FLOPs and the kernel's own (unfused) HBM bytes of ONE launch, from the '<ctx>/<op>[a,b,c]' profile key."""
     op = name.split("/")[1].split("[")[0]
     a, b, c = [int(x) for x in name.split("[")[1].rstrip("]").split(",")]
     if op in ("gemm_store", "gemm_scatter_emb"):          # [M, N, K]
@@ -129,6 +182,10 @@ def kernel_work(name):
         return 4.0 * a * b * b * c, 2.0 * a * b * c * 4
     if op == "mhsa_core_bwd":
         return 10.0 * a * b * b * c, 2.0 * a * b * c * 7
+    if op == "mhsa_fused_fwd":                             # [n_seq, T, d]: gather + Q|K|V + attention; reads ids + table rows, writes C hi/lo (+X)
+        return 6.0 * a * b * c * c + 4.0 * a * b * b * c, a * b * (8.0 + 2.0 * c) + 3.0 * 2.0 * a * b * c
+    if op == "mhsa_fused_bwd":                             # recompute Q|K|V + attention backward; reads X, dC, C, writes dQKV
+        return 6.0 * a * b * c * c + 10.0 * a * b * b * c, 2.0 * a * b * c * (3 + 3)
     if op == "gather_rows":                                # [n_tok, D, ld]
         return 0.0, 2.0 * a * c * 2
     if op == "pool_dscore":                                # [n_seg, seg_len, D]
@@ -136,15 +193,13 @@ def kernel_work(name):
     return 0.0, 0.0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised in
-# profiles/ncu_r01_kernel_summary.csv (batch 512 shapes only; other shapes report null)
-NCU_DRAM_BYTES = {
-    "mhsa_core_bwd[28160,20,300]": 1.483482e9 + 1.050252e9,   # 48-byte-tile kernels, profiles/ncu_r01_attention_final.csv
-    "mhsa_core_fwd[28160,20,300]": 1.055464e9 + 0.329299e9,
-    "gemm_store[563200,900,300]": 0.443694e9 + 0.979511e9,
-    "gemm_additive_pool[563200,200,300]": 0.374886e9 + 0.030811e9,
-    "gemm_additive_dpre[563200,200,300]": 0.344909e9 + 0.191328e9,
-}
+def ncu_dram_bytes(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summaries
+    (profiles/ncu_dram_bytes.json: {"<op>[a,b,c]": bytes}); null when the shape was not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_dram_bytes.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel_key)
 
 
 def usable_cores():
@@ -170,24 +225,49 @@ def log(msg):
     print(f"[bench] {msg}", file=sys.stderr, flush=True)
 
 
-def run_reference(args):
-    """The reference's own CPU path (oracle port with the reference's per-slot call structure), all usable host threads."""
+def run_reference(model, B, steps, warmup, F):
+    """The reference's own CPU path on all usable host threads, same shapes and the SAME batch as the GPU arm.
+    NRMS: the oracle port with the reference's per-slot call structure, dropout active (train mode).  The CNN families:
+    the oracle's functional restatement (fp32 autograd, eval-mode arithmetic: their dropout masks are not restated)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import newsrec_oracle as O
     cores = usable_cores()
     torch.set_num_threads(cores)
-    log(f"reference arm: {cores} threads, batch {args.ref_batch}, {args.warmup}+{args.steps} steps")
-    B = args.ref_batch
-    model = O.ReferenceStructuredNRMS(V_WORDS, D_MODEL, HEADS, Q_DIM, 0.2, 0)
-    model.train()
-    batches = [synth_slots(B, 100 + i) for i in range(2)]
-    for i in range(args.warmup):
-        O.reference_cpu_step(model, *batches[i % 2])
+    log(f"reference arm ({model}): {cores} threads, batch {B}, {warmup}+{steps} steps")
+    batches = [synth_slots(model, B, 100 + i) for i in range(2)]
+    if model == "NRMS":
+        net = O.ReferenceStructuredNRMS(V_WORDS, D_MODEL, HEADS, Q_DIM, 0.2, 0)
+        net.train()
+        one = lambda b: O.reference_cpu_step(net, b[1], b[2])
+        kind = "torch CPU, fp32, train mode (dropout on), one encoder call per slot as the reference"
+    else:
+        shapes = {"NAML": lambda: O.naml_shapes(V_WORDS, N_CAT, Fn=F), "TANR": lambda: O.tanr_shapes(V_WORDS, N_CAT, Fn=F),
+                  "LSTUR": lambda: O.lstur_shapes(V_WORDS, N_CAT, N_USERS, Fn=F)}[model]()
+        p = {k: v.requires_grad_(True) for k, v in O.tie_shared(O.det_state_dict(shapes, 0)).items()}
+        stack = lambda lst, f: torch.stack([x[f] for x in lst], dim=1)
+
+        def one(b):
+            extra, cand, clicked = b
+            for v in p.values():
+                v.grad = None
+            cd = {f: stack(cand, f) for f in FIELDS[model]}
+            hd = {f: stack(clicked, f) for f in FIELDS[model]}
+            if model == "NAML":
+                loss = O.click_loss(O.naml_forward(cd, hd, p))
+            elif model == "TANR":
+                lg, tl = O.tanr_forward(cd, hd, p)
+                loss = O.click_loss(lg) + 0.1 * tl
+            else:
+                loss = O.click_loss(O.lstur_forward(extra[0], extra[1], cd, hd, p, "ini"))
+            loss.backward()
+        kind = "torch CPU, fp32, functional restatement (eval-mode arithmetic)"
+    for i in range(warmup):
+        one(batches[i % 2])
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        O.reference_cpu_step(model, *batches[i % 2])
+    for i in range(steps):
+        one(batches[i % 2])
     dt = time.perf_counter() - t0
-    return B * args.steps / dt, dt / max(args.steps, 1) * 1e3, cores, B
+    return B * steps / dt, dt / max(steps, 1) * 1e3, cores, kind
 
 
 def main():
@@ -196,27 +276,31 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="NRMS", choices=["NRMS", "NAML", "LSTUR", "TANR"])
     ap.add_argument("--batch", type=int, default=512, help="impressions per GPU per step (BASELINE.json configs[1])")
-    ap.add_argument("--ref-batch", type=int, default=64, help="impressions per CPU step of the reference arm (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="impressions per CPU step of the reference arm (0 = --batch: same configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
-
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(min(args.warmup, 1), 1)
+    model_name = args.model
+    F = 400 if model_name == "NAML" else 300  # BASELINE.json configs[2]: CNN filters=400
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = f"NRMS bf16 fwd+bwd: batch={args.batch}/GPU, title_len={T_TITLE}, history={H_HIST}, K={K_NEG}, {HEADS} heads x d_k={D_MODEL // HEADS}, d={D_MODEL}, V={V_WORDS}"
+    workload = WORKLOADS[model_name].format(B=args.batch)
+    ref_batch = args.ref_batch or args.batch
 
     if args.impl == "reference":
         if rank != 0:
             return
-        val, ms, cores, B = run_reference(args)
+        steps = min(args.steps, 6)  # a bounded sample: one CPU step of 512 impressions takes ~10-15 s on 16 cores
+        val, ms, cores, kind = run_reference(model_name, ref_batch, steps, args.warmup, F)
         print(json.dumps({
-            "metric": "impressions/sec (fwd+bwd)", "value": val, "unit": "impressions/s", "n_gpus": args.gpus, "steps": args.steps,
+            "metric": "impressions/sec (fwd+bwd)", "value": val, "unit": "impressions/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload, "reference_step_batch": B},
+            "config": {"workload": workload, "global_batch": ref_batch, "reference_step_batch": ref_batch},
             "cpu_baseline": {"value": val, "unit": "impressions/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of {B} impressions (same shapes), fp32, torch CPU, train mode"},
+                             "sample": f"{steps} steps of {ref_batch} impressions (same shapes, same batch as the GPU arm); {kind}"},
             "e2e": {"value": val, "unit": "impressions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -228,56 +312,49 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import config as cfgmod
-    from model.NRMS import NRMS
+    Model = getattr(importlib.import_module("model." + model_name), model_name)
+    over = {"num_filters": F} if model_name == "NAML" else ({"long_short_term_method": "ini"} if model_name == "LSTUR" else {})
+    cfg = type("Cfg", (getattr(cfgmod, model_name + "Config"),), over)
     lib = newsrec_b200.load_library()
     torch.manual_seed(0)
-    model = NRMS(cfgmod.NRMSConfig).to(dev)
+    model = Model(cfg).to(dev)
     model.train()  # dropout active exactly as in the reference's training step
     grads = ddp.FlatGradients(model.parameters(), world)
     B = args.batch
-    n_rot = 3  # rotate distinct batches; X/QKV intermediates (>1.5 GB per step) far exceed the 126 MB L2
-    dev_batches = [synth_slots(B, 1000 * rank + i, device=dev) for i in range(n_rot)]
-    host_batches = [synth_slots(B, 1000 * rank + 50 + i, pin=True) for i in range(n_rot)]
+    n_rot = 3  # rotate distinct batches; the per-step intermediates (> 1 GB) far exceed the 126 MB L2
+    dev_batches = [synth_slots(model_name, B, 1000 * rank + i, device=dev) for i in range(n_rot)]
+    host_batches = [synth_slots(model_name, B, 1000 * rank + 50 + i, pin=True) for i in range(n_rot)]
     label = torch.zeros(B, dtype=torch.long, device=dev)
+    topic_w = getattr(cfg, "topic_classification_loss_weight", 0.1)
+
+    def loss_of(out):
+        if isinstance(out, tuple):  # TANR: (click logits, topic loss), train.py:190,224
+            return torch.nn.functional.cross_entropy(out[0], label) + topic_w * out[1]
+        return torch.nn.functional.cross_entropy(out, label)
+
+    def fwd(batch):
+        extra, cand, clicked = batch
+        if model_name == "LSTUR":
+            return model(extra[0], extra[1].clone(), cand, clicked)  # the reference mutates clicked_news_length in place
+        return model(cand, clicked)
 
     def step(batch, read_loss=False):
         grads.zero()
-        logits = model(batch[0], batch[1])
-        loss = torch.nn.functional.cross_entropy(logits, label)
+        loss = loss_of(fwd(batch))
         loss.backward()
         grads.all_reduce_mean()
         return loss.item() if read_loss else None
-
-    def timed_e2e(batches):
-        """End to end with HOST batches through the public API: every timed step stages one batch (host stacking into
-        pinned memory + H2D + device re-ordering, `NRMS.prefetch`, on a copy stream while the previous step's kernels
-        run) and reads its own loss back (D2H, synchronising).  `steps` copies and `steps` reads inside the timed region."""
-        def run(n):
-            cur = model.prefetch(*batches[0])
-            for i in range(n):
-                grads.zero()
-                loss = torch.nn.functional.cross_entropy(model(cur), label)
-                loss.backward()
-                grads.all_reduce_mean()
-                if i + 1 < n:
-                    cur = model.prefetch(*batches[(i + 1) % n_rot])  # overlaps the kernels enqueued above
-                loss.item()
-        run(args.warmup)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run(args.steps)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return float(ms.item())
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
+
+    def max_ms(e0, e1):
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
 
     def timed(batches, read_loss, profile=False):
         for i in range(args.warmup):
@@ -292,24 +369,42 @@ def main():
             step(batches[i % n_rot], read_loss)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return float(ms.item()), newsrec_b200.launch_count() - l0
+        return max_ms(e0, e1), newsrec_b200.launch_count() - l0
 
-    log(f"rank {rank}/{world}: model + data ready; timing device-resident steps")
-    # ---- device-resident inputs: `value` ----
+    def timed_prefetch(batches):
+        """NRMS only: every timed step stages the NEXT batch (host stacking + H2D + device re-ordering) on a copy stream
+        while this step's kernels run, and reads its own loss back."""
+        def run(n):
+            cur = model.prefetch(batches[0][1], batches[0][2])
+            for i in range(n):
+                grads.zero()
+                loss = torch.nn.functional.cross_entropy(model(cur), label)
+                loss.backward()
+                grads.all_reduce_mean()
+                if i + 1 < n:
+                    nb = batches[(i + 1) % n_rot]
+                    cur = model.prefetch(nb[1], nb[2])
+                loss.item()
+        run(args.warmup)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(args.steps)
+        e1.record()
+        barrier()
+        return max_ms(e0, e1)
+
+    log(f"rank {rank}/{world}: {model_name} + data ready; timing device-resident steps")
     with ClockSampler(local) as clk:
         ms_total, launches = timed(dev_batches, read_loss=False)
     log(f"device-resident: {ms_total / args.steps:.3f} ms/step; per-kernel pass")
-    # ---- per-kernel durations: a separate pass (the event pairs around every launch are kept out of `value`) ----
-    timed(dev_batches, read_loss=False, profile=True)
+    timed(dev_batches, read_loss=False, profile=True)  # separate pass: the event pairs around every launch stay out of `value`
     prof = newsrec_b200.profile_report()
     lib.nr_profile_enable(0)
-    log("timing end-to-end steps")
-    # ---- end to end through the public API with HOST buffers (H2D of ids + D2H of the loss inside) ----
-    ms_e2e = timed_e2e(host_batches)
-    log(f"end-to-end: {ms_e2e / args.steps:.3f} ms/step")
+    log("timing end-to-end steps (host slot lists through model(candidate_news, clicked_news), loss read back)")
+    ms_e2e, _ = timed(host_batches, read_loss=True)
+    log(f"end-to-end (reference API): {ms_e2e / args.steps:.3f} ms/step")
+    ms_pref = timed_prefetch(host_batches) if model_name == "NRMS" else None
 
     if world > 1:
         torch.distributed.barrier()
@@ -321,7 +416,6 @@ def main():
     value = imp / (ms_total / 1e3)
     e2e = imp / (ms_e2e / 1e3)
     # dominant kernel of the step and its roofline (timed inside a long step -> sustained tensor peak)
-    steps_profiled = args.steps
     tot_prof = sum(v[1] for v in prof.values())
     dom = max(prof.items(), key=lambda kv: kv[1][1])
     flops, bytes_ = kernel_work(dom[0])
@@ -332,31 +426,40 @@ def main():
     else:
         roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]}
     roof.update({"kernel": dom[0], "share_of_step": dom[1][1] / tot_prof, "avg_launch_ms": dur_s * 1e3,
-                 "traffic": NCU_DRAM_BYTES.get(dom[0].split("/")[1]), "algorithmic_bytes": bytes_,
+                 "traffic": ncu_dram_bytes(dom[0].split("/")[1]), "algorithmic_bytes": bytes_, "algorithmic_flops": flops,
                  "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)"})
-    step_tf = value / world * 3 * FLOP_FWD_PER_IMPRESSION / 1e12
-    breakdown = {k: round(v[1] / steps_profiled, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    ffwd = flop_fwd_per_impression(model_name, F)
+    step_tf = value / world * 3 * ffwd / 1e12
+    comp_bytes = bytes_per_impression(model_name)
+    step_gbs = value / world * comp_bytes / 1e9
+    breakdown = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    n_tok_bytes = sum(int(t.numel()) * 8 for d in (host_batches[0][1] + host_batches[0][2]) for t in d.values())
     out = {
         "metric": "impressions/sec (fwd+bwd)", "value": value, "unit": "impressions/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "l2": "3 rotating batches; per-step intermediates (~1.7 GB) exceed the 126 MB L2", "dropout": 0.2},
+                   "l2": "3 rotating batches; per-step intermediates (> 1 GB) exceed the 126 MB L2", "dropout": 0.2},
         "e2e": {"value": e2e, "unit": "impressions/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": B * N_NEWS * T_TITLE * 8, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": n_tok_bytes, "d2h_bytes_per_step": 4,
+                "path": "model(candidate_news, clicked_news) with CPU slot lists (the call of the reference's train.py:202), loss.item() every step"},
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "roofline": roof,
         "roofline_step": {"bound": "tensor", "achieved": step_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                           "frac": step_tf / pk["bf16_tflops_sustained"],
-                          "note": "whole step: algorithmic 3 x %.1f MFLOP per impression / step time, per GPU" % (FLOP_FWD_PER_IMPRESSION / 1e6)},
+                          "hbm_compulsory": {"bytes_per_step": comp_bytes * B, "achieved_gbs": step_gbs, "frac": step_gbs / pk["hbm_gbs"]},
+                          "note": "whole step per GPU: algorithmic 3 x %.1f MFLOP and %.2f MB compulsory HBM bytes per impression (SURVEY 8d) / step time"
+                                  % (ffwd / 1e6, comp_bytes / 1e6)},
         "kernel_ms_per_step": breakdown,
     }
+    if ms_pref is not None:
+        out["e2e_prefetch"] = {"value": imp / (ms_pref / 1e3), "unit": "impressions/s", "ms_per_step": ms_pref / args.steps,
+                               "path": "NRMS.prefetch stages the next batch on a copy stream (not a reference API)"}
     if world == 1 and not args.no_cpu_baseline:
-        ra = argparse.Namespace(steps=3, warmup=1, ref_batch=args.ref_batch)
-        val, ms, cores, rb = run_reference(ra)
+        val, ms, cores, kind = run_reference(model_name, ref_batch, 2, 1, F)
         out["cpu_baseline"] = {"value": val, "unit": "impressions/s", "cores": cores, "kind": "port",
-                               "sample": f"3 steps of {rb} impressions (same shapes), fp32, torch CPU, train mode, {ms:.0f} ms/step"}
+                               "sample": f"2 steps of {ref_batch} impressions after 1 warm-up (same shapes, same batch); {kind}; {ms:.0f} ms/step"}
     print(json.dumps(out))
 
 

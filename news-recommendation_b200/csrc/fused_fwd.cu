@@ -574,7 +574,9 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
                 }
                 if (progressed) {
                     idle_polls = 0;
-                } else {  // nothing was ready: bounded like every other wait of this kernel (~10^7 polls of >= 400 cycles)
+                } else {  // nothing was ready: back off (the polls would otherwise take this scheduler's issue slots from the
+                          // epilogue warps sharing it); bounded like every other wait of this kernel
+                    __nanosleep(64);
                     if (++idle_polls > 20000000u) f_timeout(317, static_cast<uint32_t>(q_next));
                     if (tmon) { tm_idle += clock64() - ti0; ++n_idle; }
                 }

@@ -91,6 +91,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or `ns` nanoseconds pass.  Without
+// the hint the instruction gives up after ~30 cycles and a waiting warp turns into a busy loop that competes for issue
+// slots with the warps it is waiting for (ncu on the fused front end: 8 waiting warps per SM took most of the issue slots,
+// tensor pipe 8 % active; profiles/).
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete)
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -114,11 +129,12 @@ __device__ __noinline__ void mbar_timeout(int code, uint32_t aux) {
     asm volatile("trap;");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) mbar_timeout(code, parity);
+    if (mbar_try_wait_sleep(bar, parity, 20000u)) return;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait_sleep(bar, parity, 1000000u)) {  // every failed probe slept for up to 1 ms (or came back early: timed below)
+        const uint64_t t = globaltimer_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ull) mbar_timeout(code, parity);
     }
 }
 #endif

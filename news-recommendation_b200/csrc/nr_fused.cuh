@@ -44,11 +44,12 @@ __device__ __noinline__ void f_timeout(int code, uint32_t aux) {
     asm volatile("trap;");
 }
 __device__ __forceinline__ void f_wait(uint64_t* bar, uint32_t parity, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = globaltimer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) f_timeout(code, parity);
+    if (mbar_try_wait_sleep(bar, parity, 20000u)) return;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait_sleep(bar, parity, 1000000u)) {  // sleeps in hardware; wakes when the phase completes
+        const uint64_t t = globaltimer_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 4000000000ull) f_timeout(code, parity);
     }
 }
 #endif
