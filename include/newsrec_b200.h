@@ -175,6 +175,9 @@ typedef struct {
     /* QKV_bf16 == NULL (the fused forward keeps Q|K|V on chip): recomputed here from X_bf16 with these operands */
     const void* wqkv_bf16;               /* [3d][ldx]                                                    */
     const float* bqkv;                   /* [3d]                                                         */
+    /* optional cudaEvent_t recorded on `stream` as soon as demb is complete (before the weight-gradient GEMM): a data-
+     * parallel caller starts the embedding-gradient all-reduce on a side stream that waits for it */
+    void* emb_grad_ready_event;
 } nr_mhsa_encoder_bwd_args;
 long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q);
 int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream);

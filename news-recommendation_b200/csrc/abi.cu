@@ -235,17 +235,20 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
                                     a->ldx, st));
     // --- attention backward ---
     NR_PROPAGATE(mhsa_core_bwd(QKV, a->ld3, dC, a->ldx, a->n_seq, a->T, a->heads, a->d / a->heads, dQKV, a->ld3, st));
-    // --- projection backward: weights (+bias through the ones column of X), then the input ---
-    NR_PROPAGATE(gemm_tn_accumulate(dQKV, M, 3 * a->d, a->ld3, a->X_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWqkv_ext,
-                                    a->ldx, st));
+    // --- projection backward: the input first (the embedding gradient is 97 % of a data-parallel step's all-reduce: the
+    //     caller's event lets the communication start under the weight-gradient GEMM), then the weights (+bias through the
+    //     ones column of X) ---
     if (a->ids != nullptr) {
         NR_REQUIRE(a->V >= 1, "nr_mhsa_encoder_bwd: V=%d", a->V);
         NR_PROPAGATE(gemm_scatter_emb(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, a->ids, a->demb, a->V, a->d,
                                       kIdentity, DropoutCfg{a->p_drop, a->seed}, a->ldx, st));
+        if (a->emb_grad_ready_event != nullptr) NR_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->emb_grad_ready_event), st));
     } else {
         NR_PROPAGATE(gemm_store(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, nullptr, 0, a->ddense, a->d,
                                 0, kIdentity, 0, kNoDrop, -1, 0, st));
     }
+    NR_PROPAGATE(gemm_tn_accumulate(dQKV, M, 3 * a->d, a->ld3, a->X_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWqkv_ext,
+                                    a->ldx, st));
     return 0;
 }
 

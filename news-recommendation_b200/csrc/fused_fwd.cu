@@ -112,20 +112,73 @@ __device__ __forceinline__ int next_head(int h, int H) { return (!(h & 1) && h +
 __device__ __forceinline__ int group_of(int h) { return (h >> 1) & 1; }
 
 // ---------------------------------------------------------------------------------------------------------------------------
+// scores -> exp-softmax (multihead_self.py:16-20) -> P as the bf16 A operand in TMEM, for the 32 rows of lane quarter QD.
+// The only piece of the epilogue that needs the lane quarter at compile time (register-array offsets of the score window):
+// everything else runs from ONE copy of the code (the fully specialised role was 4 x 25 KB of SASS; ncu: no_instruction stalls).
+// ---------------------------------------------------------------------------------------------------------------------------
+template <int T, int QD>
+__device__ __forceinline__ void softmax_step(uint32_t s_t, int sel, float sc) {
+    using W = Win<T, QD>;
+    float x[T];
+    {
+        float v[64];
+        tmem_ld32(s_t + W::start, v);
+        tmem_ld32(s_t + W::start + 32, v + 32);
+        tmem_ld_wait();
+        constexpr int o0 = W::tlo * T - W::start;
+        constexpr int o1 = W::ncand > 1 ? o0 + T : o0;       // candidates that do not exist alias candidate 0
+        constexpr int o2 = W::ncand > 2 ? o0 + 2 * T : o0;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            x[j] = v[o0 + j];
+            if (W::ncand > 1 && sel == 1) x[j] = v[o1 + j];
+            if (W::ncand > 2 && sel == 2) x[j] = v[o2 + j];
+        }
+    }
+    float m = x[0];
+#pragma unroll
+    for (int j = 1; j < T; ++j) m = fmaxf(m, x[j]);
+    m *= sc;
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+        x[j] = exp2f(fmaf(x[j], sc, -m));
+        l += x[j];
+    }
+    const float inv = 1.f / (l + 1e-8f * exp2f(-m));  // == exp(S) / (sum exp(S) + 1e-8)
+    uint32_t pk[T / 2];
+#pragma unroll
+    for (int i = 0; i < T / 2; ++i) pk[i] = pack_bf16x2(x[2 * i] * inv, x[2 * i + 1] * inv);
+    // all 64 packed columns of the P operand are rewritten (the score MMA overwrote them): zeros off the diagonal
+    uint32_t pw[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+        pw[c] = 0u;
+#pragma unroll
+        for (int i = 0; i < W::ncand; ++i) {
+            const int c0 = (W::tlo + i) * (T / 2);
+            if (c >= c0 && c < c0 + T / 2) pw[c] = (sel == i) ? pk[c - c0] : 0u;
+        }
+    }
+    tmem_st32(s_t, pw);
+    tmem_st32(s_t + 32, pw + 32);
+    tmem_st_wait();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
 // epilogue / softmax role of one warp: TMEM lane quarter QD of group g
 // ---------------------------------------------------------------------------------------------------------------------------
-template <int T, int DK, int QD>
-__device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps& maps, const Smem& sm, uint32_t tmem_base, int g,
-                                              int lane) {
+template <int T, int DK>
+__device__ __noinline__ void epilogue_role(const FwdParams& p, const CtxMaps& maps, const Smem& sm, uint32_t tmem_base, int g,
+                                           int QD, int lane) {
     using G = Geo<T>;
-    using W = Win<T, QD>;
     static_assert(DK % 4 == 0 && DK <= kVLo && 3 * DK <= kNB && kVLo + DK <= kNV && 2 * DK * 2 * 32 <= kStageBuf, "head width");
     constexpr int H2 = DK / 2;  // packed words per head row
-    constexpr int kBoxRows = (G::kRows - 32 * QD) < 32 ? (G::kRows - 32 * QD) : 32;  // used rows of this lane quarter
+    const int kBoxRows = (G::kRows - 32 * QD) < 32 ? (G::kRows - 32 * QD) : 32;  // used rows of this lane quarter
     const int r = 32 * QD + lane;
     int t = r / T;
     if (t > G::kTPT - 1) t = G::kTPT - 1;  // dead rows ride with the last title (their results are never stored)
-    const int sel = t - W::tlo;
+    const int sel = t - (32 * QD) / T;  // index among the titles of this lane quarter (Win<T, QD>::tlo)
     const uint32_t lane_base = static_cast<uint32_t>(QD * 32) << 16;
     const uint32_t qk_tile = smem_u32(sm.qk + g * kTile), v_tile = smem_u32(sm.v + g * kTile);
     const uint32_t acc_t = tmem_base + lane_base + g * kNB;
@@ -195,59 +248,19 @@ __device__ __forceinline__ void epilogue_role(const FwdParams& p, const CtxMaps&
                 fence_proxy_async();
                 warp_arrive(&bars[QK_READY + g], lane);
             }
-            // ---- (b) scores -> exp-softmax (multihead_self.py:16-20) -> P as the bf16 A operand in TMEM ---------------------
+            // ---- (b) scores -> exp-softmax -> P as the bf16 A operand in TMEM --------------------------------------------------
             lap(1);
             f_wait(&bars[S_FULL + g], par, 332);
             tc_fence_after();
             lap(2);
-            {
-                float x[T];
-                {
-                    float v[64];
-                    tmem_ld32(s_t + W::start, v);
-                    tmem_ld32(s_t + W::start + 32, v + 32);
-                    tmem_ld_wait();
-                    constexpr int o0 = W::tlo * T - W::start;
-                    constexpr int o1 = W::ncand > 1 ? o0 + T : o0;       // candidates that do not exist alias candidate 0
-                    constexpr int o2 = W::ncand > 2 ? o0 + 2 * T : o0;
-#pragma unroll
-                    for (int j = 0; j < T; ++j) {
-                        x[j] = v[o0 + j];
-                        if (W::ncand > 1 && sel == 1) x[j] = v[o1 + j];
-                        if (W::ncand > 2 && sel == 2) x[j] = v[o2 + j];
-                    }
-                }
-                float m = x[0];
-#pragma unroll
-                for (int j = 1; j < T; ++j) m = fmaxf(m, x[j]);
-                m *= p.sc;
-                float l = 0.f;
-#pragma unroll
-                for (int j = 0; j < T; ++j) {
-                    x[j] = exp2f(fmaf(x[j], p.sc, -m));
-                    l += x[j];
-                }
-                const float inv = 1.f / (l + 1e-8f * exp2f(-m));  // == exp(S) / (sum exp(S) + 1e-8)
-                uint32_t pk[T / 2];
-#pragma unroll
-                for (int i = 0; i < T / 2; ++i) pk[i] = pack_bf16x2(x[2 * i] * inv, x[2 * i + 1] * inv);
-                // all 64 packed columns of the P operand are rewritten (the score MMA overwrote them): zeros off the diagonal
-                uint32_t pw[64];
-#pragma unroll
-                for (int c = 0; c < 64; ++c) {
-                    pw[c] = 0u;
-#pragma unroll
-                    for (int i = 0; i < W::ncand; ++i) {
-                        const int c0 = (W::tlo + i) * (T / 2);
-                        if (c >= c0 && c < c0 + T / 2) pw[c] = (sel == i) ? pk[c - c0] : 0u;
-                    }
-                }
-                tmem_st32(s_t, pw);
-                tmem_st32(s_t + 32, pw + 32);
-                tmem_st_wait();
-                tc_fence_before();
-                warp_arrive(&bars[P_READY + g], lane);
+            switch (QD) {
+                case 0: softmax_step<T, 0>(s_t, sel, p.sc); break;
+                case 1: softmax_step<T, 1>(s_t, sel, p.sc); break;
+                case 2: softmax_step<T, 2>(s_t, sel, p.sc); break;
+                default: softmax_step<T, 3>(s_t, sel, p.sc); break;
             }
+            tc_fence_before();
+            warp_arrive(&bars[P_READY + g], lane);
             // ---- (c) context accumulator -> hi + lo parts -> dropout -> staging tiles -> TMA store per head pair -------------
             lap(3);
             f_wait(&bars[O_FULL + g], par, 333);
@@ -371,13 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
     uint64_t* bars = sm.bars;
 
     if (warp < 8) {
-        const int g = warp >> 2;
-        switch (warp & 3) {
-            case 0: epilogue_role<T, DK, 0>(p, maps, sm, tmem_base, g, lane); break;
-            case 1: epilogue_role<T, DK, 1>(p, maps, sm, tmem_base, g, lane); break;
-            case 2: epilogue_role<T, DK, 2>(p, maps, sm, tmem_base, g, lane); break;
-            default: epilogue_role<T, DK, 3>(p, maps, sm, tmem_base, g, lane); break;
-        }
+        epilogue_role<T, DK>(p, maps, sm, tmem_base, warp >> 2, warp & 3, lane);
     } else if (warp < 12) {
         // ===================== gather: table rows -> (dropout) -> X tile (+ the X rows in HBM) =====================
         const int gw = warp - 8;

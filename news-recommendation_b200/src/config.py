@@ -31,7 +31,10 @@ BaseConfig = type("BaseConfig", (), dict(_COMMON, __doc__="General configuration
 
 _CNN = {"num_filters": 300, "window_size": 3}
 _PER_MODEL = {
-    "NRMS": dict(dataset_attributes={"news": ["title"], "record": []}, num_attention_heads=15),
+    # fused_news_encoder is an extension knob of this build (not in the reference): True selects the one-kernel news front
+    # end with hi/lo V / context (the precise mode, ~3x closer to the reference's fp32 results, slower)
+    "NRMS": dict(dataset_attributes={"news": ["title"], "record": []}, num_attention_heads=15,
+                 fused_news_encoder=os.environ.get("NEWSREC_FUSED") == "1"),
     "NAML": dict(dataset_attributes={"news": ["category", "subcategory", "title", "abstract"], "record": []}, **_CNN),
     "LSTUR": dict(dataset_attributes={"news": ["category", "subcategory", "title"],
                                       "record": ["user", "clicked_news_length"]},

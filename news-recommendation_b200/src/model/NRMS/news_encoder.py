@@ -35,7 +35,8 @@ class NewsEncoder(nn.Module):
         return MhsaPoolEncoderFn.apply(ids, None, self.word_embedding.weight,
                                        *self.multihead_self_attention.qkv_parameters(),
                                        a.linear.weight, a.linear.bias, a.attention_query_vector,
-                                       self.config.num_attention_heads, p, self._cache, "news", self.bad_id_flag(dev))
+                                       self.config.num_attention_heads, p, self._cache, "news", self.bad_id_flag(dev),
+                                       bool(getattr(self.config, "fused_news_encoder", False)))
 
     def forward(self, news):
         """news: {"title": (batch, num_words_title) int64} -> (batch, word_embedding_dim)"""

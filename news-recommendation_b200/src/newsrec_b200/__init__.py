@@ -38,7 +38,7 @@ class MhsaEncoderBwdArgs(C.Structure):
         ("X_bf16", _vp), ("QKV_bf16", _vp), ("C_bf16", _vp), ("w", _vp), ("dout", _vp),
         ("dWqkv_ext", _vp), ("dWa_ext", _vp), ("dqv", _vp), ("demb", _vp), ("ddense", _vp),
         ("workspace", _vp), ("workspace_bytes", _ll),
-        ("wqkv_bf16", _vp), ("bqkv", _vp),
+        ("wqkv_bf16", _vp), ("bqkv", _vp), ("emb_grad_ready_event", _vp),
     ]
 
 

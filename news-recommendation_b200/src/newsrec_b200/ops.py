@@ -30,6 +30,10 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Data-parallel hook (ddp.FlatGradients): a torch.cuda.Event the news-encoder backward records as soon as the embedding
+# gradient is complete, so that its all-reduce can start under the remaining backward kernels.  None = not armed.
+grad_ready_hook = {"event": None, "recorded": False}
+
 _seed_counter = [0x243F6A8885A308D3]
 
 
@@ -138,7 +142,7 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, ids, dense, emb_w, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv, heads, p_drop, cache, prefix, bad_flag):
+    def forward(ctx, ids, dense, emb_w, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv, heads, p_drop, cache, prefix, bad_flag, precise=False):
         lib = load_library()
         dev = require_cuda()
         d, q = Wq.shape[0], Wa.shape[0]
@@ -162,8 +166,10 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
             table = None
         n_tok = n_seq * T
         need_bwd = any(ctx.needs_input_grad)
-        # the fused front end (gather -> Q|K|V -> attention in one kernel) covers the reference's news level shapes
-        fused = ids is not None and os.environ.get("NEWSREC_NO_FUSED") is None and bool(lib.nr_mhsa_fused_supported(T, d, heads))
+        # the fused front end (gather -> Q|K|V -> attention in ONE kernel, V / context as hi/lo bf16 pairs) is the PRECISE
+        # mode of the news level: 2.6e-3 instead of 7e-3 against the reference's fp32 logits, at ~3.6x the time of the
+        # unfused gather | GEMM | attention sequence -- opt-in (config.fused_news_encoder / NEWSREC_FUSED=1)
+        fused = ids is not None and (precise or os.environ.get("NEWSREC_FUSED") == "1") and bool(lib.nr_mhsa_fused_supported(T, d, heads))
         X = QKV = C_lo = None
         if need_bwd or not fused:  # X only exists in HBM when a backward pass (or the unfused sequence) reads it
             X = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
@@ -238,6 +244,10 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         a.p_drop, a.seed = m["p_drop"], m["seed"]
         a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.dout = _p(X), (_p(QKV) if QKV.numel() else None), _p(Cx), _p(w), _p(dout)
         a.wqkv_bf16, a.bqkv = _p(ops["wqkv"]), _p(ops["bqkv"])
+        ev = grad_ready_hook["event"] if (m["has_ids"] and emb_direct) else None
+        if ev is not None:
+            a.emb_grad_ready_event = C.c_void_p(ev.cuda_event)
+            grad_ready_hook["recorded"] = True
         a.dWqkv_ext, a.dWa_ext, a.dqv = _p(dWqkv), _p(dWa), _p(dqv)
         a.demb, a.ddense = _p(demb), _p(ddense)
         a.workspace, a.workspace_bytes = _p(ws), ws_bytes
@@ -249,11 +259,11 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
                 check(lib.nr_accumulate_ext_grad(_p(dWqkv[i * d:(i + 1) * d]), d, ldx, d, _p(sinks[2 * i]), _p(sinks[2 * i + 1]),
                                                  _stream()), "nr_accumulate_ext_grad")
             check(lib.nr_accumulate_ext_grad(_p(dWa), q, ldx, d, _p(sinks[6]), _p(sinks[7]), _stream()), "nr_accumulate_ext_grad")
-            return (None, g_dense, g_emb) + (None,) * 14
+            return (None, g_dense, g_emb) + (None,) * 15
         gW = [dWqkv[i * d:(i + 1) * d, :d].contiguous() for i in range(3)]
         gb = [dWqkv[i * d:(i + 1) * d, d].contiguous() for i in range(3)]
         return (None, g_dense, g_emb, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2],
-                dWa[:, :d].contiguous(), dWa[:, d].contiguous(), dqv, None, None, None, None, None)
+                dWa[:, :d].contiguous(), dWa[:, d].contiguous(), dqv, None, None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -43,12 +43,12 @@ def t(g, key):
     return torch.from_numpy(g[key])
 
 
-def oracle_forward(case, g, p, contract=O.EXACT):
-    """Runs the oracle on a golden case's inputs.  Returns (logits, topic_loss or None)."""
+def oracle_forward(case, g, p, contract=O.EXACT, fused=False):
+    """Runs the oracle on a golden case's inputs.  Returns (logits, topic_loss or None).
+    fused: the NRMS news level runs through the one-kernel front end (V / context as hi/lo bf16 pairs)."""
     cand_t, clicked_t = t(g, "cand_title"), t(g, "clicked_title")
     if case == "nrms":
-        # the news level runs through the fused front end (V / context as hi/lo pairs) whenever a bf16 contract is asked for
-        c_news = O.BF16_FUSED if contract.bf16 else contract
+        c_news = O.BF16_FUSED if (contract.bf16 and fused) else contract
         return O.nrms_forward(cand_t, clicked_t, p, 15, contract, c_news=c_news), None
     if case.startswith("naml"):
         cand = dict(title=cand_t, abstract=t(g, "cand_abstract"), category=t(g, "cand_category"),

@@ -221,10 +221,11 @@ def check_dot_score(B=9, Cn=5, D=300):
 
 
 # ------------------------------------------------------------------------------------------------
-def nrms_model_and_params(V, seed, heads=15, dropout=0.2):
+def nrms_model_and_params(V, seed, heads=15, dropout=0.2, fused=False):
     import config as cfgmod
     from model.NRMS import NRMS
-    cfg = type("Cfg", (cfgmod.NRMSConfig,), dict(num_words=V, num_attention_heads=heads, dropout_probability=dropout))
+    cfg = type("Cfg", (cfgmod.NRMSConfig,), dict(num_words=V, num_attention_heads=heads, dropout_probability=dropout,
+                                                 fused_news_encoder=fused))
     sd = O.det_state_dict(O.nrms_shapes(V), seed)
     model = NRMS(cfg)
     model.load_state_dict(sd)
@@ -268,13 +269,13 @@ def check_nrms_golden():
     return out
 
 
-def check_nrms_random(B=8, Cn=5, H=50, T=20, V=500, seed=5):
+def check_nrms_random(B=8, Cn=5, H=50, T=20, V=500, seed=5, fused=False):
     """A MIND-shaped batch (K=4, history 50, left padded) vs the oracle under the bf16 contract."""
     cand_t, clicked_t, _ = O.synth_batch(B, Cn, H, T, V, seed * 100)
-    model, sd = nrms_model_and_params(V, seed)
+    model, sd = nrms_model_and_params(V, seed, fused=fused)
     model.eval()
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16, c_news=O.BF16_FUSED)
+    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16, c_news=O.BF16_FUSED if fused else O.BF16)
     O.click_loss(logits_o).backward()
     with torch.no_grad():
         logits_x = O.nrms_forward(cand_t, clicked_t, {k: v.detach() for k, v in p.items()}, 15, O.EXACT)
@@ -357,7 +358,7 @@ def check_nrms_eval_api(V=300, seed=9):
     titles = O.synth_titles(40, 20, V, 3)
     with torch.no_grad():
         nv = model.get_news_vector({"title": titles, "id": ["N%d" % i for i in range(40)]})
-        nv_o = O.nrms_news_encoder(titles, p, 15, O.BF16_FUSED)
+        nv_o = O.nrms_news_encoder(titles, p, 15, O.BF16)
         B, H = 4, 10
         stacked = torch.stack([nv[i * 4:(i + 1) * 4] for i in range(H)], dim=0).transpose(0, 1)  # (B,H,d) non-contiguous
         uv = model.get_user_vector(stacked)
@@ -392,7 +393,7 @@ def check_nrms_train_mode(B=16, V=400, seed=4):
             "grads_finite": bool(torch.isfinite(g).all()), "emb_row0_grad_zero": bool((g[0] == 0).all())}
 
 
-def check_nrms_train_masked(B=6, Cn=5, H=50, T=20, V=500, seed=8, p_drop=0.2):
+def check_nrms_train_masked(B=6, Cn=5, H=50, T=20, V=500, seed=8, p_drop=0.2, fused=False):
     """TRAIN mode -- the configuration bench.py times -- forward AND backward against the oracle under the SAME dropout
     masks: the kernels draw their masks from a counter hash of (seed, row, column); the test reads the seed the next
     forward will use (ops.peek_seeds) and hands it to the oracle, which rebuilds the masks with the NumPy restatement of
@@ -400,12 +401,12 @@ def check_nrms_train_masked(B=6, Cn=5, H=50, T=20, V=500, seed=8, p_drop=0.2):
     self-attention, :43).  A backward that regenerated a different mask than its forward would fail every gradient."""
     from newsrec_b200 import ops
     cand_t, clicked_t, _ = O.synth_batch(B, Cn, H, T, V, seed * 100)
-    model, sd = nrms_model_and_params(V, seed, dropout=p_drop)
+    model, sd = nrms_model_and_params(V, seed, dropout=p_drop, fused=fused)
     model.train()
     kseed = ops.peek_seeds(1)[0]  # the news encoder draws the only seed of a forward pass (the user encoder has no dropout)
     drop = dict(p=p_drop, seed=kseed, ld=ru8(300 + 1))
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16, c_news=O.BF16_FUSED, drop=drop)
+    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16, c_news=O.BF16_FUSED if fused else O.BF16, drop=drop)
     O.click_loss(logits_o).backward()
     px = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     logits_x = O.nrms_forward(cand_t, clicked_t, px, 15, O.EXACT, drop=drop)  # exact arithmetic, same masks
@@ -607,13 +608,15 @@ def check_encoder_backend_diff(B=8, V=500, seed=5):
 
 
 # ------------------------------------------------------------------------------------------------
-def build_model(case, V=120, ncat=15, nusers=40, H=6, dropout=0.2):
+def build_model(case, V=120, ncat=15, nusers=40, H=6, dropout=0.2, fused=False):
     """Drop-in model + deterministic state_dict for a golden case name (see oracle/make_golden.py)."""
     import importlib
     import config as cfgmod
     from golden_util import case_shapes
     name = {"nrms": "NRMS", "naml": "NAML", "naml_f400": "NAML", "tanr": "TANR", "lstur_ini": "LSTUR", "lstur_con": "LSTUR"}[case]
     over = dict(num_words=V, num_categories=ncat, num_users=nusers, num_clicked_news_a_user=H, dropout_probability=dropout)
+    if name == "NRMS":
+        over["fused_news_encoder"] = fused
     if case == "naml_f400":
         over["num_filters"] = 400
     if case.startswith("lstur"):
@@ -640,19 +643,19 @@ def golden_inputs(case, g):
     return mk("cand"), mk("clicked")
 
 
-def check_golden(case):
+def check_golden(case, fused=False):
     """A committed golden case (minted from the live reference): CUDA drop-in vs the reference's fp32 outputs, vs the
     oracle under the bf16 storage contract, and -- per gradient -- against the exact fp32 oracle next to the error the
     bf16 contract itself has (kernel_err <= ~1.5 x contract_err is the pass criterion)."""
     from golden_util import case_params, load_case, oracle_forward, unique_params
     g = load_case(case)
     p_b = case_params(case, g)
-    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16)
+    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, fused)
     (O.click_loss(logits_b) + (0.1 * topic_b if topic_b is not None else 0.0)).backward()
     p_x = case_params(case, g)
     logits_x, topic_x = oracle_forward(case, g, p_x, O.EXACT)
     (O.click_loss(logits_x) + (0.1 * topic_x if topic_x is not None else 0.0)).backward()
-    model, _ = build_model(case)
+    model, _ = build_model(case, fused=fused)
     sd = O.tie_shared(O.det_state_dict(__import__("golden_util").case_shapes(case), int(g["seed"])))
     model.load_state_dict(sd)
     model.eval()

@@ -29,8 +29,18 @@ def test_golden_case(case):
         assert r["topic_loss_rel_vs_reference"] < 1e-3, r
 
 
-def test_nrms_mind_shaped_batch_vs_oracle():
-    r = G.check_nrms_random()
+def test_nrms_precise_mode_golden_case():
+    """config.fused_news_encoder: the one-kernel news front end with hi/lo V / context.  Same assertions as the default path
+    against its own storage contract, and a tighter bound against the reference's fp32 outputs (measured 2.6e-3 vs 7.3e-3)."""
+    r = G.check_golden("nrms", fused=True)
+    assert r["logits_vs_oracle_bf16"] < 1e-3, r
+    assert r["logits_vs_reference_fp32"] < 4e-3, r
+    assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_nrms_mind_shaped_batch_vs_oracle(fused):
+    r = G.check_nrms_random(fused=fused)
     assert r["logits_vs_oracle_bf16"] < 1e-3, r
     assert r["logits_vs_exact_fp32"] < 1.25 * r["oracle_bf16_vs_exact"] + 1e-4, r
 
@@ -59,9 +69,11 @@ def test_nrms_train_mode_dropout_statistics():
     assert r["mean_train_vs_eval_rel"] < 0.3, r
 
 
-def test_nrms_train_mode_matches_masked_oracle():
-    """The benchmarked configuration (train mode, dropout 0.2), forward and backward, at the eval-mode tolerances."""
-    r = G.check_nrms_train_masked()
+@pytest.mark.parametrize("fused", [False, True])
+def test_nrms_train_mode_matches_masked_oracle(fused):
+    """The benchmarked configuration (train mode, dropout 0.2), forward and backward, at the eval-mode tolerances
+    (default kernel sequence and the fused precise mode: both draw the same masks from the same counter hash)."""
+    r = G.check_nrms_train_masked(fused=fused)
     assert r["masks_matter"] > 0.05, r                                   # the masks change the result by far more than any tolerance
     assert r["logits_vs_masked_oracle"] < 1e-3, r                        # same masks, same storage contract
     assert r["logits_vs_masked_exact_fp32"] < 1.25 * r["masked_oracle_vs_masked_exact"] + 1e-4, r

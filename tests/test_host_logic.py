@@ -192,7 +192,7 @@ def test_flat_gradient_all_reduce_equals_single_process_mean_gloo():
 def test_bench_synthetic_batches_are_mind_shaped():
     sys.path.insert(0, ROOT)
     import bench
-    cand, clicked = bench.synth_slots(6, 3)
+    _, cand, clicked = bench.synth_slots("NRMS", 6, 3)
     assert len(cand) == 5 and len(clicked) == 50 and cand[0]["title"].shape == (6, 20) and cand[0]["title"].dtype == torch.int64
     hist = torch.stack([x["title"] for x in clicked], 1)             # (B, 50, 20)
     empty = (hist.sum(-1) == 0)
@@ -206,3 +206,11 @@ def test_bench_synthetic_batches_are_mind_shaped():
     assert int(t.max()) < bench.V_WORDS and bench.usable_cores() >= 1
     f, b = bench.kernel_work("news.fwd/gemm_store[563200,900,300]")
     assert f == 2.0 * 563200 * 900 * 300 and b > 0
+    # the other BASELINE configurations: every attribute the model reads, LSTUR's record fields, left-padded history
+    extra, cand, clicked = bench.synth_slots("LSTUR", 4, 5)
+    assert set(cand[0]) == {"category", "subcategory", "title"} and extra[0].shape == (4,) and int(extra[1].min()) >= 1
+    _, cand, clicked = bench.synth_slots("NAML", 4, 5)
+    assert cand[0]["abstract"].shape == (4, 50) and clicked[0]["category"].shape == (4,)
+    hl = (torch.stack([x["title"] for x in clicked], 1).sum(-1) != 0).sum(1)
+    assert bool((torch.stack([x["category"] for x in clicked], 1) != 0).sum(1).eq(hl).all())  # empty news are empty in every field
+    assert abs(bench.flop_fwd_per_impression("NRMS", 300) / 1e6 - 789.5) < 0.5
