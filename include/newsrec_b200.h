@@ -282,6 +282,10 @@ typedef struct {
     float* out;                     /* fp32 [B][Hd] last hidden state                                     */
 } nr_gru_fwd_args;
 int nr_gru_fwd(const nr_gru_fwd_args* a, void* stream);
+/* 1 if nr_gru_fwd runs the whole recurrence as ONE cooperative launch for this shape on this device (users in 128-row tiles x
+ * hidden units in slices of 32, one CTA each, all resident: tiles * slices <= SM count; Hd % 4 == 0, Hd <= 960); else it
+ * runs three launches per step */
+int nr_gru_persistent_supported(int B, int Hd);
 
 typedef struct {
     int B, S, D, Hd;

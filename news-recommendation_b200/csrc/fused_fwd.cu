@@ -32,7 +32,7 @@
 #include <algorithm>
 #include <cstring>
 
-#define NR_FUSED_OWNS_WATCHDOG 1
+#define NR_WATCHDOG_SYMBOL g_fused_dev_error
 #include "nr_fused.cuh"
 #include "nr_ops.h"
 
@@ -40,8 +40,11 @@ namespace nr {
 
 extern int g_launches;
 
+int read_gru_device_error(int* out4);
 int read_fused_device_error(int* out4) {
-    return static_cast<int>(cudaMemcpyFromSymbol(out4, fused::g_fused_dev_error, sizeof(int) * 4));
+    const int rc = static_cast<int>(cudaMemcpyFromSymbol(out4, fused::g_fused_dev_error, sizeof(int) * 4));
+    if (rc != 0 || out4[0] != 0) return rc;
+    return read_gru_device_error(out4);  // the persistent GRU kernel keeps its own record (gru_persist.cu)
 }
 
 namespace fused {

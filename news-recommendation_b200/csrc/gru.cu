@@ -7,6 +7,7 @@
 //   r = sig(gi_r + gh_r), z = sig(gi_z + gh_z), n = tanh(gi_n + r * gh_n), h' = (1 - z) n + z h ;
 // user b stops updating after len[b] steps.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/newsrec_b200.h"
@@ -134,6 +135,11 @@ int nr_gru_fwd(const nr_gru_fwd_args* a, void* stream) {
     // h_0
     NR_CHECK_CUDA(cudaMemcpyAsync(a->hs, a->h0, sizeof(float) * BH, cudaMemcpyDeviceToDevice, st));
     NR_PROPAGATE(rows_to_bf16(a->h0, B, 1, Hd, Hd, 0, 1, a->hb, ldh, st));
+    static const bool no_persist = getenv("NEWSREC_GRU_STEPWISE") != nullptr;  // tests compare the two paths
+    if (!no_persist && gru_persistent_supported(B, Hd)) {
+        // one cooperative launch for the whole recurrence (gru_persist.cu); same saved state as the per-step sequence below
+        return gru_fwd_persistent(B, S, Hd, ldh, ldg, a->gi, a->whh_bf16, a->bhh, a->h0, a->len, a->gh, a->hs, a->hb, a->out, st);
+    }
     for (int t = 0; t < S; ++t) {
         float* gh_t = a->gh + static_cast<size_t>(t) * B * ldg;
         const void* hb_t = static_cast<const __nv_bfloat16*>(a->hb) + static_cast<size_t>(t) * B * ldh;
@@ -151,6 +157,8 @@ int nr_gru_fwd(const nr_gru_fwd_args* a, void* stream) {
     NR_CHECK_CUDA(cudaMemcpyAsync(a->out, a->hs + static_cast<size_t>(S) * BH, sizeof(float) * BH, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
+
+int nr_gru_persistent_supported(int B, int Hd) { return gru_persistent_supported(B, Hd); }
 
 long long nr_gru_bwd_workspace(int B, int S, int D, int Hd) {
     const long long ldb = ru8(3 * Hd + 1), BP = static_cast<long long>(B) * ru4(Hd);

@@ -33,13 +33,14 @@ struct Win {
 };
 
 // ---- device error record + bounded waits of the fused kernels -------------------------------------------------------------
-#ifdef NR_FUSED_OWNS_WATCHDOG
-__device__ int g_fused_dev_error[4] = {0, 0, 0, 0};
-__device__ __noinline__ void f_timeout(int code, uint32_t aux) {
-    g_fused_dev_error[0] = code;
-    g_fused_dev_error[1] = blockIdx.x;
-    g_fused_dev_error[2] = threadIdx.x;
-    g_fused_dev_error[3] = static_cast<int>(aux);
+// every translation unit of this family names its own record (no relocatable device code): #define NR_WATCHDOG_SYMBOL first
+#ifdef NR_WATCHDOG_SYMBOL
+__device__ int NR_WATCHDOG_SYMBOL[4] = {0, 0, 0, 0};
+static __device__ __noinline__ void f_timeout(int code, uint32_t aux) {
+    NR_WATCHDOG_SYMBOL[0] = code;
+    NR_WATCHDOG_SYMBOL[1] = blockIdx.x;
+    NR_WATCHDOG_SYMBOL[2] = threadIdx.x;
+    NR_WATCHDOG_SYMBOL[3] = static_cast<int>(aux);
     __threadfence_system();
     asm volatile("trap;");
 }

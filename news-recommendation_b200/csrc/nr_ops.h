@@ -86,6 +86,11 @@ int mhsa_fused_fwd(const long long* ids, long long n_seq, int T, const void* tab
                    int* bad_id_flag, cudaStream_t stream);
 int read_fused_device_error(int* out4);
 
+// ---- persistent GRU recurrence (gru_persist.cu): all S steps of h_t = GRU(gi_t, h_{t-1}) in one cooperative launch --------
+int gru_persistent_supported(int B, int Hd);
+int gru_fwd_persistent(int B, int S, int Hd, int ldh, int ldg, const float* gi, const void* whh, const float* bhh, const float* h0,
+                       const long long* len, float* gh, float* hs, void* hb, float* out, cudaStream_t stream);
+
 int num_sms();
 
 // ---- live per-kernel timing (bench.py): CUDA events on the launching stream around every kernel ------

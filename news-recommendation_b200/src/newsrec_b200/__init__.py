@@ -129,6 +129,7 @@ SIGNATURES = {
     "nr_element_encoder_fwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "nr_element_encoder_bwd": (_i, [_vp, _ll, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "nr_gru_fwd": (_i, [C.POINTER(GruFwdArgs), _vp]),
+    "nr_gru_persistent_supported": (_i, [_i, _i]),
     "nr_gru_bwd_workspace": (_ll, [_i, _i, _i, _i]),
     "nr_gru_bwd": (_i, [C.POINTER(GruBwdArgs), _vp]),
 }

@@ -179,7 +179,10 @@ def main(argv=None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         backend = args.backend or ("nccl" if torch.cuda.is_available() else "gloo")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        # rank 0 alone runs the reference's evaluate() (a Python loop over up to 200k impressions) while the other ranks
+        # already wait in the next collective: the default 10-minute NCCL watchdog would abort the job
+        import datetime
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, timeout=datetime.timedelta(hours=6))
 
     import importlib
     if args.set:

@@ -202,6 +202,8 @@ def multihead_self_attention(x, p, prefix, heads, c: Contract = EXACT, ctx_mask=
     ctx = scaled_dot_product_attention(split(proj("Q")), split(proj("K")), split(proj("V")), c)
     ctx = ctx.transpose(1, 2).contiguous().view(N, T, d)  # (:74-76)
     if ctx_mask is not None:  # train mode: dropout on the context (NRMS/news_encoder.py:43) with an injected mask
+        if not (c.bf16 and c.hilo):
+            ctx = c.act(ctx)  # the unfused attention kernel rounds the context to bf16 BEFORE the 1/(1-p) scaling (and again after)
         ctx = ctx * ctx_mask
     return c.act_hilo(ctx)
 

@@ -221,6 +221,37 @@ def check_dot_score(B=9, Cn=5, D=300):
 
 
 # ------------------------------------------------------------------------------------------------
+def check_gru(B=37, S=50, D=900, Hd=900, seed=3):
+    """LSTUR user-encoder GRU (pack_padded_sequence + nn.GRU, last hidden state; LSTUR/user_encoder.py:27-45) at the
+    reference's history length, mixed lengths including 0 (clamped to 1) and S: forward and every gradient against the
+    oracle under the bf16 operand contract.  B <= 128 * floor(SMs / 29) runs the persistent single-launch recurrence."""
+    from newsrec_b200.ops import OperandCache
+    from newsrec_b200.ops_gru import GruLastHiddenFn
+    a = math.sqrt(1.0 / Hd)
+    p = {"g.weight_ih_l0": O.det_uniform((3 * Hd, D), seed, -a, a), "g.weight_hh_l0": O.det_uniform((3 * Hd, Hd), seed + 1, -a, a),
+         "g.bias_ih_l0": O.det_uniform((3 * Hd,), seed + 2, -a, a), "g.bias_hh_l0": O.det_uniform((3 * Hd,), seed + 3, -a, a)}
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    x = _rand_bf16((B, S, D), seed + 4, 0.5).requires_grad_(True)
+    h0 = O.det_uniform((B, Hd), seed + 5, -0.5, 0.5).requires_grad_(True)
+    lengths = O.det_randint((B,), seed + 6, 0, S + 1)
+    lengths[0], lengths[1 % B] = 0, S
+    ref = O.gru_last_hidden(x, lengths.clamp(min=1), h0, p, "g", O.BF16)
+    gout = O.det_uniform((B, Hd), seed + 7)
+    ref.backward(gout)
+    xd, hd = x.detach().to(DEV).requires_grad_(True), h0.detach().to(DEV).requires_grad_(True)
+    pd = {k: v.detach().to(DEV).requires_grad_(True) for k, v in p.items()}
+    out = GruLastHiddenFn.apply(xd, lengths.to(DEV), hd, pd["g.weight_ih_l0"], pd["g.weight_hh_l0"], pd["g.bias_ih_l0"],
+                                pd["g.bias_hh_l0"], OperandCache(), "gru")
+    out.backward(gout.to(DEV))
+    torch.cuda.synchronize()
+    res = {"fwd_rel": relerr(out, ref), "dx_rel": relerr(xd.grad, x.grad), "dh0_rel": relerr(hd.grad, h0.grad),
+           "persistent": bool(load_library().nr_gru_persistent_supported(B, Hd))}
+    for k in p:
+        res["d" + k.split(".")[1]] = relerr(pd[k].grad, p[k].grad)
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 def nrms_model_and_params(V, seed, heads=15, dropout=0.2, fused=False):
     import config as cfgmod
     from model.NRMS import NRMS

@@ -94,3 +94,13 @@ def test_fused_news_front_end(kw):
     assert r.get("x_vs_masked_oracle_exact", True), r
     assert r["ctx_vs_oracle_fused_contract"] < 1e-3, r
     assert r["out_vs_oracle"] < 1e-3 and r["w_sums_to_one"] < 1e-5, r
+
+
+@pytest.mark.parametrize("kw", [dict(B=37, S=50), dict(B=300, S=50), dict(B=5, S=7, D=450, Hd=900), dict(B=9, S=12, D=900, Hd=450),
+                                dict(B=700, S=6)])
+def test_gru_last_hidden_history_50_mixed_lengths(kw):
+    """BASELINE.json configs[3] shapes (history 50, D = Hd = 900): the persistent recurrence kernel (one cooperative launch
+    for all steps) and, for shapes it does not cover (B = 700: more CTAs than SMs), the per-step sequence."""
+    r = G.check_gru(**kw)
+    assert r["fwd_rel"] < 1e-3, r
+    assert r["dx_rel"] < 5e-3 and r["dh0_rel"] < 5e-3 and r["dweight_ih_l0"] < 5e-3 and r["dweight_hh_l0"] < 5e-3, r
