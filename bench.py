@@ -406,8 +406,10 @@ def main():
     log(f"end-to-end (reference API): {ms_e2e / args.steps:.3f} ms/step")
     ms_pref = timed_prefetch(host_batches) if model_name == "NRMS" else None
 
+    log(f"rank {rank}: timed regions done")
     if world > 1:
         torch.distributed.barrier()
+        torch.cuda.synchronize()
         torch.distributed.destroy_process_group()
     if rank != 0:
         return
@@ -460,7 +462,7 @@ def main():
         val, ms, cores, kind = run_reference(model_name, ref_batch, 2, 1, F)
         out["cpu_baseline"] = {"value": val, "unit": "impressions/s", "cores": cores, "kind": "port",
                                "sample": f"2 steps of {ref_batch} impressions after 1 warm-up (same shapes, same batch); {kind}; {ms:.0f} ms/step"}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

@@ -35,6 +35,9 @@ int nr_num_sms(void);
 /* TRIAGE ONLY (tests): route the GEMMs through a plain SIMT accumulate + the same epilogue functors, to
  * tell a tcgen05/TMA pipeline bug from an epilogue bug.  Never enabled by the product path. */
 void nr_debug_set_simt_gemm(int on);
+/* 1 in a triage build (`make TRIAGE=1`), 0 in the release library, where nr_debug_set_simt_gemm is a no-op, the SIMT
+ * kernels are not compiled and no environment switch is consulted on a launch path */
+int nr_has_triage_backends(void);
 /* TUNING ONLY (tools/kbench.py): dev_buf holds slots x 148 x 16 int64; the k-th gemm_nt planned after this call
  * writes, per CTA, cycle counters into slot k: [0] TMA producer waiting for a free A stage, [1] MMA issuer waiting
  * for A data, [2] MMA issuer waiting for a free TMEM accumulator, [3] epilogue waiting for a finished accumulator,

@@ -810,9 +810,17 @@ int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int 
     const int d = heads * dk;
     int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, d);
     if (bwd) piece = (piece == 8 && (ld_out % 4) == 0) ? 8 : ((piece >= 4 && (ld_out % 2) == 0) ? 4 : 2);
-    static const bool force_loops = getenv("NEWSREC_ATTN_LOOPS") != nullptr;  // tuning switch (tools/kbench.py)
+#ifdef NEWSREC_TRIAGE
+    static const bool force_loops = getenv("NEWSREC_ATTN_LOOPS") != nullptr;  // tuning switch (tools/kbench.py), triage builds only
+#else
+    constexpr bool force_loops = false;
+#endif
     const bool fast = !force_loops && piece >= 4 && T * (dk / (piece / 2)) <= kMaxP * 32;
+#ifdef NEWSREC_TRIAGE
     static const bool no_fixed = getenv("NEWSREC_ATTN_GENERIC") != nullptr;  // tuning switch: skip the fixed-shape kernels
+#else
+    constexpr bool no_fixed = false;
+#endif
     if constexpr (TP == 32 && KSD == 2 && NTD == 3) {
         // the reference's title encoder (config.py: num_words_title 20, 15 heads x 20) gets a fully fixed-shape kernel
         if (fast && !no_fixed && piece == 8 && T == 20 && dk == 20 && heads == 15)
@@ -829,14 +837,22 @@ int launch_mma(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_d
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     // 64-row tiles (history-level attention): one cooperative CTA of TP/16 warps per (sequence, head)
     if constexpr (TP > 32) {
+#ifdef NEWSREC_TRIAGE
         static const bool no_coop = getenv("NEWSREC_ATTN_NOCOOP") != nullptr;  // tuning switch
+#else
+        constexpr bool no_coop = false;
+#endif
         if (!no_coop) {
             if constexpr (TP == 64 && KSD == 2 && NTD == 3) {
                 // the reference's user encoder (config.py: num_clicked_news_a_user 50, 15 heads x 20): fixed shape
                 const int d = heads * dk;
                 int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, d);
                 if (bwd && (ld_out % 4) != 0) piece = 0;
+#ifdef NEWSREC_TRIAGE
                 static const bool no_fixed = getenv("NEWSREC_ATTN_GENERIC") != nullptr;
+#else
+                constexpr bool no_fixed = false;
+#endif
                 if (!no_fixed && piece == 8 && T == 50 && dk == 20 && heads == 15)
                     return launch_mma_cfg2<TP, KSD, NTD, 2, TP / 16, false, 50, 20, 15, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads,
                                                                                               dk, out, ld_out, drop, stream);

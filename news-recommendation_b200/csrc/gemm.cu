@@ -126,6 +126,7 @@ int num_sms() {
     return n;
 }
 
+#ifdef NEWSREC_TRIAGE
 static int g_debug_simt = -1;
 bool debug_simt_gemm() {
     if (g_debug_simt < 0) {
@@ -135,6 +136,12 @@ bool debug_simt_gemm() {
     return g_debug_simt == 1;
 }
 void set_debug_simt_gemm(int on) { g_debug_simt = on ? 1 : 0; }
+int has_triage_backends() { return 1; }
+#else
+bool debug_simt_gemm() { return false; }
+void set_debug_simt_gemm(int) {}
+int has_triage_backends() { return 0; }
+#endif
 // tuning (tools/kbench.py): device buffer [slots][148][16]; every planned gemm_nt takes the next slot
 static long long* g_gemm_timing = nullptr;
 static int g_gemm_timing_slots = 0, g_gemm_timing_next = 0;
@@ -207,8 +214,10 @@ int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B,
     p.k_chunks = ceil_div(K, kChunkK);
     p.taps = taps;
     p.b_tap_rows = b_tap_rows;
+#ifdef NEWSREC_TRIAGE
     static const int dbg_flags = [] { const char* v = getenv("NEWSREC_GEMM_DBG"); return v != nullptr ? atoi(v) : 0; }();
     p.dbg_flags = dbg_flags;
+#endif
     if (g_gemm_timing != nullptr && g_gemm_timing_next < g_gemm_timing_slots) {
         p.timing = g_gemm_timing + static_cast<size_t>(g_gemm_timing_next) * 148 * 16;
         fprintf(stderr, "[nr] gemm timing slot %d: M=%d N=%d K=%d taps=%d\n", g_gemm_timing_next, M, N, K, taps);
@@ -241,6 +250,7 @@ int plan_gemm_nt(GemmNTPlan* plan, const void* A, int M, int lda, const void* B,
     return 0;
 }
 
+#ifdef NEWSREC_TRIAGE
 // Debug backend accumulate: thread = one output column of one M tile (slow, obviously correct).
 __global__ void gemm_nt_simt_acc_kernel(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                                         GemmNTParams p) {
@@ -262,6 +272,8 @@ __global__ void gemm_nt_simt_acc_kernel(const __nv_bfloat16* A, int lda, const _
         p.dbg_acc[(static_cast<size_t>(tile) * 128 + r) * p.dbg_ld + n] = acc;
     }
 }
+
+#endif  // NEWSREC_TRIAGE
 
 // ------------------------------------------------------------------------------------------------
 // gemm_tn kernel
@@ -387,6 +399,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+#ifdef NEWSREC_TRIAGE
 __global__ void gemm_tn_simt_kernel(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int b_rows,
                                     GemmTNParams p) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,6 +414,7 @@ __global__ void gemm_tn_simt_kernel(const __nv_bfloat16* A, int lda, const __nv_
     }
     atomicAdd(p.D + static_cast<size_t>(m) * p.ldd + n, acc);
 }
+#endif
 
 int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, int b_rows, int b_cols, int ldb,
                        int b_col0, int Nb, int b_row_shift, float* D, int ldd, cudaStream_t stream) {
@@ -416,6 +430,7 @@ int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, in
     p.D = D;
     p.ldd = ldd;
     ProfScope ps("gemm_tn", Kr, Ma, Nb, stream);
+#ifdef NEWSREC_TRIAGE
     if (debug_simt_gemm()) {
         dim3 g(ceil_div(Nb, 64), Ma);
         gemm_tn_simt_kernel<<<g, 64, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda,
@@ -424,6 +439,7 @@ int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, in
         NR_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
+#endif
     const int sms = num_sms();
     NR_REQUIRE(sms > 0, "no CUDA device");
     p.m_tiles = ceil_div(Ma, 128);
@@ -487,8 +503,10 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
     e.drop = to_drop(drop);
     e.ones_col = ones_col;
     e.ones_cols_zero_upto = ones_zero_upto;
+#ifdef NEWSREC_TRIAGE
     static const int dbg_skip = [] { const char* v = getenv("NEWSREC_EPI_DBG"); return v != nullptr && v[0] == '1' ? 1 : 0; }();
     e.dbg_skip = dbg_skip;
+#endif
     g_launches += debug_simt_gemm() ? 2 : 1;
     ProfScope ps("gemm_store", M, N, K * taps, stream);
     return launch_gemm_nt(plan, e, A, lda, W, ldw, stream);

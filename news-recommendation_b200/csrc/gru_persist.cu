@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_fwd_persistent_kernel(const _
     uint64_t* tfull = bars + 1 + 2 * kAStages;
     uint64_t* tempty = tfull + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
-    float* sBias = reinterpret_cast<float*>(tmem_slot + 4);  // [3][kU] b_hh of this slice (zero for units that do not exist)
+    float* sBias = reinterpret_cast<float*>(bars + 16);      // [3][kU] b_hh of this slice (zero for units that do not exist); 16-byte aligned
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x / p.slices, s = blockIdx.x - m * p.slices;
     const int j0 = s * kU;

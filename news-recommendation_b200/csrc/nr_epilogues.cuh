@@ -105,10 +105,12 @@ struct EpiStore {
         long long orow;
         int t;
         const bool v = rm.map(c.grow, orow, t) && c.valid;
+#ifdef NEWSREC_TRIAGE
         if (dbg_skip) {
             acc.release();
             return;
         }
+#endif
         const int lane = c.tid & 31;
         WarpTileStore ts;
         if (use_tma) {

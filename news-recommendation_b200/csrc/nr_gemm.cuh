@@ -280,9 +280,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kc = 0; kc < p.k_chunks; ++kc) {
                     timed_wait(&empty[st], ph ^ 1, 101, tw_a);
                     if (elect_one()) {
+#ifdef NEWSREC_TRIAGE
                         if (p.dbg_flags & 2) {
                             if (leader) mbar_arrive(&full[st]);
-                        } else {
+                        } else
+#endif
+                        {
                             if (leader) mbar_arrive_expect_tx(&full[st], 2 * kAStageBytes);
                             tma_load_2d_pair(sA + st * kAStageBytes, &tmA, mapa_shared(&full[st], 0), kc * kChunkK,
                                              row0 + s - tap_shift);
@@ -377,7 +380,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == kEpiWarps + 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
-// Debug backend (triage only, NR_DEBUG_SIMT_GEMM=1): plain SIMT accumulate + the SAME epilogue functors.
+// Debug backend (TRIAGE builds only -- `make TRIAGE=1`, -DNEWSREC_TRIAGE; the release library has no second backend and
+// consults no environment switch on the launch path): plain SIMT accumulate + the SAME epilogue functors.
+#ifdef NEWSREC_TRIAGE
 __global__ void gemm_nt_simt_acc_kernel(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                                         GemmNTParams p);
 template <class Epi>
@@ -412,6 +417,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) gemm_nt_simt_epi_kernel(const 
     }
     epi.finish(ei);
 }
+#endif  // NEWSREC_TRIAGE
 
 // ---------------------------------------------------------------------------------------------
 // gemm_tn kernel
@@ -454,6 +460,7 @@ template <class Epi>
 int launch_gemm_nt(const GemmNTPlan& plan, const Epi& epi, const void* A, int lda, const void* B, int ldb,
                    cudaStream_t stream) {
     if (plan.p.num_m_tiles <= 0) return 0;
+#ifdef NEWSREC_TRIAGE
     if (debug_simt_gemm()) {
         GemmNTParams p = plan.p;
         const size_t ld = static_cast<size_t>(round_up(p.N, 32) + 32);
@@ -475,6 +482,7 @@ int launch_gemm_nt(const GemmNTPlan& plan, const Epi& epi, const void* A, int ld
         NR_CHECK_CUDA(cudaFreeAsync(acc, stream));
         return 0;
     }
+#endif
     static bool attr_set = false;  // per Epi instantiation
     if (!attr_set) {
         NR_CHECK_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));

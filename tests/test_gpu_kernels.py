@@ -60,6 +60,10 @@ def test_tcgen05_weight_grad_gemm(kw):
 
 
 def test_tcgen05_matches_simt_triage_backend():
+    """Triage builds only (`make -C news-recommendation_b200/csrc TRIAGE=1`): the release library has no second backend."""
+    from newsrec_b200 import load_library
+    if not load_library().nr_has_triage_backends():
+        pytest.skip("release build: SIMT triage backend not compiled in")
     r = G.check_backend_agreement()
     assert r["n_bad"] == 0 and r["tc_rerun_maxabs"] == 0.0 and r["tc_vs_ref_rel"] < 1e-5, r
 
