@@ -411,6 +411,7 @@ def main():
         torch.distributed.barrier()
         torch.cuda.synchronize()
         torch.distributed.destroy_process_group()
+    log(f"rank {rank}: process group closed")
     if rank != 0:
         return
     pk = peaks()
@@ -466,4 +467,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # noqa: BLE001  (a failure must never look like an empty result)
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        raise

@@ -235,14 +235,40 @@ def embedding(ids, table, c: Contract = EXACT):
     return F.embedding(ids, c.operand(table), padding_idx=0)
 
 
-def title_cnn(x, weight, bias, c: Contract = EXACT):
+def title_cnn(x, weight, bias, c: Contract = EXACT, y_mask=None):
     """Conv2d(1, F, (window, d), padding=((window-1)/2, 0)) over tokens + ReLU.
     src/model/NAML/news_encoder.py:15-17,27-32; LSTUR/news_encoder.py:24-28,60-66;
     TANR/news_encoder.py:21-25,43-48.  x: (N, T, d) -> (N, T, F).
-    Contract: x is a bf16 activation, weight a bf16 operand; output stored bf16."""
+    Contract: x is a bf16 activation, weight a bf16 operand; output stored bf16.
+    y_mask (N, T, F): train mode, the dropout after the ReLU (e.g. NAML/news_encoder.py:33-34) with an injected mask --
+    the kernel applies it in fp32 before the one bf16 store."""
     window = weight.shape[2]
     y = F.conv2d(x.unsqueeze(1), c.operand(weight), bias, padding=((window - 1) // 2, 0)).squeeze(3)
-    return c.act(F.relu(y).transpose(1, 2))
+    y = F.relu(y).transpose(1, 2)
+    if y_mask is not None:
+        y = y * y_mask.to(y.dtype)
+    return c.act(y)
+
+
+def cnn_text_encoder(ids, table, conv_w, conv_b, p, att_prefix, c: Contract = EXACT, drop=None):
+    """embedding -> dropout -> Conv2d + ReLU -> dropout -> additive pooling: the text encoder NAML, LSTUR and TANR share
+    (NAML/news_encoder.py:21-37, LSTUR/news_encoder.py:56-72, TANR/news_encoder.py:40-52).
+    drop=None: eval mode.  drop=dict(p, seed, n0): train mode with the kernels' masks -- the gathered rows live in the
+    zero-padded layout (title n, token t -> row (n0+n)*(T+2) + 1 + t, pitch round_up(d+1, 8)) under hash(seed); the conv
+    output in the compact layout (row (n0+n)*T + t, pitch round_up(F+1, 8)) under hash(seed ^ 0x5bd1e995); n0 = index of
+    the first title of `ids` in the order the drop-in packs the batch (browsed block, then candidates)."""
+    x = embedding(ids, table, c)
+    y_mask = None
+    if drop is not None and drop["p"] > 0:
+        N, T, d = x.shape
+        Fn = conv_w.shape[0]
+        ru8 = lambda v: (v + 7) // 8 * 8
+        n0 = drop.get("n0", 0)
+        mx = dropout_mask(drop["seed"], drop["p"], N * (T + 2), d, ru8(d + 1), n0 * (T + 2)).view(N, T + 2, d)[:, 1:T + 1]
+        y_mask = dropout_mask(drop["seed"] ^ 0x5bd1e995, drop["p"], N * T, Fn, ru8(Fn + 1), n0 * T).view(N, T, Fn)
+        x = c.act(x * mx.to(x.dtype))
+    y = title_cnn(x, conv_w, conv_b, c, y_mask)
+    return additive_attention(y, p, att_prefix, c)
 
 
 # --------------------------------------------------------------------------- #
@@ -289,11 +315,10 @@ def nrms_forward(cand_title, clicked_title, p, heads, c: Contract = EXACT, c_new
 # --------------------------------------------------------------------------- #
 # NAML  (reference: src/model/NAML/**)
 # --------------------------------------------------------------------------- #
-def naml_text_encoder(ids, p, prefix, c: Contract = EXACT):
-    """src/model/NAML/news_encoder.py:21-37 (eval)."""
-    x = embedding(ids, p[f"{prefix}.word_embedding.weight"], c)
-    y = title_cnn(x, p[f"{prefix}.CNN.weight"], p[f"{prefix}.CNN.bias"], c)
-    return additive_attention(y, p, f"{prefix}.additive_attention", c)
+def naml_text_encoder(ids, p, prefix, c: Contract = EXACT, drop=None):
+    """src/model/NAML/news_encoder.py:21-37 (drop: see cnn_text_encoder)."""
+    return cnn_text_encoder(ids, p[f"{prefix}.word_embedding.weight"], p[f"{prefix}.CNN.weight"], p[f"{prefix}.CNN.bias"], p,
+                            f"{prefix}.additive_attention", c, drop)
 
 
 def naml_element_encoder(ids, p, prefix, c: Contract = EXACT):
@@ -306,7 +331,7 @@ def naml_element_encoder(ids, p, prefix, c: Contract = EXACT):
 NAML_VIEW_ORDER = ("title", "abstract", "category", "subcategory")
 
 
-def naml_news_encoder(news, p, c: Contract = EXACT, prefix="news_encoder"):
+def naml_news_encoder(news, p, c: Contract = EXACT, prefix="news_encoder", drop=None):
     """src/model/NAML/news_encoder.py:86-115.  The reference's view order follows a
     Python set (PYTHONHASHSEED dependent); the additive fusion is
     permutation invariant up to fp summation order, so a fixed order is used."""
@@ -315,7 +340,8 @@ def naml_news_encoder(news, p, c: Contract = EXACT, prefix="news_encoder"):
         if name not in news:
             continue
         if name in ("title", "abstract"):
-            vecs.append(naml_text_encoder(news[name], p, f"{prefix}.text_encoders.{name}", c))
+            d_view = None if drop is None else dict(p=drop["p"], seed=drop["seeds"][name], n0=drop.get("n0", 0))
+            vecs.append(naml_text_encoder(news[name], p, f"{prefix}.text_encoders.{name}", c, d_view))
         else:
             vecs.append(naml_element_encoder(news[name], p, f"{prefix}.element_encoders.{name}", c))
     if len(vecs) == 1:
@@ -324,13 +350,16 @@ def naml_news_encoder(news, p, c: Contract = EXACT, prefix="news_encoder"):
     return additive_attention(stacked, p, f"{prefix}.final_attention", c)
 
 
-def naml_forward(cand, clicked, p, c: Contract = EXACT):
-    """src/model/NAML/__init__.py:19-54.  cand/clicked: dict name -> (B,C,..)/(B,H,..)."""
+def naml_forward(cand, clicked, p, c: Contract = EXACT, drop=None):
+    """src/model/NAML/__init__.py:19-54.  cand/clicked: dict name -> (B,C,..)/(B,H,..).
+    drop=dict(p, seeds={"title": s1, "abstract": s2}): train mode with the kernels' masks (one seed per text encoder call)."""
     B, C = cand["title"].shape[:2]
     H = clicked["title"].shape[1]
     flat = lambda d, n: {k: v.reshape(B * n, *v.shape[2:]) for k, v in d.items()}
-    cv = naml_news_encoder(flat(cand, C), p, c).view(B, C, -1)
-    hv = naml_news_encoder(flat(clicked, H), p, c).view(B, H, -1)
+    d_h = None if drop is None else dict(drop, n0=0)
+    d_c = None if drop is None else dict(drop, n0=B * H)
+    cv = naml_news_encoder(flat(cand, C), p, c, drop=d_c).view(B, C, -1)
+    hv = naml_news_encoder(flat(clicked, H), p, c, drop=d_h).view(B, H, -1)
     user = additive_attention(c.act(hv), p, "user_encoder.additive_attention", c)  # NAML/user_encoder.py:11-19
     return dot_product_click_predictor(cv, user)
 
@@ -338,19 +367,20 @@ def naml_forward(cand, clicked, p, c: Contract = EXACT):
 # --------------------------------------------------------------------------- #
 # TANR  (reference: src/model/TANR/**)
 # --------------------------------------------------------------------------- #
-def tanr_news_encoder(title, p, c: Contract = EXACT, prefix="news_encoder"):
-    """src/model/TANR/news_encoder.py:30-54 (eval)."""
-    x = embedding(title, p[f"{prefix}.word_embedding.weight"], c)
-    y = title_cnn(x, p[f"{prefix}.title_CNN.weight"], p[f"{prefix}.title_CNN.bias"], c)
-    return additive_attention(y, p, f"{prefix}.title_attention", c)
+def tanr_news_encoder(title, p, c: Contract = EXACT, prefix="news_encoder", drop=None):
+    """src/model/TANR/news_encoder.py:30-54 (drop: see cnn_text_encoder)."""
+    return cnn_text_encoder(title, p[f"{prefix}.word_embedding.weight"], p[f"{prefix}.title_CNN.weight"],
+                            p[f"{prefix}.title_CNN.bias"], p, f"{prefix}.title_attention", c, drop)
 
 
-def tanr_forward(cand, clicked, p, c: Contract = EXACT):
-    """src/model/TANR/__init__.py:24-69.  Returns (logits, topic_classification_loss)."""
+def tanr_forward(cand, clicked, p, c: Contract = EXACT, drop=None):
+    """src/model/TANR/__init__.py:24-69.  Returns (logits, topic_classification_loss).  drop=dict(p, seed): train mode."""
     B, C, T = cand["title"].shape
     H = clicked["title"].shape[1]
-    cv = tanr_news_encoder(cand["title"].reshape(B * C, T), p, c).view(B, C, -1)
-    hv = tanr_news_encoder(clicked["title"].reshape(B * H, T), p, c).view(B, H, -1)
+    d_h = None if drop is None else dict(drop, n0=0)
+    d_c = None if drop is None else dict(drop, n0=B * H)
+    cv = tanr_news_encoder(cand["title"].reshape(B * C, T), p, c, drop=d_c).view(B, C, -1)
+    hv = tanr_news_encoder(clicked["title"].reshape(B * H, T), p, c, drop=d_h).view(B, H, -1)
     user = additive_attention(c.act(hv), p, "user_encoder.additive_attention", c)  # TANR/user_encoder.py:11-19
     logits = dot_product_click_predictor(cv, user)
     # :58-67  topic head over all B*(C+H) news vectors, class 0 has weight 0
@@ -365,13 +395,12 @@ def tanr_forward(cand, clicked, p, c: Contract = EXACT):
 # --------------------------------------------------------------------------- #
 # LSTUR  (reference: src/model/LSTUR/**)
 # --------------------------------------------------------------------------- #
-def lstur_news_encoder(news, p, c: Contract = EXACT, prefix="news_encoder"):
-    """src/model/LSTUR/news_encoder.py:32-76 (eval): [cat | subcat | title-CNN-pool]."""
+def lstur_news_encoder(news, p, c: Contract = EXACT, prefix="news_encoder", drop=None):
+    """src/model/LSTUR/news_encoder.py:32-76: [cat | subcat | title-CNN-pool] (drop: see cnn_text_encoder)."""
     catv = F.embedding(news["category"], p[f"{prefix}.category_embedding.weight"], padding_idx=0)
     subv = F.embedding(news["subcategory"], p[f"{prefix}.category_embedding.weight"], padding_idx=0)
-    x = embedding(news["title"], p[f"{prefix}.word_embedding.weight"], c)
-    y = title_cnn(x, p[f"{prefix}.title_CNN.weight"], p[f"{prefix}.title_CNN.bias"], c)
-    t = additive_attention(y, p, f"{prefix}.title_attention", c)
+    t = cnn_text_encoder(news["title"], p[f"{prefix}.word_embedding.weight"], p[f"{prefix}.title_CNN.weight"],
+                         p[f"{prefix}.title_CNN.bias"], p, f"{prefix}.title_attention", c, drop)
     return torch.cat([catv, subv, t], dim=1)
 
 
@@ -401,15 +430,21 @@ def gru_last_hidden(x, lengths, h0, p, prefix, c: Contract = EXACT):
     return h
 
 
-def lstur_forward(user, lengths, cand, clicked, p, method="ini", c: Contract = EXACT):
-    """src/model/LSTUR/__init__.py:44-87 in eval mode (dropout2d off) ==
-    get_user_vector path :89-108.  lengths==0 is clamped to 1 (user_encoder.py:27)."""
+def lstur_forward(user, lengths, cand, clicked, p, method="ini", c: Contract = EXACT, drop=None, user_keep=None):
+    """src/model/LSTUR/__init__.py:44-87.  drop=None, user_keep=None: eval mode (== the get_user_vector path :89-108).
+    drop=dict(p, seed): the title encoder's dropout with the kernels' masks; user_keep (B, 1): the multipliers of
+    F.dropout2d on the (1, B, dim) user embedding (:74-77) == whole user vectors dropped with masking_probability and the
+    rest scaled by 1/(1-p).  lengths==0 is clamped to 1 (user_encoder.py:27)."""
     B, C = cand["title"].shape[:2]
     H = clicked["title"].shape[1]
     flat = lambda d, n: {k: v.reshape(B * n, *v.shape[2:]) for k, v in d.items()}
-    cv = lstur_news_encoder(flat(cand, C), p, c).view(B, C, -1)
-    hv = lstur_news_encoder(flat(clicked, H), p, c).view(B, H, -1)
+    d_h = None if drop is None else dict(drop, n0=0)
+    d_c = None if drop is None else dict(drop, n0=B * H)
+    cv = lstur_news_encoder(flat(cand, C), p, c, drop=d_c).view(B, C, -1)
+    hv = lstur_news_encoder(flat(clicked, H), p, c, drop=d_h).view(B, H, -1)
     uemb = F.embedding(user, p["user_embedding.weight"], padding_idx=0)
+    if user_keep is not None:
+        uemb = uemb * user_keep.to(uemb.dtype)
     lengths = lengths.clamp(min=1)
     if method == "ini":
         uv = gru_last_hidden(hv, lengths, uemb, p, "user_encoder.gru", c)

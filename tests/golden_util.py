@@ -43,27 +43,28 @@ def t(g, key):
     return torch.from_numpy(g[key])
 
 
-def oracle_forward(case, g, p, contract=O.EXACT, fused=False):
+def oracle_forward(case, g, p, contract=O.EXACT, fused=False, drop=None, user_keep=None):
     """Runs the oracle on a golden case's inputs.  Returns (logits, topic_loss or None).
     fused: the NRMS news level runs through the one-kernel front end (V / context as hi/lo bf16 pairs)."""
     cand_t, clicked_t = t(g, "cand_title"), t(g, "clicked_title")
     if case == "nrms":
         c_news = O.BF16_FUSED if (contract.bf16 and fused) else contract
-        return O.nrms_forward(cand_t, clicked_t, p, 15, contract, c_news=c_news), None
+        return O.nrms_forward(cand_t, clicked_t, p, 15, contract, c_news=c_news, drop=drop), None
     if case.startswith("naml"):
         cand = dict(title=cand_t, abstract=t(g, "cand_abstract"), category=t(g, "cand_category"),
                     subcategory=t(g, "cand_subcategory"))
         clicked = dict(title=clicked_t, abstract=t(g, "clicked_abstract"), category=t(g, "clicked_category"),
                        subcategory=t(g, "clicked_subcategory"))
-        return O.naml_forward(cand, clicked, p, contract), None
+        return O.naml_forward(cand, clicked, p, contract, drop=drop), None
     if case == "tanr":
         cand = dict(title=cand_t, category=t(g, "cand_category"))
         clicked = dict(title=clicked_t, category=t(g, "clicked_category"))
-        return O.tanr_forward(cand, clicked, p, contract)
+        return O.tanr_forward(cand, clicked, p, contract, drop=drop)
     method = case.split("_")[1]
     cand = dict(title=cand_t, category=t(g, "cand_category"), subcategory=t(g, "cand_subcategory"))
     clicked = dict(title=clicked_t, category=t(g, "clicked_category"), subcategory=t(g, "clicked_subcategory"))
-    return O.lstur_forward(t(g, "user"), t(g, "clicked_news_length"), cand, clicked, p, method, contract), None
+    return O.lstur_forward(t(g, "user"), t(g, "clicked_news_length"), cand, clicked, p, method, contract, drop=drop,
+                           user_keep=user_keep), None
 
 
 def grad_summary(gt: torch.Tensor, key: str):

@@ -728,3 +728,70 @@ def check_golden(case, fused=False):
     w = grads.get("news_encoder.word_embedding.weight", grads.get("news_encoder.text_encoders.title.word_embedding.weight"))
     res["emb_row0_grad_zero"] = bool((w.grad[0] == 0).all())
     return res
+
+
+def check_train_masked(case, p_drop=0.2, mask_p=0.5):
+    """TRAIN mode of a CNN family (NAML / TANR / LSTUR) on its golden inputs, forward AND backward, against the oracle under
+    the SAME dropout masks (see check_nrms_train_masked): one seed per text-encoder call (NAML: title, then abstract), masks
+    over the zero-padded gather layout and the compact conv-output layout.  LSTUR's user masking (F.dropout2d on the
+    (1, B, dim) user embedding, LSTUR/__init__.py:74-77) is drawn by torch.rand on the device generator: the test seeds it,
+    reads the draw the model is going to make, re-seeds and hands the same keep-multipliers to the oracle."""
+    from golden_util import case_params, case_shapes, load_case, oracle_forward, unique_params
+    from newsrec_b200 import ops
+    g = load_case(case)
+    model, cfg = build_model(case, dropout=p_drop)
+    sd = O.tie_shared(O.det_state_dict(case_shapes(case), int(g["seed"])))
+    model.load_state_dict(sd)
+    model.train()
+    cand, clicked = golden_inputs(case, g)
+    B = g["cand_title"].shape[0]
+    user_keep = None
+    if case.startswith("lstur"):
+        cfg.masking_probability = mask_p
+        torch.cuda.manual_seed(1234)
+        user_keep = ((torch.rand(B, 1, device=DEV) >= mask_p).float() / (1.0 - mask_p)).cpu()
+        torch.cuda.manual_seed(1234)
+    if case.startswith("naml"):
+        s1, s2 = ops.peek_seeds(2)
+        drop = dict(p=p_drop, seeds={"title": s1, "abstract": s2})
+    else:
+        drop = dict(p=p_drop, seed=ops.peek_seeds(1)[0])
+    tw = lambda t: (0.1 * t if t is not None else 0.0)
+    p_b = case_params(case, g)
+    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, drop=drop, user_keep=user_keep)
+    (O.click_loss(logits_b) + tw(topic_b)).backward()
+    p_x = case_params(case, g)
+    logits_x, topic_x = oracle_forward(case, g, p_x, O.EXACT, drop=drop, user_keep=user_keep)
+    (O.click_loss(logits_x) + tw(topic_x)).backward()
+    with torch.no_grad():
+        logits_eval, _ = oracle_forward(case, g, case_params(case, g, requires_grad=False), O.EXACT)
+    if case.startswith("lstur"):
+        out = model(torch.from_numpy(g["user"]), torch.from_numpy(g["clicked_news_length"]).clone(), cand, clicked)
+    else:
+        out = model(cand, clicked)
+    logits, topic = (out if isinstance(out, tuple) else (out, None))
+    loss = torch.nn.functional.cross_entropy(logits, torch.zeros(logits.shape[0], dtype=torch.long, device=DEV))
+    (loss + tw(topic)).backward()
+    torch.cuda.synchronize()
+    res = {"logits_vs_masked_oracle": relerr(logits, logits_b), "logits_vs_masked_exact_fp32": relerr(logits, logits_x),
+           "masked_oracle_vs_masked_exact": relerr(logits_b, logits_x), "masks_matter": relerr(logits_x, logits_eval)}
+    if topic is not None:
+        res["topic_loss_rel_vs_masked_exact"] = abs(topic.item() - float(topic_x)) / abs(float(topic_x))
+    grads = dict(model.named_parameters())
+    gscale = max(float(v.grad.norm()) for v in unique_params(p_x).values())
+    worst_ratio, worst_key = 0.0, ""
+    for k, prm in unique_params(p_x).items():
+        if grads[k].grad is None:
+            res["missing_grad:" + k] = True
+            continue
+        if prm.grad.norm() < 1e-4 * gscale:
+            continue
+        e_kernel = relerr(grads[k].grad, prm.grad)
+        e_contract = relerr(unique_params(p_b)[k].grad, prm.grad)
+        res["grad:" + k] = [e_kernel, e_contract]
+        ratio = e_kernel / max(e_contract, 2e-3)
+        if ratio > worst_ratio:
+            worst_ratio, worst_key = ratio, k
+    res["worst_grad_ratio_kernel_over_contract"] = worst_ratio
+    res["worst_grad_key"] = worst_key
+    return res

@@ -100,7 +100,7 @@ def test_fused_news_front_end(kw):
     assert r["out_vs_oracle"] < 1e-3 and r["w_sums_to_one"] < 1e-5, r
 
 
-@pytest.mark.parametrize("kw", [dict(B=37, S=50), dict(B=300, S=50), dict(B=5, S=7, D=450, Hd=900), dict(B=9, S=12, D=900, Hd=450),
+@pytest.mark.parametrize("kw", [dict(B=37, S=50), dict(B=300, S=50), dict(B=5, S=7, D=600, Hd=900), dict(B=9, S=12, D=900, Hd=450),
                                 dict(B=700, S=6)])
 def test_gru_last_hidden_history_50_mixed_lengths(kw):
     """BASELINE.json configs[3] shapes (history 50, D = Hd = 900): the persistent recurrence kernel (one cooperative launch

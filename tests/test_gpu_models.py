@@ -81,6 +81,20 @@ def test_nrms_train_mode_matches_masked_oracle(fused):
     assert r["emb_row0_grad_zero"], r
 
 
+@pytest.mark.parametrize("case", ["naml", "naml_f400", "tanr", "lstur_ini", "lstur_con"])
+def test_cnn_families_train_mode_match_masked_oracle(case):
+    """Train mode of NAML / TANR / LSTUR (both dropout sites of every text encoder, and LSTUR's whole-vector user masking),
+    forward and backward, against the oracle under the kernels' own masks."""
+    r = G.check_train_masked(case)
+    assert r["masks_matter"] > 0.02, r
+    assert r["logits_vs_masked_oracle"] < 1e-3, r
+    assert r["logits_vs_masked_exact_fp32"] < 1.25 * r["masked_oracle_vs_masked_exact"] + 1e-4, r
+    assert r["worst_grad_ratio_kernel_over_contract"] < 1.5, r
+    assert not any(k.startswith("missing_grad:") for k in r), r
+    if "topic_loss_rel_vs_masked_exact" in r:
+        assert r["topic_loss_rel_vs_masked_exact"] < 2e-3, r
+
+
 def test_nrms_full_size_properties():
     """BASELINE.json configs[1] sizes (batch 512): permutation equivariance and sub-batch consistency hold to fp32
     accumulation-order noise (six titles share one 128-row score tile in the fused front end: which titles are tile mates
