@@ -100,6 +100,15 @@ int nr_dot_score_fwd(const float* cand, const float* user, int B, int C, int D, 
 int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
                      float* duser, void* stream);
 
+/* Batched form of the evaluator's scoring loop (src/evaluate.py:245-265 calls get_prediction once per impression and
+ * synchronises on .tolist() each time): the news vectors live in ONE device matrix news[n_news][D]; the candidates of
+ * impression s are cand[seg_offsets[s] .. seg_offsets[s+1]) (indices into news), user[s] its user vector;
+ * scores[i] = news[cand[i]] . user[s].  seg_offsets has n_seg + 1 entries (int64, device), seg_offsets[0] = 0.
+ * *bad_id_flag is set if a candidate index is outside [0, n_news). */
+int nr_segment_dot(const float* news, long long n_news, int D, const long long* cand, long long n_cand,
+                   const long long* seg_offsets, long long n_seg, const float* user, float* scores, int* bad_id_flag,
+                   void* stream);
+
 /* Host-side glue of the weight-gradient GEMMs (nr_gemm_tn with the ones column): ext is [rows][ld] fp32 whose columns
  * [0,D) hold dW and column D holds db.  Adds them into the parameters' own gradient storage (dW [rows][D] contiguous,
  * db [rows] or null) and CLEARS ext, so the caller can keep it as a persistent accumulator across steps. */

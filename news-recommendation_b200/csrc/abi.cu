@@ -123,6 +123,13 @@ int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits,
 
 int nr_mhsa_fused_supported(int T, int d, int heads) { return mhsa_fused_supported(T, d, heads); }
 
+int nr_segment_dot(const float* news, long long n_news, int D, const long long* cand, long long n_cand, const long long* seg_offsets,
+                   long long n_seg, const float* user, float* scores, int* bad_id_flag, void* stream) {
+    NR_REQUIRE(news && cand && seg_offsets && user && scores && bad_id_flag && n_seg >= 1 && D >= 1 && n_cand >= 0,
+               "nr_segment_dot: null operand or empty problem");
+    return segment_dot(news, n_news, D, cand, n_cand, seg_offsets, n_seg, user, scores, bad_id_flag, S(stream));
+}
+
 int nr_accumulate_ext_grad(float* ext, int rows, int ld, int D, float* dW, float* db, void* stream) {
     NR_REQUIRE(ext && dW && rows >= 0 && D >= 1, "nr_accumulate_ext_grad: null operand");
     return accumulate_ext_grad(ext, rows, ld, D, dW, db, S(stream));

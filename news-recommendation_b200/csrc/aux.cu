@@ -485,4 +485,53 @@ int dot_score_bwd(const float* cand, const float* user, const float* dlogits, in
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// evaluation stage 3, batched (reference src/evaluate.py:245-265 scores ONE impression per get_prediction call and
+// synchronises on .tolist() after each): scores[i] = news[cand[i]] . user[seg(i)] for the candidates of MANY impressions
+// in one launch.  The news vectors stay in ONE device matrix (row = news index) instead of a Python dict of rows;
+// seg_offsets[s] .. seg_offsets[s+1] delimit the candidates of impression s.  One warp per candidate, 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+__global__ void segment_dot_kernel(const float* __restrict__ news, long long n_news, int D, const long long* __restrict__ cand,
+                                   long long n_cand, const long long* __restrict__ seg_offsets, long long n_seg,
+                                   const float* __restrict__ user, float* __restrict__ scores, int* __restrict__ bad_flag) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long i = w0; i < n_cand; i += nw) {
+        long long lo = 0, hi = n_seg;  // the impression of candidate i: last s with seg_offsets[s] <= i
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldg(seg_offsets + mid) <= i) lo = mid; else hi = mid;
+        }
+        long long nid = __ldg(cand + i);
+        if (nid < 0 || nid >= n_news) {
+            if (lane == 0) atomicExch(bad_flag, 1);
+            nid = 0;
+        }
+        const float* nv = news + nid * D;
+        const float* uv = user + lo * D;
+        float acc = 0.f;
+        if ((D & 3) == 0) {
+            for (int c = lane * 4; c < D; c += 128) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(nv + c)), b = __ldg(reinterpret_cast<const float4*>(uv + c));
+                acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+            }
+        } else {
+            for (int c = lane; c < D; c += 32) acc = fmaf(nv[c], uv[c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) scores[i] = acc;
+    }
+}
+int segment_dot(const float* news, long long n_news, int D, const long long* cand, long long n_cand, const long long* seg_offsets,
+                long long n_seg, const float* user, float* scores, int* bad_flag, cudaStream_t stream) {
+    if (n_cand == 0) return 0;
+    ProfScope ps("segment_dot", static_cast<int>(n_cand), static_cast<int>(n_seg), D, stream);
+    const int blocks = static_cast<int>(std::min<long long>((n_cand + 7) / 8, 148 * 16));
+    segment_dot_kernel<<<blocks, 256, 0, stream>>>(news, n_news, D, cand, n_cand, seg_offsets, n_seg, user, scores, bad_flag);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace nr

@@ -297,7 +297,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int chunk0 = ks * p.chunks_per_slice;
     const int n_my = max(0, min(p.chunks_per_slice, total_chunks - chunk0));
     const int nb_pad = (p.Nb + 15) & ~15;
-    const int n0 = min(256, nb_pad);
+    // more than 256 columns take two MMAs per k-step: split them near the middle, on a 64-column box boundary -- a single-CTA
+    // tcgen05.mma costs >= 86 cycles whatever its N (tools/mmabench_small.cu), so 256 + 48 is 128 + 86 cycles where 192 + 112
+    // is 96 + 86
+    const int n0 = nb_pad <= 256 ? nb_pad : (((nb_pad >> 1) + 63) & ~63);
     const int n1 = nb_pad - n0;
     const uint32_t tmem_cols = nb_pad > 256 ? 512u : (nb_pad > 128 ? 256u : (nb_pad > 64 ? 128u : (nb_pad > 32 ? 64u : 32u)));
 
@@ -352,11 +355,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sb = sa + 2 * 8192;
                     const uint64_t da = make_sw128_desc(sa, 8192, 1024);
                     const uint64_t db0 = make_sw128_desc(sb, 8192, 1024);
-                    const uint64_t db1 = make_sw128_desc(sb + 4 * 8192, 8192, 1024);
+                    const uint64_t db1 = make_sw128_desc(sb + (n0 >> 6) * 8192, 8192, 1024);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // +2048 bytes per k-step = +128 in the descriptor's >>4 address field
                         umma_bf16(tmem_base, da + 128 * k, db0 + 128 * k, idesc0, (k == 0) ? acc : 1u);
-                        if (n1 > 0) umma_bf16(tmem_base + 256, da + 128 * k, db1 + 128 * k, idesc1, (k == 0) ? acc : 1u);
+                        if (n1 > 0) umma_bf16(tmem_base + n0, da + 128 * k, db1 + 128 * k, idesc1, (k == 0) ? acc : 1u);
                     }
                     umma_commit(&empty[st]);
                 }

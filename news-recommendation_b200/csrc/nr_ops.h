@@ -91,6 +91,10 @@ int gru_persistent_supported(int B, int Hd);
 int gru_fwd_persistent(int B, int S, int Hd, int ldh, int ldg, const float* gi, const void* whh, const float* bhh, const float* h0,
                        const long long* len, float* gh, float* hs, void* hb, float* out, cudaStream_t stream);
 
+// scores[i] = news[cand[i]] . user[s] for seg_offsets[s] <= i < seg_offsets[s+1]  (batched evaluate.py:245-265)
+int segment_dot(const float* news, long long n_news, int D, const long long* cand, long long n_cand, const long long* seg_offsets,
+                long long n_seg, const float* user, float* scores, int* bad_flag, cudaStream_t stream);
+
 int num_sms();
 
 // ---- live per-kernel timing (bench.py): CUDA events on the launching stream around every kernel ------

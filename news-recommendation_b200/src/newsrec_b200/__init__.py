@@ -114,6 +114,7 @@ SIGNATURES = {
     "nr_additive_attention_bwd": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i,
                                         _vp, _vp, _vp, _ll, _vp]),
     "nr_dot_score_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nr_segment_dot": (_i, [_vp, _ll, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp]),
     "nr_accumulate_ext_grad": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "nr_dot_score_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nr_mhsa_encoder_fwd": (_i, [C.POINTER(MhsaEncoderFwdArgs), _vp]),

@@ -400,3 +400,28 @@ class MhsaFn(torch.autograd.Function):
         gW = [dW[i * d:(i + 1) * d, :d].contiguous() for i in range(3)]
         gb = [dW[i * d:(i + 1) * d, d].contiguous() for i in range(3)]
         return dx.view(N, T, d), gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# Batched scoring for evaluation (the "next" row N2 of SURVEY.md 8f)
+# ---------------------------------------------------------------------------------------------------
+def predict_impressions(news_matrix, cand_index, seg_offsets, user_vectors):
+    """Scores of MANY impressions in one launch: reference src/evaluate.py:245-265 runs `get_prediction` once per impression
+    and synchronises on `.tolist()` after each.  news_matrix (n_news, D) fp32 device matrix of news vectors (row = news
+    index, instead of the evaluator's dict of rows), cand_index (n_cand,) int64 rows of the candidates of all impressions
+    back to back, seg_offsets (n_impressions + 1,) int64 with seg_offsets[0] = 0, user_vectors (n_impressions, D).
+    Returns (n_cand,) fp32 scores; candidate i of impression s is scores[seg_offsets[s] + i]."""
+    lib = load_library()
+    dev = require_cuda()
+    news_matrix = news_matrix.to(dev).float().contiguous()
+    user_vectors = user_vectors.to(dev).float().contiguous()
+    cand_index = cand_index.to(dev).long().contiguous()
+    seg_offsets = seg_offsets.to(dev).long().contiguous()
+    n_seg = seg_offsets.numel() - 1
+    if user_vectors.shape[0] != n_seg or user_vectors.shape[1] != news_matrix.shape[1]:
+        raise NewsrecError("predict_impressions: user_vectors must be (len(seg_offsets) - 1, D)")
+    scores = torch.empty((cand_index.numel(),), dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.nr_segment_dot(_p(news_matrix), news_matrix.shape[0], news_matrix.shape[1], _p(cand_index), cand_index.numel(),
+                             _p(seg_offsets), n_seg, _p(user_vectors), _p(scores), _p(flag), _stream()), "nr_segment_dot")
+    return scores

@@ -795,3 +795,22 @@ def check_train_masked(case, p_drop=0.2, mask_p=0.5):
     res["worst_grad_ratio_kernel_over_contract"] = worst_ratio
     res["worst_grad_key"] = worst_key
     return res
+
+
+def check_predict_impressions(n_news=500, D=300, n_imp=200, seed=3):
+    """Batched evaluation scoring (ops.predict_impressions) against the evaluator's per-impression get_prediction loop."""
+    from newsrec_b200.ops import predict_impressions
+    model, _ = nrms_model_and_params(50, 1)
+    news = O.det_uniform((n_news, D), seed).to(DEV)
+    users = O.det_uniform((n_imp, D), seed + 1).to(DEV)
+    counts = O.det_randint((n_imp,), seed + 2, 1, 40)
+    offs = torch.zeros(n_imp + 1, dtype=torch.int64)
+    offs[1:] = counts.cumsum(0)
+    cand = O.det_randint((int(offs[-1]),), seed + 3, 0, n_news)
+    got = predict_impressions(news, cand, offs, users)
+    ref = []
+    for s in range(n_imp):  # evaluate.py:245-260
+        idx = cand[offs[s]:offs[s + 1]].to(DEV)
+        ref.append(model.get_prediction(news[idx], users[s]))
+    ref = torch.cat(ref)
+    return {"rel": relerr(got, ref), "n": int(got.numel())}

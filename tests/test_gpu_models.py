@@ -113,3 +113,8 @@ def test_out_of_range_token_id_is_reported():
         model.get_news_vector({"title": ids})
     with pytest.raises(IndexError):
         model.check_ids()
+
+
+def test_batched_impression_scoring_matches_per_impression_get_prediction():
+    r = G.check_predict_impressions()
+    assert r["rel"] < 1e-6 and r["n"] > 1000, r
