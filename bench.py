@@ -463,7 +463,13 @@ def main():
         val, ms, cores, kind = run_reference(model_name, ref_batch, 2, 1, F)
         out["cpu_baseline"] = {"value": val, "unit": "impressions/s", "cores": cores, "kind": "port",
                                "sample": f"2 steps of {ref_batch} impressions after 1 warm-up (same shapes, same batch); {kind}; {ms:.0f} ms/step"}
-    print(json.dumps(out), flush=True)
+    line = json.dumps(out)
+    print(line, flush=True)
+    try:  # belt and braces for launchers that hand the ranks a stdout which is gone by now: the line also goes to a file
+        with open(os.path.join(ROOT, "gpurun_out", f"bench_last_n{world}.json"), "w") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
 
 
 if __name__ == "__main__":

@@ -47,6 +47,9 @@ void nr_debug_set_gemm_timing(void* dev_buf, int slots);
  * per CTA, cycle counters of its warp roles (epilogue groups [0..6], [8..14]; gather [16,17]; weight producer [20];
  * tcgen05 issuer [24..29]).  Null (default) switches the counters off. */
 void nr_debug_set_fused_timing(void* dev_buf);
+/* Data parallel: the weight-gradient GEMMs (nr_gemm_tn and the composites' internal calls) leave n SMs free, so that the
+ * channel CTAs of a gradient all-reduce running on a side stream have somewhere to run (0 = use every SM, the default). */
+void nr_reserve_sms_for_comm(int n);
 /* Live per-kernel timing for bench.py: CUDA events on the launching stream around every kernel of this
  * library.  nr_profile_report writes JSON {"<context>/<op>[shape]": [launches, total_ms], ...}, returns its
  * length (or -1 if cap is too small) and clears the records.  Off by default. */

@@ -12,6 +12,7 @@ void set_debug_simt_gemm(int on);
 int has_triage_backends();
 void set_debug_gemm_timing(void* dev_buf, int slots);
 void set_debug_fused_timing(void* dev_buf);
+void set_comm_reserved_sms(int n);
 extern int g_launches;
 }  // namespace nr
 
@@ -30,6 +31,7 @@ long long nr_launch_count(void) { return g_launches; }
 int nr_num_sms(void) { return num_sms(); }
 void nr_debug_set_simt_gemm(int on) { set_debug_simt_gemm(on); }
 int nr_has_triage_backends(void) { return has_triage_backends(); }
+void nr_reserve_sms_for_comm(int n) { set_comm_reserved_sms(n); }
 void nr_debug_set_gemm_timing(void* dev_buf, int slots) { set_debug_gemm_timing(dev_buf, slots); }
 void nr_debug_set_fused_timing(void* dev_buf) { set_debug_fused_timing(dev_buf); }
 void nr_profile_enable(int on) { prof_enable(on); }

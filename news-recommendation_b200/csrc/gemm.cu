@@ -419,6 +419,12 @@ __global__ void gemm_tn_simt_kernel(const __nv_bfloat16* A, int lda, const __nv_
 }
 #endif
 
+// SMs the split-K weight-gradient GEMM leaves free (set by a data-parallel caller): the all-reduce of the embedding gradient
+// is issued on a side stream right before this GEMM, and NCCL's channel CTAs need SMs to run on -- with every SM holding a
+// 200 KB gemm_tn CTA the "overlapped" reduction simply waited for the GEMM to finish (2 GPUs: +0.27 ms per step, unchanged).
+static int g_comm_reserved_sms = 0;
+void set_comm_reserved_sms(int n) { g_comm_reserved_sms = n < 0 ? 0 : n; }
+
 int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, int b_rows, int b_cols, int ldb,
                        int b_col0, int Nb, int b_row_shift, float* D, int ldd, cudaStream_t stream) {
     NR_REQUIRE(Nb >= 1 && Nb <= 512 && Ma >= 1 && Kr >= 0, "gemm_tn: bad shape Kr=%d Ma=%d Nb=%d", Kr, Ma, Nb);
@@ -443,8 +449,8 @@ int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, in
         return 0;
     }
 #endif
-    const int sms = num_sms();
-    NR_REQUIRE(sms > 0, "no CUDA device");
+    NR_REQUIRE(num_sms() > 0, "no CUDA device");
+    const int sms = std::max(num_sms() / 2, num_sms() - g_comm_reserved_sms);
     p.m_tiles = ceil_div(Ma, 128);
     const int total_chunks = ceil_div(Kr, 64);
     int k_slices = std::max(1, std::min(sms / p.m_tiles, total_chunks));

@@ -97,6 +97,7 @@ SIGNATURES = {
     "nr_num_sms": (_i, []),
     "nr_debug_set_simt_gemm": (None, [_i]),
     "nr_has_triage_backends": (_i, []),
+    "nr_reserve_sms_for_comm": (None, [_i]),
     "nr_debug_set_gemm_timing": (None, [_vp, _i]),
     "nr_debug_set_fused_timing": (None, [_vp]),
     "nr_profile_enable": (None, [_i]),

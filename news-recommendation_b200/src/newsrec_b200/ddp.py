@@ -76,6 +76,9 @@ class FlatGradients:
             self._event.record()  # materialises the cudaEvent_t handle the backward records into
             ops.grad_ready_hook["event"] = self._event
             ops.grad_ready_hook["recorded"] = False
+            # NCCL's channel CTAs need SMs while the weight-gradient GEMM runs (it would otherwise hold all of them)
+            from . import load_library
+            load_library().nr_reserve_sms_for_comm(int(os.environ.get("NEWSREC_COMM_SMS", "20")))
 
     def zero(self):
         self.flat.zero_()
