@@ -280,6 +280,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="impressions per GPU per step (BASELINE.json configs[1])")
     ap.add_argument("--ref-batch", type=int, default=0, help="impressions per CPU step of the reference arm (0 = --batch: same configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="tuning: device-resident timing only (prints a short JSON line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(min(args.warmup, 1), 1)
     model_name = args.model
@@ -397,6 +398,16 @@ def main():
     log(f"rank {rank}/{world}: {model_name} + data ready; timing device-resident steps")
     with ClockSampler(local) as clk:
         ms_total, launches = timed(dev_batches, read_loss=False)
+    if args.quick:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+            torch.distributed.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms_total / args.steps,
+                              "value": B * world * args.steps / (ms_total / 1e3),
+                              "env": {k: os.environ.get(k) for k in ("NEWSREC_COMM_SMS", "NCCL_MAX_NCHANNELS", "NCCL_MIN_NCHANNELS")}}), flush=True)
+        return
     log(f"device-resident: {ms_total / args.steps:.3f} ms/step; per-kernel pass")
     timed(dev_batches, read_loss=False, profile=True)  # separate pass: the event pairs around every launch stay out of `value`
     prof = newsrec_b200.profile_report()
