@@ -78,7 +78,7 @@ class FlatGradients:
             ops.grad_ready_hook["recorded"] = False
             # NCCL's channel CTAs need SMs while the weight-gradient GEMM runs (it would otherwise hold all of them)
             from . import load_library
-            load_library().nr_reserve_sms_for_comm(int(os.environ.get("NEWSREC_COMM_SMS", "20")))
+            load_library().nr_reserve_sms_for_comm(int(os.environ.get("NEWSREC_COMM_SMS", "32")))
 
     def zero(self):
         self.flat.zero_()

@@ -95,12 +95,14 @@ class _RoundHiLo(torch.autograd.Function):
 class Contract:
     bf16: bool = False
     hilo: bool = False     # fused news front end (csrc/fused_fwd.cu): V and the context are hi/lo bf16 pairs
+    acts: bool = True      # False: ONLY parameters / embeddings are rounded to bf16, every activation and gradient stays fp32
+                           # (the tolerance definition of SURVEY.md 7.3-5: "the fp32 oracle on bf16-rounded weights/embeddings")
 
     def act(self, x):      # an activation the kernels store in bf16 (and whose grad they store in bf16)
-        return _RoundBoth.apply(x) if self.bf16 else x
+        return _RoundBoth.apply(x) if (self.bf16 and self.acts) else x
 
     def act_hilo(self, x):  # an activation the fused kernels keep as a hi/lo bf16 pair (plain bf16 on the unfused path)
-        if self.bf16 and self.hilo:
+        if self.bf16 and self.hilo and self.acts:
             return _RoundHiLo.apply(x)
         return self.act(x)
 
@@ -108,12 +110,13 @@ class Contract:
         return _RoundFwd.apply(x) if self.bf16 else x
 
     def grad(self, x):     # an fp32 value whose gradient the kernels store in bf16
-        return _RoundGrad.apply(x) if self.bf16 else x
+        return _RoundGrad.apply(x) if (self.bf16 and self.acts) else x
 
 
 EXACT = Contract(False)
 BF16 = Contract(True)
 BF16_FUSED = Contract(True, True)
+WEIGHTS_BF16 = Contract(True, False, False)   # bf16 operands (weights, embedding table), fp32 everything else
 
 
 # --------------------------------------------------------------------------- #
@@ -177,7 +180,7 @@ def scaled_dot_product_attention(Q, K, V, c: "Contract" = None):
     scores = torch.exp(raw / math.sqrt(d_k))
     attn = scores / (torch.sum(scores, dim=-1, keepdim=True) + 1e-8)
     if c is not None:
-        attn = c.operand(attn)
+        attn = c.operand(attn) if c.acts else attn  # P is an activation: it stays fp32 under the weights-only contract
     return torch.matmul(attn, V)
 
 
@@ -217,7 +220,7 @@ def additive_attention(x, p, prefix, c: Contract = EXACT):
     w.r.t. the pre-activation is stored bf16.
     """
     w = c.operand(p[f"{prefix}.linear.weight"])
-    xs = c.operand(x) if (c.bf16 and c.hilo) else x  # hi/lo input: the score GEMM reads the hi plane, the pooled sum both
+    xs = c.operand(x) if (c.bf16 and c.hilo and c.acts) else x  # hi/lo input: the score GEMM reads the hi plane, the pooled sum both
     pre = c.grad(F.linear(xs, w) + p[f"{prefix}.linear.bias"])
     temp = torch.tanh(pre)
     weights = F.softmax(torch.matmul(temp, p[f"{prefix}.attention_query_vector"]), dim=1)
@@ -385,7 +388,7 @@ def tanr_forward(cand, clicked, p, c: Contract = EXACT, drop=None):
     logits = dot_product_click_predictor(cv, user)
     # :58-67  topic head over all B*(C+H) news vectors, class 0 has weight 0
     allv = torch.cat((cv, hv), dim=1).reshape(-1, cv.shape[-1])
-    y_pred = c.grad(F.linear(c.operand(allv), c.operand(p["topic_predictor.weight"])) + p["topic_predictor.bias"])
+    y_pred = c.grad(F.linear(c.operand(allv) if c.acts else allv, c.operand(p["topic_predictor.weight"])) + p["topic_predictor.bias"])
     y = torch.cat((cand["category"], clicked["category"]), dim=1).flatten()
     class_weight = torch.ones(y_pred.shape[1], dtype=y_pred.dtype)
     class_weight[0] = 0
@@ -416,10 +419,10 @@ def gru_last_hidden(x, lengths, h0, p, prefix, c: Contract = EXACT):
     w_hh = c.operand(p[f"{prefix}.weight_hh_l0"])
     b_ih, b_hh = p[f"{prefix}.bias_ih_l0"], p[f"{prefix}.bias_hh_l0"]
     Hd = w_hh.shape[1]
-    gi_all = c.grad(F.linear(c.operand(x), w_ih) + b_ih)  # (B,S,3Hd); dX = dGI.W_ih stays fp32
+    gi_all = c.grad(F.linear(c.operand(x) if c.acts else x, w_ih) + b_ih)  # (B,S,3Hd); dX = dGI.W_ih stays fp32
     h = h0
     for t in range(S):
-        gh = c.grad(F.linear(c.operand(h) if c.bf16 else h, w_hh) + b_hh)
+        gh = c.grad(F.linear(c.operand(h) if (c.bf16 and c.acts) else h, w_hh) + b_hh)
         gi = gi_all[:, t]
         r = torch.sigmoid(gi[:, :Hd] + gh[:, :Hd])
         z = torch.sigmoid(gi[:, Hd:2 * Hd] + gh[:, Hd:2 * Hd])

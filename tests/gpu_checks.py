@@ -699,7 +699,10 @@ def check_golden(case, fused=False):
     loss = torch.nn.functional.cross_entropy(logits, torch.zeros(logits.shape[0], dtype=torch.long, device=DEV))
     (loss + (0.1 * topic if topic is not None else 0.0)).backward()
     torch.cuda.synchronize()
+    with torch.no_grad():  # the blueprint's tolerance definition: fp32 oracle on bf16-rounded weights / embeddings
+        logits_w, _ = oracle_forward(case, g, case_params(case, g, requires_grad=False), O.WEIGHTS_BF16)
     res = {"logits_vs_oracle_bf16": relerr(logits, logits_b), "logits_vs_reference_fp32": relerr(logits, torch.from_numpy(g["logits"])),
+           "logits_vs_weights_only_oracle": relerr(logits, logits_w),
            "oracle_bf16_vs_reference_fp32": relerr(logits_b, torch.from_numpy(g["logits"])),
            "loss_abs_vs_reference": abs(loss.item() - float(g["loss"]))}
     if topic is not None:

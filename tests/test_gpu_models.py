@@ -14,12 +14,20 @@ import gpu_checks as G
 
 pytestmark = pytest.mark.gpu
 CASES = ["nrms", "naml", "naml_f400", "tanr", "lstur_ini", "lstur_con"]
+# Norm-wise error of the logits against the fp32 oracle evaluated on bf16-rounded weights / embeddings -- the tolerance
+# definition of the blueprint, target 1e-3.  The CNN families meet it.  NRMS does not on the default path:
+# its error is the bf16 storage of V and of the attention context (every token of a title sees the SAME rounding error of
+# V_j, so the pooling does not average it out -- DESIGN.md 3a); the precise mode (hi/lo V / context) removes that part and
+# is left with the bf16 probabilities.  LSTUR's error is the bf16 hidden state fed back 6..50 times.  The bounds are the
+# measured values with ~30 % head room, so that a regression shows.
+WEIGHTS_ONLY_BOUND = {"nrms": 8e-3, "naml": 1e-3, "naml_f400": 1e-3, "tanr": 1e-3, "lstur_ini": 3e-3, "lstur_con": 1.5e-3}
 
 
 @pytest.mark.parametrize("case", CASES)
 def test_golden_case(case):
     r = G.check_golden(case)
     assert r["logits_vs_oracle_bf16"] < 1e-3, r
+    assert r["logits_vs_weights_only_oracle"] < WEIGHTS_ONLY_BOUND[case], r
     assert r["logits_vs_reference_fp32"] < 2e-2, r
     assert r["logits_vs_reference_fp32"] < 1.25 * r["oracle_bf16_vs_reference_fp32"] + 1e-4, r
     assert r["worst_grad_ratio_kernel_over_contract"] < 1.5, r
@@ -34,6 +42,7 @@ def test_nrms_precise_mode_golden_case():
     against its own storage contract, and a tighter bound against the reference's fp32 outputs (measured 2.6e-3 vs 7.3e-3)."""
     r = G.check_golden("nrms", fused=True)
     assert r["logits_vs_oracle_bf16"] < 1e-3, r
+    assert r["logits_vs_weights_only_oracle"] < 2.5e-3, r                 # measured 1.8e-3 (default path: 6.3e-3)
     assert r["logits_vs_reference_fp32"] < 4e-3, r
     assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
 
