@@ -157,6 +157,12 @@ typedef struct {
     const void* wqkv_heads_bf16; /* [heads*64][ldx]: per head the rows W_Q[h] | W_K[h] | W_V[h] | zero rows up to 64 */
     const float* bqkv_heads;     /* [heads*64] biases in the same order                                */
     void* C_lo_bf16;             /* [n_seq*T][ldx]                                                      */
+    /* precise DENSE variant (user encoder of the precise mode; selected by dense != NULL and C_lo_bf16 != NULL): the fp32
+     * input enters the projection as a hi/lo bf16 pair against K-concatenated weights, Q|K|V stays fp32, the attention runs
+     * in fp32 on the CUDA cores, the context leaves as hi (C_bf16) + lo (C_lo_bf16) planes.  QKV_bf16 must be NULL. */
+    const void* wqkv_kcat_bf16;  /* [3d][2*ldx]: columns [0,d) = W, [ldx, ldx+d) = W again, zeros elsewhere            */
+    void* X_kcat_bf16;           /* [n_seq*T][2*ldx] workspace: hi | lo operand rows                                   */
+    float* QKV_f32;              /* [n_seq*T][3d] workspace                                                            */
 } nr_mhsa_encoder_fwd_args;
 int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream);
 /* 1 if the fused front end handles (tokens per title, model width, heads): the reference's news level, T = 20, d_k = 20 */

@@ -154,7 +154,8 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
     const bool fused = a->ids != nullptr && a->wqkv_heads_bf16 != nullptr && a->bqkv_heads != nullptr && a->C_lo_bf16 != nullptr &&
                        mhsa_fused_supported(a->T, a->d, a->heads);
     NR_REQUIRE(a->wa_bf16 && a->ba && a->qv && a->C_bf16 && a->w && a->out, "nr_mhsa_encoder_fwd: null operand");
-    NR_REQUIRE(fused || (a->wqkv_bf16 && a->bqkv && a->X_bf16 && a->QKV_bf16), "nr_mhsa_encoder_fwd: null operand");
+    const bool precise_dense = a->dense != nullptr && a->C_lo_bf16 != nullptr;
+    NR_REQUIRE(fused || precise_dense || (a->wqkv_bf16 && a->bqkv && a->X_bf16 && a->QKV_bf16), "nr_mhsa_encoder_fwd: null operand");
     NR_REQUIRE(!fused || a->QKV_bf16 == nullptr, "nr_mhsa_encoder_fwd: the fused front end never writes Q|K|V (pass QKV_bf16 = NULL)");
     NR_REQUIRE(a->p_drop >= 0.f && a->p_drop < 1.f, "nr_mhsa_encoder_fwd: dropout p=%f", a->p_drop);
     if (a->n_seq == 0) return 0;
@@ -168,6 +169,22 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
         NR_PROPAGATE(mhsa_fused_fwd(a->ids, a->n_seq, a->T, a->table_bf16, a->V, a->d, a->heads, a->ldx, a->wqkv_heads_bf16,
                                     a->bqkv_heads, DropoutCfg{a->p_drop, a->seed}, DropoutCfg{a->p_drop, a->seed ^ 0x5bd1e995u},
                                     a->X_bf16, a->C_bf16, a->C_lo_bf16, a->bad_id_flag, st));
+        NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
+                                        a->w, st, a->C_lo_bf16));
+        return 0;
+    }
+    if (a->dense != nullptr && a->C_lo_bf16 != nullptr) {
+        // precise user encoder (user_encoder.py:15-26 at fp32 accuracy): the input enters as a hi/lo pair against the
+        // K-concatenated weights [W | W], Q|K|V stays fp32, the attention runs in fp32, the context leaves as hi/lo planes
+        NR_REQUIRE(a->wqkv_kcat_bf16 && a->X_kcat_bf16 && a->QKV_f32 && a->bqkv && a->X_bf16,
+                   "nr_mhsa_encoder_fwd: precise dense variant needs wqkv_kcat_bf16 / X_kcat_bf16 / QKV_f32 / bqkv / X_bf16");
+        NR_REQUIRE(a->QKV_bf16 == nullptr, "nr_mhsa_encoder_fwd: the precise dense variant writes no bf16 Q|K|V (pass NULL)");
+        NR_PROPAGATE(rows_to_bf16(a->dense, a->n_seq, a->T, a->d, a->dense_s_seq, a->dense_s_tok, a->dense_s_col, a->X_bf16, a->ldx, st));
+        NR_PROPAGATE(rows_to_bf16_hilo(a->dense, a->n_seq, a->T, a->d, a->dense_s_seq, a->dense_s_tok, a->dense_s_col, a->X_kcat_bf16,
+                                       a->ldx, st));
+        NR_PROPAGATE(gemm_store(a->X_kcat_bf16, M, 2 * a->ldx, a->wqkv_kcat_bf16, 3 * a->d, 2 * a->ldx, 2 * a->ldx, 1, 0, 128, a->bqkv, 0,
+                                a->QKV_f32, 3 * a->d, 0, kIdentity, 0, kNoDrop, -1, 0, st));
+        NR_PROPAGATE(mhsa_f32_fwd(a->QKV_f32, 3 * a->d, a->n_seq, a->T, a->heads, a->d / a->heads, a->C_bf16, a->C_lo_bf16, a->ldx, st));
         NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
                                         a->w, st, a->C_lo_bf16));
         return 0;

@@ -486,6 +486,128 @@ int dot_score_bwd(const float* cand, const float* user, const float* dlogits, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Precise user encoder (NRMS precise mode): operand and attention kernels that keep the history-level path at fp32 accuracy.
+// The level is 4.6 % of the model's FLOPs (512 users x 50 news vectors), so plain CUDA-core arithmetic is affordable.
+// ------------------------------------------------------------------------------------------------
+// fp32 rows [n_seq][T][D] (element strides) -> bf16 [rows][2*ld]: columns [0, D) = hi = bf16(x), column D = 1.0, zeros up to
+// ld; columns [ld, ld + D) = lo = bf16(x - hi), zeros up to 2*ld.  Against the K-concatenated weight operand [W | W] the GEMM
+// computes (hi + lo) . W^T: the input enters with ~16 mantissa bits instead of 8.
+__global__ void __launch_bounds__(256) rows_to_bf16_hilo_kernel(const float* __restrict__ src, long long n_rows, int T, int D,
+                                                                long long s_seq, long long s_tok, long long s_col,
+                                                                __nv_bfloat16* __restrict__ dst, int ld) {
+    const int chunks = (2 * ld) >> 3;
+    const long long total = n_rows * chunks;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / chunks;
+        const int c = static_cast<int>(i - r * chunks) * 8;
+        const bool lo = c >= ld;
+        const int col = lo ? c - ld : c;
+        const long long seq = r / T;
+        const float* sp = src + seq * s_seq + (r - seq * T) * s_tok;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int cc = col + j;
+            float x = cc < D ? sp[cc * s_col] : 0.f;
+            const float hi = bf16_round(x);
+            v[j] = lo ? (x - hi) : (cc == D ? 1.0f : hi);
+        }
+        *reinterpret_cast<uint4*>(dst + r * (2 * ld) + c) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+int rows_to_bf16_hilo(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col, void* dst,
+                      int ld, cudaStream_t stream) {
+    const long long n = n_seq * T;
+    if (n == 0) return 0;
+    NR_REQUIRE(ld >= D + 1 && ld % 8 == 0, "rows_to_bf16_hilo: pitch %d for D=%d plus the ones column", ld, D);
+    ProfScope ps("rows_to_bf16_hilo", static_cast<int>(n), D, ld, stream);
+    const int blocks = static_cast<int>(std::min<long long>((n * (2 * ld / 8) + 255) / 256, 148 * 8));
+    rows_to_bf16_hilo_kernel<<<blocks, 256, 0, stream>>>(src, n, T, D, s_seq, s_tok, s_col, static_cast<__nv_bfloat16*>(dst), ld);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// fp32 multi-head self-attention core (multihead_self.py:15-23) on fp32 Q|K|V rows [n_seq*T][ld] (Q at column 0, K at d, V at
+// 2d): one CTA per (sequence, head), thread i owns query row i (T <= 64): scores, exp-softmax with the +1e-8, P.V -- all in
+// fp32 registers / shared memory.  The context leaves as bf16 hi + lo planes (pitch ldc, ones column at d in the hi plane).
+constexpr int kF32MaxT = 64, kF32MaxDk = 32;
+__global__ void __launch_bounds__(64) mhsa_f32_fwd_kernel(const float* __restrict__ qkv, int ld, int T, int heads, int dk,
+                                                          __nv_bfloat16* __restrict__ c_hi, __nv_bfloat16* __restrict__ c_lo, int ldc) {
+    __shared__ float sk[kF32MaxT][kF32MaxDk + 1], sv[kF32MaxT][kF32MaxDk + 1];
+    const int seq = blockIdx.x / heads, h = blockIdx.x - seq * heads;
+    const int d = heads * dk;
+    const float* base = qkv + static_cast<size_t>(seq) * T * ld + h * dk;
+    for (int i = threadIdx.x; i < T * dk; i += blockDim.x) {
+        const int r = i / dk, c = i - r * dk;
+        sk[r][c] = base[static_cast<size_t>(r) * ld + d + c];
+        sv[r][c] = base[static_cast<size_t>(r) * ld + 2 * d + c];
+    }
+    __syncthreads();
+    const int i = threadIdx.x;
+    if (i >= T) return;
+    float q[kF32MaxDk];
+#pragma unroll
+    for (int c = 0; c < kF32MaxDk; ++c) q[c] = c < dk ? base[static_cast<size_t>(i) * ld + c] : 0.f;
+    const float rs = rsqrtf(static_cast<float>(dk));
+    float s[kF32MaxT];
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < kF32MaxDk; ++c) acc = fmaf(q[c], c < dk ? sk[j][c] : 0.f, acc);
+        s[j] = acc * rs;
+        m = fmaxf(m, s[j]);
+    }
+    float l = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+        s[j] = __expf(s[j] - m);
+        l += s[j];
+    }
+    const float inv = 1.f / (l + 1e-8f * __expf(-m));  // == exp(S) / (sum exp(S) + 1e-8)
+    float o[kF32MaxDk];
+#pragma unroll
+    for (int c = 0; c < kF32MaxDk; ++c) o[c] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < T; ++j) {
+        const float p = s[j] * inv;
+#pragma unroll
+        for (int c = 0; c < kF32MaxDk; ++c) o[c] = fmaf(p, c < dk ? sv[j][c] : 0.f, o[c]);
+    }
+    const size_t row = (static_cast<size_t>(seq) * T + i) * ldc;
+#pragma unroll
+    for (int c = 0; c < kF32MaxDk; ++c) {
+        if (c < dk) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(o[c]);
+            c_hi[row + h * dk + c] = hi;
+            c_lo[row + h * dk + c] = __float2bfloat16_rn(o[c] - __bfloat162float(hi));
+        }
+    }
+    if (h == 0) {
+        for (int c = d; c < ldc; ++c) {
+            c_hi[row + c] = __float2bfloat16_rn(c == d ? 1.0f : 0.f);
+            c_lo[row + c] = __float2bfloat16_rn(0.f);
+        }
+    }
+}
+int mhsa_f32_fwd(const float* qkv, int ld, long long n_seq, int T, int heads, int dk, void* c_hi, void* c_lo, int ldc,
+                 cudaStream_t stream) {
+    if (n_seq == 0) return 0;
+    NR_REQUIRE(T >= 1 && T <= kF32MaxT && dk >= 1 && dk <= kF32MaxDk && ldc >= heads * dk + 1 && n_seq * heads < (1ll << 31),
+               "mhsa_f32_fwd: T=%d dk=%d ldc=%d", T, dk, ldc);
+    ProfScope ps("mhsa_f32_fwd", static_cast<int>(n_seq), T, heads * dk, stream);
+    mhsa_f32_fwd_kernel<<<static_cast<int>(n_seq * heads), 64, 0, stream>>>(qkv, ld, T, heads, dk, static_cast<__nv_bfloat16*>(c_hi),
+                                                                           static_cast<__nv_bfloat16*>(c_lo), ldc);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // evaluation stage 3, batched (reference src/evaluate.py:245-265 scores ONE impression per get_prediction call and
 // synchronises on .tolist() after each): scores[i] = news[cand[i]] . user[seg(i)] for the candidates of MANY impressions
 // in one launch.  The news vectors stay in ONE device matrix (row = news index) instead of a Python dict of rows;

@@ -27,8 +27,8 @@
 // together with the hi/lo context planes this removes the two roundings that dominated the bf16 error of the unfused path
 // (V and C: every token of a title sees the same rounding error of V_j, so pooling does not average it away).
 //
-// TMEM (512 columns): [0,128) two Q|K|V accumulators, [128,384) two score tiles (P aliases the first 64 columns of its
-// score tile), [384,512) two context accumulators.
+// TMEM (512 columns): [0,128) two Q|K|V accumulators, [128,384) two score tiles (the P operand -- a hi/lo bf16 pair, 64 + 64
+// packed columns -- overwrites its score tile), [384,512) two context accumulators.
 #include <algorithm>
 #include <cstring>
 
@@ -149,22 +149,32 @@ __device__ __forceinline__ void softmax_step(uint32_t s_t, int sel, float sc) {
         l += x[j];
     }
     const float inv = 1.f / (l + 1e-8f * exp2f(-m));  // == exp(S) / (sum exp(S) + 1e-8)
-    uint32_t pk[T / 2];
+    // P leaves as a hi/lo bf16 pair (the bf16 rounding of the probabilities alone is 1.1e-3 of the logits): packed columns
+    // [0, 64) of the score tile take P_hi, [64, 128) take P_lo; the issuer accumulates P_hi.V and P_lo.V into one accumulator
+    uint32_t pk[T / 2], pl[T / 2];
 #pragma unroll
-    for (int i = 0; i < T / 2; ++i) pk[i] = pack_bf16x2(x[2 * i] * inv, x[2 * i + 1] * inv);
-    // all 64 packed columns of the P operand are rewritten (the score MMA overwrote them): zeros off the diagonal
+    for (int i = 0; i < T / 2; ++i) {
+        const float p0 = x[2 * i] * inv, p1 = x[2 * i + 1] * inv;
+        pk[i] = pack_bf16x2(p0, p1);
+        const float2 f = unpack_bf16x2(pk[i]);
+        pl[i] = pack_bf16x2(p0 - f.x, p1 - f.y);
+    }
+    // all 128 columns of the tile are rewritten (the score MMA overwrote them): zeros off the diagonal
     uint32_t pw[64];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-        pw[c] = 0u;
+    for (int part = 0; part < 2; ++part) {
 #pragma unroll
-        for (int i = 0; i < W::ncand; ++i) {
-            const int c0 = (W::tlo + i) * (T / 2);
-            if (c >= c0 && c < c0 + T / 2) pw[c] = (sel == i) ? pk[c - c0] : 0u;
+        for (int c = 0; c < 64; ++c) {
+            pw[c] = 0u;
+#pragma unroll
+            for (int i = 0; i < W::ncand; ++i) {
+                const int c0 = (W::tlo + i) * (T / 2);
+                if (c >= c0 && c < c0 + T / 2) pw[c] = (sel == i) ? (part == 0 ? pk[c - c0] : pl[c - c0]) : 0u;
+            }
         }
+        tmem_st32(s_t + 64 * part, pw);
+        tmem_st32(s_t + 64 * part + 32, pw + 32);
     }
-    tmem_st32(s_t, pw);
-    tmem_st32(s_t + 32, pw + 32);
     tmem_st_wait();
 }
 
@@ -571,8 +581,8 @@ __global__ void __launch_bounds__(kThreads, 1) mhsa_fused_fwd_kernel(const __gri
                         if (elect_one()) {
                             const uint64_t db = make_sw128_desc(v_s + g * kTile, 8192, 1024);
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)  // 16 key rows per k-step: +2048 bytes in B, +8 packed columns in A
-                                umma_bf16_ts(tmem_base + 384 + g * 64, tmem_base + 128 + g * 128 + 8 * k, db + 128 * k, idesc_pv,
+                            for (int k = 0; k < 16; ++k)  // P_hi then P_lo; 16 key rows per k-step: +2048 bytes in B, +8 packed columns in A
+                                umma_bf16_ts(tmem_base + 384 + g * 64, tmem_base + 128 + g * 128 + 8 * k, db + 128 * (k & 7), idesc_pv,
                                              k ? 1u : 0u);
                             umma_commit(&bars[O_FULL + g]);
                         }

@@ -91,6 +91,11 @@ int gru_persistent_supported(int B, int Hd);
 int gru_fwd_persistent(int B, int S, int Hd, int ldh, int ldg, const float* gi, const void* whh, const float* bhh, const float* h0,
                        const long long* len, float* gh, float* hs, void* hb, float* out, cudaStream_t stream);
 
+// precise user encoder (NRMS precise mode): hi/lo K-concatenated operand rows, fp32 attention with hi/lo context planes
+int rows_to_bf16_hilo(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col, void* dst,
+                      int ld, cudaStream_t stream);
+int mhsa_f32_fwd(const float* qkv, int ld, long long n_seq, int T, int heads, int dk, void* c_hi, void* c_lo, int ldc,
+                 cudaStream_t stream);
 // scores[i] = news[cand[i]] . user[s] for seg_offsets[s] <= i < seg_offsets[s+1]  (batched evaluate.py:245-265)
 int segment_dot(const float* news, long long n_news, int D, const long long* cand, long long n_cand, const long long* seg_offsets,
                 long long n_seg, const float* user, float* scores, int* bad_flag, cudaStream_t stream);

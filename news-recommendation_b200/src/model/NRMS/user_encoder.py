@@ -20,4 +20,5 @@ class UserEncoder(nn.Module):
         a = self.additive_attention
         return MhsaPoolEncoderFn.apply(None, user_vector, None, *self.multihead_self_attention.qkv_parameters(),
                                        a.linear.weight, a.linear.bias, a.attention_query_vector,
-                                       self.config.num_attention_heads, 0.0, self._cache, "user", None)
+                                       self.config.num_attention_heads, 0.0, self._cache, "user", None,
+                                       bool(getattr(self.config, "fused_news_encoder", False)))  # precise mode: fp32-accurate forward

@@ -25,6 +25,7 @@ class MhsaEncoderFwdArgs(C.Structure):
         ("p_drop", _f), ("seed", _ull),
         ("X_bf16", _vp), ("QKV_bf16", _vp), ("C_bf16", _vp), ("w", _vp), ("out", _vp), ("bad_id_flag", _vp),
         ("wqkv_heads_bf16", _vp), ("bqkv_heads", _vp), ("C_lo_bf16", _vp),
+        ("wqkv_kcat_bf16", _vp), ("X_kcat_bf16", _vp), ("QKV_f32", _vp),
     ]
 
 

@@ -170,10 +170,11 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         # mode of the news level: 2.6e-3 instead of 7e-3 against the reference's fp32 logits, at ~3.6x the time of the
         # unfused gather | GEMM | attention sequence -- opt-in (config.fused_news_encoder / NEWSREC_FUSED=1)
         fused = ids is not None and (precise or os.environ.get("NEWSREC_FUSED") == "1") and bool(lib.nr_mhsa_fused_supported(T, d, heads))
+        precise_dense = ids is None and precise  # user encoder of the precise mode: fp32-accurate forward (abi.cu)
         X = QKV = C_lo = None
         if need_bwd or not fused:  # X only exists in HBM when a backward pass (or the unfused sequence) reads it
             X = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
-        if not fused:              # the fused front end keeps Q|K|V on chip; its backward recomputes it from X
+        if not fused and not precise_dense:  # the precise paths keep no bf16 Q|K|V; their backward recomputes it from X
             QKV = torch.empty((n_tok, ld3), dtype=torch.bfloat16, device=dev)
         Cx = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
         w = torch.empty((n_tok,), dtype=torch.float32, device=dev)
@@ -187,6 +188,13 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
                            lambda Wq, bq, Wk, bk, Wv, bv: pack_head_blocks(Wq, bq, Wk, bk, Wv, bv, heads, ldx))
             C_lo = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
             a.wqkv_heads_bf16, a.bqkv_heads, a.C_lo_bf16 = _p(hb[0]), _p(hb[1]), _p(C_lo)
+        keep = None
+        if precise_dense:
+            kcat = cache.get(prefix + ".kcat", (Wq, Wk, Wv), lambda Wq, Wk, Wv: cast_pad(
+                torch.cat((torch.nn.functional.pad(torch.cat((Wq, Wk, Wv), 0).float(), (0, ldx - d)),) * 2, dim=1), 2 * ldx))
+            C_lo = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
+            keep = (torch.empty((n_tok, 2 * ldx), dtype=torch.bfloat16, device=dev), torch.empty((n_tok, 3 * d), dtype=torch.float32, device=dev))
+            a.wqkv_kcat_bf16, a.X_kcat_bf16, a.QKV_f32, a.C_lo_bf16 = _p(kcat), _p(keep[0]), _p(keep[1]), _p(C_lo)
         a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.out = _p(X), _p(QKV), _p(Cx), _p(w), _p(out)
         a.bad_id_flag = _p(bad_flag)
         check(lib.nr_mhsa_encoder_fwd(C.byref(a), _stream()), "nr_mhsa_encoder_fwd")

@@ -180,7 +180,8 @@ def scaled_dot_product_attention(Q, K, V, c: "Contract" = None):
     scores = torch.exp(raw / math.sqrt(d_k))
     attn = scores / (torch.sum(scores, dim=-1, keepdim=True) + 1e-8)
     if c is not None:
-        attn = c.operand(attn) if c.acts else attn  # P is an activation: it stays fp32 under the weights-only contract
+        if c.acts:  # P is an activation: it stays fp32 under the weights-only contract; the fused kernels keep it as a hi/lo pair
+            attn = _RoundHiLo.apply(attn) if c.hilo else c.operand(attn)
     return torch.matmul(attn, V)
 
 

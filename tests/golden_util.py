@@ -48,8 +48,10 @@ def oracle_forward(case, g, p, contract=O.EXACT, fused=False, drop=None, user_ke
     fused: the NRMS news level runs through the one-kernel front end (V / context as hi/lo bf16 pairs)."""
     cand_t, clicked_t = t(g, "cand_title"), t(g, "clicked_title")
     if case == "nrms":
-        c_news = O.BF16_FUSED if (contract.bf16 and fused) else contract
-        return O.nrms_forward(cand_t, clicked_t, p, 15, contract, c_news=c_news, drop=drop), None
+        if contract.bf16 and contract.acts and fused:
+            # precise mode: fused news front end (V / context / P as hi/lo pairs, Q / K bf16) + fp32-accurate user encoder
+            return O.nrms_forward(cand_t, clicked_t, p, 15, O.WEIGHTS_BF16, c_news=O.BF16_FUSED, drop=drop), None
+        return O.nrms_forward(cand_t, clicked_t, p, 15, contract, c_news=contract, drop=drop), None
     if case.startswith("naml"):
         cand = dict(title=cand_t, abstract=t(g, "cand_abstract"), category=t(g, "cand_category"),
                     subcategory=t(g, "cand_subcategory"))

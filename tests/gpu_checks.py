@@ -306,7 +306,7 @@ def check_nrms_random(B=8, Cn=5, H=50, T=20, V=500, seed=5, fused=False):
     model, sd = nrms_model_and_params(V, seed, fused=fused)
     model.eval()
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16, c_news=O.BF16_FUSED if fused else O.BF16)
+    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.WEIGHTS_BF16 if fused else O.BF16, c_news=O.BF16_FUSED if fused else O.BF16)
     O.click_loss(logits_o).backward()
     with torch.no_grad():
         logits_x = O.nrms_forward(cand_t, clicked_t, {k: v.detach() for k, v in p.items()}, 15, O.EXACT)
@@ -437,7 +437,8 @@ def check_nrms_train_masked(B=6, Cn=5, H=50, T=20, V=500, seed=8, p_drop=0.2, fu
     kseed = ops.peek_seeds(1)[0]  # the news encoder draws the only seed of a forward pass (the user encoder has no dropout)
     drop = dict(p=p_drop, seed=kseed, ld=ru8(300 + 1))
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.BF16, c_news=O.BF16_FUSED if fused else O.BF16, drop=drop)
+    logits_o = O.nrms_forward(cand_t, clicked_t, p, 15, O.WEIGHTS_BF16 if fused else O.BF16, c_news=O.BF16_FUSED if fused else O.BF16,
+                              drop=drop)
     O.click_loss(logits_o).backward()
     px = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     logits_x = O.nrms_forward(cand_t, clicked_t, px, 15, O.EXACT, drop=drop)  # exact arithmetic, same masks

@@ -38,12 +38,14 @@ def test_golden_case(case):
 
 
 def test_nrms_precise_mode_golden_case():
-    """config.fused_news_encoder: the one-kernel news front end with hi/lo V / context.  Same assertions as the default path
-    against its own storage contract, and a tighter bound against the reference's fp32 outputs (measured 2.6e-3 vs 7.3e-3)."""
+    """config.fused_news_encoder -- the PRECISE mode: one-kernel news front end (V / context / probabilities as hi/lo bf16
+    pairs) + fp32-accurate user encoder forward.  It meets the blueprint's tolerance: logits within 1e-3 of the fp32 oracle
+    evaluated on bf16-rounded weights / embeddings (default path: 6.3e-3); against the reference's own fp32 logits what is
+    left is the bf16 rounding of the weights themselves (2.3e-3 on this case for ANY bf16-weight implementation)."""
     r = G.check_golden("nrms", fused=True)
     assert r["logits_vs_oracle_bf16"] < 1e-3, r
-    assert r["logits_vs_weights_only_oracle"] < 2.5e-3, r                 # measured 1.8e-3 (default path: 6.3e-3)
-    assert r["logits_vs_reference_fp32"] < 4e-3, r
+    assert r["logits_vs_weights_only_oracle"] < 1e-3, r
+    assert r["logits_vs_reference_fp32"] < 3.5e-3, r
     assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
 
 
