@@ -80,9 +80,10 @@ int nr_gemm_tn(const void* A_bf16, int Kr, int Ma, int lda, const void* B_bf16, 
                int b_col0, int Nb, int b_row_shift, float* D, int ldd, void* stream);
 
 /* ---- reference: MultiHeadSelfAttention core (src/model/general/attention/multihead_self.py:15-23) -- */
-int nr_mhsa_core_fwd(const void* qkv_bf16, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx_bf16,
+/* Q | K | V sections of a row start at columns 0, sec, 2*sec (sec >= heads*dk; dQ|dK|dV likewise, padding written as zeros) */
+int nr_mhsa_core_fwd(const void* qkv_bf16, int ld_qkv, int sec, long long n_seq, int T, int heads, int dk, void* ctx_bf16,
                      int ld_ctx, float p_drop, unsigned long long seed, void* stream);
-int nr_mhsa_core_bwd(const void* qkv_bf16, int ld_qkv, const void* dctx_bf16, int ld_dctx, long long n_seq, int T,
+int nr_mhsa_core_bwd(const void* qkv_bf16, int ld_qkv, int sec, const void* dctx_bf16, int ld_dctx, long long n_seq, int T,
                      int heads, int dk, void* dqkv_bf16, int ld_dqkv, void* stream);
 
 /* ---- reference: AdditiveAttention.forward (src/model/general/attention/additive.py:27-53) ----------- */
@@ -127,7 +128,8 @@ typedef struct {
     int heads;                /* num_attention_heads, d % heads == 0                                */
     int q;                    /* query_vector_dim                                                   */
     int ldx;                  /* pitch of X / C / weight operands: multiple of 8, >= d+1            */
-    int ld3;                  /* pitch of QKV: round_up(3d, 16) (32-byte rows for STG.256 epilogues) */
+    int ld3;                  /* pitch of Q|K|V rows: round_up(3*sec, 16), sec = round_up(d, 8): sections at columns 0, sec, 2*sec;
+                                 packed weights / biases carry zero rows at the section padding */
     /* input: ids+table (news encoder) or dense (user encoder) */
     const long long* ids;     /* [n_seq*T] or NULL                                                  */
     const void* table_bf16;   /* [V][ldx]                                                           */
@@ -162,7 +164,7 @@ typedef struct {
      * in fp32 on the CUDA cores, the context leaves as hi (C_bf16) + lo (C_lo_bf16) planes.  QKV_bf16 must be NULL. */
     const void* wqkv_kcat_bf16;  /* [3d][2*ldx]: columns [0,d) = W, [ldx, ldx+d) = W again, zeros elsewhere            */
     void* X_kcat_bf16;           /* [n_seq*T][2*ldx] workspace: hi | lo operand rows                                   */
-    float* QKV_f32;              /* [n_seq*T][3d] workspace                                                            */
+    float* QKV_f32;              /* [n_seq*T][3*sec] workspace                                                           */
 } nr_mhsa_encoder_fwd_args;
 int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream);
 /* 1 if the fused front end handles (tokens per title, model width, heads): the reference's news level, T = 20, d_k = 20 */
@@ -173,7 +175,7 @@ typedef struct {
     int T, d, heads, q, ldx, ld3, ldq;   /* ldq: pitch of dPre / WaT = round_up(q, 16)                   */
     const long long* ids;                /* NULL for the dense (user) variant                            */
     int V;
-    const void* wqkvT_bf16;              /* [d][ld3]  = (W_Q|W_K|W_V)^T                                  */
+    const void* wqkvT_bf16;              /* [d][ld3]  = (W_Q|0|W_K|0|W_V|0)^T                               */
     const void* wa_bf16;                 /* [q][ldx]                                                     */
     const void* waT_bf16;                /* [d][ldq]                                                     */
     const float* ba;

@@ -65,15 +65,15 @@ int nr_gemm_tn(const void* A, int Kr, int Ma, int lda, const void* B, int b_rows
     NR_REQUIRE(A && B && D, "nr_gemm_tn: null operand");
     return gemm_tn_accumulate(A, Kr, Ma, lda, B, b_rows, b_cols, ldb, b_col0, Nb, b_row_shift, D, ldd, S(stream));
 }
-int nr_mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
+int nr_mhsa_core_fwd(const void* qkv, int ld_qkv, int sec, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
                      float p_drop, unsigned long long seed, void* stream) {
     NR_REQUIRE(qkv && ctx, "nr_mhsa_core_fwd: null operand");
-    return mhsa_core_fwd(qkv, ld_qkv, n_seq, T, heads, dk, ctx, ld_ctx, DropoutCfg{p_drop, seed}, S(stream));
+    return mhsa_core_fwd(qkv, ld_qkv, sec, n_seq, T, heads, dk, ctx, ld_ctx, DropoutCfg{p_drop, seed}, S(stream));
 }
-int nr_mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads,
+int nr_mhsa_core_bwd(const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int T, int heads,
                      int dk, void* dqkv, int ld_dqkv, void* stream) {
     NR_REQUIRE(qkv && dctx && dqkv, "nr_mhsa_core_bwd: null operand");
-    return mhsa_core_bwd(qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, S(stream));
+    return mhsa_core_bwd(qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, S(stream));
 }
 
 // ---- AdditiveAttention ---------------------------------------------------------------------------
@@ -138,11 +138,15 @@ int nr_accumulate_ext_grad(float* ext, int rows, int ld, int D, float* dW, float
 }
 
 // ---- NRMS encoders ---------------------------------------------------------------------------------
+// Q | K | V sections of the projected rows start at columns 0, sec, 2*sec with sec = round_up(d, 8): every section (and so
+// every head of every section) has the same 16-byte phase, which the title-level attention kernels rely on.  The packed
+// projection operands carry zero rows / columns at the section padding, so the padding columns of Q|K|V are exact zeros.
+static int qkv_section(int d) { return (d + 7) & ~7; }
 static int check_mhsa_shape(long long n_seq, int T, int d, int heads, int q, int ldx, int ld3) {
     NR_REQUIRE(n_seq >= 0 && T >= 1 && T <= 64 && d >= 8 && heads >= 1 && d % heads == 0 && q >= 1 && q <= 256,
                "mhsa encoder: bad shape n_seq=%lld T=%d d=%d heads=%d q=%d", n_seq, T, d, heads, q);
-    NR_REQUIRE(ldx % 8 == 0 && ldx >= d + 1 && ld3 % 8 == 0 && ld3 >= 3 * d, "mhsa encoder: bad pitches ldx=%d ld3=%d", ldx,
-               ld3);
+    NR_REQUIRE(ldx % 8 == 0 && ldx >= d + 1 && ld3 % 8 == 0 && ld3 >= 3 * qkv_section(d), "mhsa encoder: bad pitches ldx=%d ld3=%d",
+               ldx, ld3);
     NR_REQUIRE(n_seq * T < (1ll << 31), "mhsa encoder: too many tokens (%lld)", n_seq * T);
     return 0;
 }
@@ -182,9 +186,9 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
         NR_PROPAGATE(rows_to_bf16(a->dense, a->n_seq, a->T, a->d, a->dense_s_seq, a->dense_s_tok, a->dense_s_col, a->X_bf16, a->ldx, st));
         NR_PROPAGATE(rows_to_bf16_hilo(a->dense, a->n_seq, a->T, a->d, a->dense_s_seq, a->dense_s_tok, a->dense_s_col, a->X_kcat_bf16,
                                        a->ldx, st));
-        NR_PROPAGATE(gemm_store(a->X_kcat_bf16, M, 2 * a->ldx, a->wqkv_kcat_bf16, 3 * a->d, 2 * a->ldx, 2 * a->ldx, 1, 0, 128, a->bqkv, 0,
-                                a->QKV_f32, 3 * a->d, 0, kIdentity, 0, kNoDrop, -1, 0, st));
-        NR_PROPAGATE(mhsa_f32_fwd(a->QKV_f32, 3 * a->d, a->n_seq, a->T, a->heads, a->d / a->heads, a->C_bf16, a->C_lo_bf16, a->ldx, st));
+        NR_PROPAGATE(gemm_store(a->X_kcat_bf16, M, 2 * a->ldx, a->wqkv_kcat_bf16, 3 * qkv_section(a->d), 2 * a->ldx, 2 * a->ldx, 1, 0, 128,
+                                a->bqkv, 0, a->QKV_f32, 3 * qkv_section(a->d), 0, kIdentity, 0, kNoDrop, -1, 0, st));
+        NR_PROPAGATE(mhsa_f32_fwd(a->QKV_f32, 3 * qkv_section(a->d), qkv_section(a->d), a->n_seq, a->T, a->heads, a->d / a->heads, a->C_bf16, a->C_lo_bf16, a->ldx, st));
         NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
                                         a->w, st, a->C_lo_bf16));
         return 0;
@@ -198,11 +202,11 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
                                   a->X_bf16, a->ldx, st));
     }
     // Q|K|V = X . Wqkv^T + b   (multihead_self.py:53-58)
-    NR_PROPAGATE(gemm_store(a->X_bf16, M, a->ldx, a->wqkv_bf16, 3 * a->d, a->ldx, a->d, 1, 0, 128, a->bqkv, 0,
+    NR_PROPAGATE(gemm_store(a->X_bf16, M, a->ldx, a->wqkv_bf16, 3 * qkv_section(a->d), a->ldx, a->d, 1, 0, 128, a->bqkv, 0,
                             a->QKV_bf16, a->ld3, 1, kIdentity, 0, kNoDrop, -1, 0, st));
     // per-head attention (multihead_self.py:15-23), dropout on the context only in the news encoder
     const DropoutCfg cdrop = {a->ids != nullptr ? a->p_drop : 0.f, a->seed ^ 0x5bd1e995u};
-    NR_PROPAGATE(mhsa_core_fwd(a->QKV_bf16, a->ld3, a->n_seq, a->T, a->heads, a->d / a->heads, a->C_bf16, a->ldx, cdrop,
+    NR_PROPAGATE(mhsa_core_fwd(a->QKV_bf16, a->ld3, qkv_section(a->d), a->n_seq, a->T, a->heads, a->d / a->heads, a->C_bf16, a->ldx, cdrop,
                                st));
     // additive pooling (additive.py:35-53)
     NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
@@ -212,7 +216,7 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
 
 long long nr_mhsa_encoder_bwd_workspace(long long n_seq, int T, int d, int q) {
     const long long rows = n_seq * T;
-    const long long ldx = (d + 1 + 7) & ~7, ld3 = (3 * d + 15) & ~15, ldq = (q + 15) & ~15;
+    const long long ldx = (d + 1 + 7) & ~7, ld3 = (3 * qkv_section(d) + 15) & ~15, ldq = (q + 15) & ~15;
     return align256(rows * 4) + align256(rows * ldq * 2) + align256(rows * ldx * 2) + 2 * align256(rows * ld3 * 2) + 256;
 }
 
@@ -220,8 +224,8 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     NR_REQUIRE(a != nullptr, "nr_mhsa_encoder_bwd: null args");
     NR_PROPAGATE(check_mhsa_shape(a->n_seq, a->T, a->d, a->heads, a->q, a->ldx, a->ld3));
     NR_REQUIRE(a->ldq % 8 == 0 && a->ldq >= a->q, "nr_mhsa_encoder_bwd: ldq=%d", a->ldq);
-    NR_REQUIRE(a->ldx == ((a->d + 8) & ~7) && a->ld3 == ((3 * a->d + 15) & ~15) && a->ldq == ((a->q + 15) & ~15),
-               "nr_mhsa_encoder_bwd: pitches must be canonical: ldx=round_up(d+1,8), ld3=round_up(3d,16), ldq=round_up(q,16)");
+    NR_REQUIRE(a->ldx == ((a->d + 8) & ~7) && a->ld3 == ((3 * qkv_section(a->d) + 15) & ~15) && a->ldq == ((a->q + 15) & ~15),
+               "nr_mhsa_encoder_bwd: pitches must be canonical: ldx=round_up(d+1,8), ld3=round_up(3*round_up(d,8),16), ldq=round_up(q,16)");
     NR_REQUIRE(a->wqkvT_bf16 && a->wa_bf16 && a->waT_bf16 && a->ba && a->qv && a->X_bf16 && a->C_bf16 &&
                    a->w && a->dout && a->dWqkv_ext && a->dWa_ext && a->dqv && a->workspace,
                "nr_mhsa_encoder_bwd: null operand");
@@ -235,6 +239,7 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     const long long rows = a->n_seq * a->T;
     const int M = static_cast<int>(rows);
     const cudaStream_t st = S(stream);
+    const int sec = qkv_section(a->d);
     char* ws = static_cast<char*>(a->workspace);
     float* dscore = reinterpret_cast<float*>(ws);
     ws += align256(rows * 4);
@@ -248,7 +253,7 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     prof_context(a->ids != nullptr ? "news.bwd" : "user.bwd");
     const void* QKV = a->QKV_bf16;
     if (QKV == nullptr) {  // the fused forward keeps Q|K|V on chip: recompute it from the saved rows (multihead_self.py:53-58)
-        NR_PROPAGATE(gemm_store(a->X_bf16, M, a->ldx, a->wqkv_bf16, 3 * a->d, a->ldx, a->d, 1, 0, 128, a->bqkv, 0, ws, a->ld3, 1,
+        NR_PROPAGATE(gemm_store(a->X_bf16, M, a->ldx, a->wqkv_bf16, 3 * sec, a->ldx, a->d, 1, 0, 128, a->bqkv, 0, ws, a->ld3, 1,
                                 kIdentity, 0, kNoDrop, -1, 0, st));
         QKV = ws;
     }
@@ -262,20 +267,20 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     NR_PROPAGATE(gemm_tn_accumulate(dpre, M, a->q, a->ldq, a->C_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWa_ext,
                                     a->ldx, st));
     // --- attention backward ---
-    NR_PROPAGATE(mhsa_core_bwd(QKV, a->ld3, dC, a->ldx, a->n_seq, a->T, a->heads, a->d / a->heads, dQKV, a->ld3, st));
+    NR_PROPAGATE(mhsa_core_bwd(QKV, a->ld3, sec, dC, a->ldx, a->n_seq, a->T, a->heads, a->d / a->heads, dQKV, a->ld3, st));
     // --- projection backward: the input first (the embedding gradient is 97 % of a data-parallel step's all-reduce: the
     //     caller's event lets the communication start under the weight-gradient GEMM), then the weights (+bias through the
     //     ones column of X) ---
     if (a->ids != nullptr) {
         NR_REQUIRE(a->V >= 1, "nr_mhsa_encoder_bwd: V=%d", a->V);
-        NR_PROPAGATE(gemm_scatter_emb(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, a->ids, a->demb, a->V, a->d,
+        NR_PROPAGATE(gemm_scatter_emb(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * sec, 1, 0, 128, a->ids, a->demb, a->V, a->d,
                                       kIdentity, DropoutCfg{a->p_drop, a->seed}, a->ldx, st));
         if (a->emb_grad_ready_event != nullptr) NR_CHECK_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->emb_grad_ready_event), st));
     } else {
-        NR_PROPAGATE(gemm_store(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * a->d, 1, 0, 128, nullptr, 0, a->ddense, a->d,
+        NR_PROPAGATE(gemm_store(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * sec, 1, 0, 128, nullptr, 0, a->ddense, a->d,
                                 0, kIdentity, 0, kNoDrop, -1, 0, st));
     }
-    NR_PROPAGATE(gemm_tn_accumulate(dQKV, M, 3 * a->d, a->ld3, a->X_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWqkv_ext,
+    NR_PROPAGATE(gemm_tn_accumulate(dQKV, M, 3 * sec, a->ld3, a->X_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWqkv_ext,
                                     a->ldx, st));
     return 0;
 }

@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "nr_common.cuh"
+#include "nr_mma.cuh"
 #include "nr_ops.h"
 
 namespace nr {
@@ -20,41 +21,13 @@ extern int g_launches;
 
 namespace {
 
+using namespace mma;
+
 constexpr int kPitch = 40;   // bf16 elements per tile row (80 B: 16-byte aligned, ldmatrix conflict-free), generic kernels
 constexpr int kPitch24 = 24; // fixed-shape d_k = 20 kernels: 48-byte rows (also conflict-free: 8 rows x 16 B hit 8 distinct bank
                              // quads); the second k-step over d_k is then an m16n8k8 MMA over columns 16..23 (20..23 stay zero).
                              // 40 % less shared memory per tile -> 4 instead of 3 resident CTAs (backward), 6 instead of 5 (forward):
                              // the kernels are latency bound (25-36 % issue-active, ncu profiles/), residency is what they lack.
-
-__device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t* r, const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldsm_x2_t(uint32_t* r, const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldsm_x1(uint32_t* r, const void* p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r[0]) : "r"(smem_u32(p)));
-}
-// m16n8k8: A (16 x 8) = 2 registers, B (8 x 8) = 1 register
-__device__ __forceinline__ void mma_bf16_k8(float* c, const uint32_t* a, const uint32_t* b) {
-    asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(b[0]));
-}
-__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, const uint32_t* b) {
-    // not volatile: a pure register operation, the compiler may interleave independent MMAs with the softmax arithmetic
-    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 
 // A fragment (16 x 16) of a row-major [row][k] tile:           rows row0.., k columns k0..
 __device__ __forceinline__ void load_a(uint32_t* a, const __nv_bfloat16* tile, int pitch, int row0, int k0, int lane) {
@@ -80,14 +53,6 @@ __device__ __forceinline__ void load_b_t(uint32_t* b, const __nv_bfloat16* tile,
     ldsm_x2_t(b, tile + (k0 + (lane & 7) + (((lane >> 3) & 1) << 3)) * pitch + n0);
 }
 
-__device__ __forceinline__ float quad_max(float v) {
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-}
-__device__ __forceinline__ float quad_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v + __shfl_xor_sync(0xffffffffu, v, 2);
-}
 __device__ __forceinline__ float drop_mult(uint64_t seed, uint32_t thresh, float scale, long long row, int ld, int col) {
     const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row) * ld + col) >> 2);
     return (((bits >> (16 * (col & 3))) & 0xffffu) >= thresh) ? scale : 0.f;
@@ -330,7 +295,7 @@ __host__ __device__ inline int piece_bytes(int dk, int ld_a, int ld_b, int d) {
 // 3 warps per SM resident (0.28 ms for 4 % of the tokens).  Tiles are loaded/stored by all threads, phases are separated
 // by __syncthreads instead of __syncwarp.
 template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH, bool COOP>
-__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (COOP ? 3 : 1))) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, long long n_seq,
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (COOP ? 3 : 1))) mhsa_mma_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int sec, long long n_seq,
                                                                   int T_, int heads_, int dk_, __nv_bfloat16* __restrict__ ctx,
                                                                   int ld_ctx, float p, uint64_t seed) {
     constexpr int NTJ = TP / 8, MT = TP / 16;
@@ -354,7 +319,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (C
     const uint32_t thresh = static_cast<uint32_t>(p * 65536.0f + 0.5f);
     const float dscale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     const int ntj = (T + 7) >> 3;
-    const int piece = CT > 0 ? 8 : piece_bytes(dk, ld, ld_ctx, d);
+    const int piece = CT > 0 ? 8 : piece_bytes(dk, ld, ld_ctx, sec);
     const int n_tasks = static_cast<int>(n_seq * heads);  // < 2^31, checked by the launcher
     const int W = COOP ? gridDim.x : gridDim.x * WPS;
     const int gw = COOP ? blockIdx.x : blockIdx.x * WPS + warp;
@@ -374,13 +339,13 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (C
             if constexpr (fast) {
                 const uint32_t t0s = wbase_s + 2 * stage * 3 * TILE;
                 tile_load_map(t0s, src, lmap, piece);
-                tile_load_map(t0s + 2 * TILE, src + d, lmap, piece);
-                tile_load_map(t0s + 4 * TILE, src + 2 * d, lmap, piece);
+                tile_load_map(t0s + 2 * TILE, src + sec, lmap, piece);
+                tile_load_map(t0s + 4 * TILE, src + 2 * sec, lmap, piece);
             } else {
                 __nv_bfloat16* t0 = wbase + stage * 3 * TILE;
                 tile_load(t0, src, ld, T, dk, piece, ctid, cnt, PT);
-                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt, PT);
-                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + TILE, src + sec, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + 2 * TILE, src + 2 * sec, ld, T, dk, piece, ctid, cnt, PT);
             }
         }
         cp_commit();
@@ -492,7 +457,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 8 : 5) : (C
 // backward
 // ------------------------------------------------------------------------------------------------
 template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT, int CDK, int CH, bool COOP>
-__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (COOP ? 3 : 1))) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld,
+__global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (COOP ? 3 : 1))) mhsa_mma_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int sec,
                                                                   const __nv_bfloat16* __restrict__ dctx, int ld_dctx,
                                                                   long long n_seq, int T_, int heads_, int dk_,
                                                                   __nv_bfloat16* __restrict__ dqkv, int ld_d) {
@@ -518,7 +483,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
     const float sc = rs * 1.4426950408889634f;
     const int ntj = (T + 7) >> 3;
     const int piece = CT > 0 ? 8
-                             : (piece_bytes(dk, ld, ld_dctx, d) == 8 && (ld_d % 4) == 0 ? 8 : (piece_bytes(dk, ld, ld_dctx, d) >= 4 && (ld_d % 2) == 0 ? 4 : 2));
+                             : (piece_bytes(dk, ld, ld_dctx, sec) == 8 && (ld_d % 4) == 0 ? 8 : (piece_bytes(dk, ld, ld_dctx, sec) >= 4 && (ld_d % 2) == 0 ? 4 : 2));
     const int n_tasks = static_cast<int>(n_seq * heads);
     const int W = COOP ? gridDim.x : gridDim.x * WPS;
     const int gw = COOP ? blockIdx.x : blockIdx.x * WPS + warp;
@@ -540,14 +505,14 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
             if constexpr (fast) {
                 const uint32_t t0s = wbase_s + 2 * stage * 4 * TILE;
                 tile_load_map(t0s, src, lmap, piece);
-                tile_load_map(t0s + 2 * TILE, src + d, lmap, piece);
-                tile_load_map(t0s + 4 * TILE, src + 2 * d, lmap, piece);
+                tile_load_map(t0s + 2 * TILE, src + sec, lmap, piece);
+                tile_load_map(t0s + 4 * TILE, src + 2 * sec, lmap, piece);
                 tile_load_map(t0s + 6 * TILE, gsrc, gmap, piece);
             } else {
                 __nv_bfloat16* t0 = wbase + stage * 4 * TILE;
                 tile_load(t0, src, ld, T, dk, piece, ctid, cnt, PT);
-                tile_load(t0 + TILE, src + d, ld, T, dk, piece, ctid, cnt, PT);
-                tile_load(t0 + 2 * TILE, src + 2 * d, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + TILE, src + sec, ld, T, dk, piece, ctid, cnt, PT);
+                tile_load(t0 + 2 * TILE, src + 2 * sec, ld, T, dk, piece, ctid, cnt, PT);
                 tile_load(t0 + 3 * TILE, gsrc, ld_dctx, T, dk, piece, ctid, cnt, PT);
             }
         }
@@ -759,11 +724,11 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
         }
         phase_sync();
         if constexpr (fast) {
-            tile_store_map(k, gout + d + h * dk, smap, piece);
-            tile_store_map(v, gout + 2 * d + h * dk, smap, piece);
+            tile_store_map(k, gout + sec + h * dk, smap, piece);
+            tile_store_map(v, gout + 2 * sec + h * dk, smap, piece);
         } else {
-            tile_store(k, gout + d + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
-            tile_store(v, gout + 2 * d + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
+            tile_store(k, gout + sec + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
+            tile_store(v, gout + 2 * sec + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
         }
         phase_sync();
         stage = (stage + 1) % STG;
@@ -772,7 +737,7 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
 }
 
 template <int TP, int KSD, int NTD, int STG, int WPS, bool FAST, int CT = 0, int CDK = 0, int CH = 0, bool COOP = false>
-int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     const long long tasks = n_seq * heads;
     NR_REQUIRE(tasks < (1ll << 31), "mhsa: too many (sequence, head) tasks");
@@ -788,12 +753,12 @@ int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int
                                                           static_cast<long long>(num_sms()) * per_sm));
     if (!bwd) {
         NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, n_seq, T,
+        mhsa_mma_fwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, sec, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out, drop.p,
                                                                              drop.seed);
     } else {
         NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv,
+        mhsa_mma_bwd_kernel<TP, KSD, NTD, STG, WPS, FAST, CT, CDK, CH, COOP><<<grid, WPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld_qkv, sec,
                                                                              static_cast<const __nv_bfloat16*>(dctx), ld_dctx, n_seq, T,
                                                                              heads, dk, static_cast<__nv_bfloat16*>(out), ld_out);
     }
@@ -805,10 +770,10 @@ int launch_mma_cfg2(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int
 
 // the per-lane copy plan covers tiles of up to 128 pieces of >= 4 bytes; anything else takes the generic loops
 template <int TP, int KSD, int NTD, int STG, int WPS>
-int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                    void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     const int d = heads * dk;
-    int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, d);
+    int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, sec);
     if (bwd) piece = (piece == 8 && (ld_out % 4) == 0) ? 8 : ((piece >= 4 && (ld_out % 2) == 0) ? 4 : 2);
 #ifdef NEWSREC_TRIAGE
     static const bool force_loops = getenv("NEWSREC_ATTN_LOOPS") != nullptr;  // tuning switch (tools/kbench.py), triage builds only
@@ -824,16 +789,16 @@ int launch_mma_cfg(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int 
     if constexpr (TP == 32 && KSD == 2 && NTD == 3) {
         // the reference's title encoder (config.py: num_words_title 20, 15 heads x 20) gets a fully fixed-shape kernel
         if (fast && !no_fixed && piece == 8 && T == 20 && dk == 20 && heads == 15)
-            return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, true, 20, 20, 15>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out,
+            return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, true, 20, 20, 15>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out,
                                                                              drop, stream);
     }
     if (fast)
-        return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
-    return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, false>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+        return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, true>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    return launch_mma_cfg2<TP, KSD, NTD, STG, WPS, false>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
 }
 
 template <int TP, int KSD, int NTD>
-int launch_mma(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+int launch_mma(bool bwd, const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
     // 64-row tiles (history-level attention): one cooperative CTA of TP/16 warps per (sequence, head)
     if constexpr (TP > 32) {
@@ -846,7 +811,7 @@ int launch_mma(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_d
             if constexpr (TP == 64 && KSD == 2 && NTD == 3) {
                 // the reference's user encoder (config.py: num_clicked_news_a_user 50, 15 heads x 20): fixed shape
                 const int d = heads * dk;
-                int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, d);
+                int piece = piece_bytes(dk, ld_qkv, bwd ? ld_dctx : ld_out, sec);
                 if (bwd && (ld_out % 4) != 0) piece = 0;
 #ifdef NEWSREC_TRIAGE
                 static const bool no_fixed = getenv("NEWSREC_ATTN_GENERIC") != nullptr;
@@ -854,48 +819,58 @@ int launch_mma(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_d
                 constexpr bool no_fixed = false;
 #endif
                 if (!no_fixed && piece == 8 && T == 50 && dk == 20 && heads == 15)
-                    return launch_mma_cfg2<TP, KSD, NTD, 2, TP / 16, false, 50, 20, 15, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads,
+                    return launch_mma_cfg2<TP, KSD, NTD, 2, TP / 16, false, 50, 20, 15, true>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads,
                                                                                               dk, out, ld_out, drop, stream);
             }
-            return launch_mma_cfg2<TP, KSD, NTD, 2, TP / 16, false, 0, 0, 0, true>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out,
+            return launch_mma_cfg2<TP, KSD, NTD, 2, TP / 16, false, 0, 0, 0, true>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out,
                                                                                    ld_out, drop, stream);
         }
         if (bwd)
-            return launch_mma_cfg<TP, KSD, NTD, 2, 3>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+            return launch_mma_cfg<TP, KSD, NTD, 2, 3>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
     }
-    return launch_mma_cfg<TP, KSD, NTD, 2, 4>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    return launch_mma_cfg<TP, KSD, NTD, 2, 4>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
 }
 
 template <int TP>
-int dispatch_dk(bool bwd, const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+int dispatch_dk(bool bwd, const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                 void* out, int ld_out, DropoutCfg drop, cudaStream_t stream) {
-    if (dk <= 16) return launch_mma<TP, 1, 2>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
-    if (dk <= 24) return launch_mma<TP, 2, 3>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
-    return launch_mma<TP, 2, 4>(bwd, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    if (dk <= 16) return launch_mma<TP, 1, 2>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    if (dk <= 24) return launch_mma<TP, 2, 3>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
+    return launch_mma<TP, 2, 4>(bwd, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, out, ld_out, drop, stream);
 }
 
 }  // namespace
 
-int mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx, DropoutCfg drop,
+int mhsa_core_fwd(const void* qkv, int ld_qkv, int sec, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx, DropoutCfg drop,
                   cudaStream_t stream) {
     if (n_seq == 0) return 0;
     NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
     NR_REQUIRE(dk >= 2 && dk <= 32, "mhsa: head size d_k=%d not in [2,32]", dk);
     NR_REQUIRE(ld_ctx >= heads * dk + 1, "mhsa: context pitch %d has no room for the ones column", ld_ctx);
+    NR_REQUIRE(sec >= heads * dk && ld_qkv >= 3 * sec, "mhsa: Q|K|V section stride %d / pitch %d too small for d=%d", sec, ld_qkv, heads * dk);
     ProfScope ps("mhsa_core_fwd", static_cast<int>(n_seq), T, heads * dk, stream);
-    if (T <= 32) return dispatch_dk<32>(false, qkv, ld_qkv, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
-    return dispatch_dk<64>(false, qkv, ld_qkv, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
+    if (T <= 32) return dispatch_dk<32>(false, qkv, ld_qkv, sec, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
+    return dispatch_dk<64>(false, qkv, ld_qkv, sec, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
 }
 
-int mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+int mhsa_core_bwd(const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                   void* dqkv, int ld_dqkv, cudaStream_t stream) {
     if (n_seq == 0) return 0;
     NR_REQUIRE(T >= 1 && T <= 64, "mhsa: sequence length %d not in [1,64]", T);
     NR_REQUIRE(dk >= 2 && dk <= 32, "mhsa: head size d_k=%d not in [2,32]", dk);
+    NR_REQUIRE(sec >= heads * dk && ld_qkv >= 3 * sec && ld_dqkv >= 3 * sec, "mhsa: Q|K|V section stride %d too small / pitches %d %d",
+               sec, ld_qkv, ld_dqkv);
     ProfScope ps("mhsa_core_bwd", static_cast<int>(n_seq), T, heads * dk, stream);
     const DropoutCfg nodrop{0.f, 0};
-    if (T <= 32) return dispatch_dk<32>(true, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
-    return dispatch_dk<64>(true, qkv, ld_qkv, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
+    if (mhsa_title_bwd_supported(T, dk, heads, sec, ld_qkv, ld_dctx, ld_dqkv))  // the news encoder's shape: whole titles per CTA, TMA in / out
+        return mhsa_title_bwd(qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, heads, dqkv, ld_dqkv, stream);
+    if (sec > heads * dk) {  // the head-level kernels below write head columns only: the section padding of dQ|dK|dV must be zero
+        for (int i = 0; i < 3; ++i)
+            NR_CHECK_CUDA(cudaMemset2DAsync(static_cast<__nv_bfloat16*>(dqkv) + i * sec + heads * dk, sizeof(__nv_bfloat16) * ld_dqkv, 0,
+                                            sizeof(__nv_bfloat16) * (sec - heads * dk), static_cast<size_t>(n_seq) * T, stream));
+    }
+    if (T <= 32) return dispatch_dk<32>(true, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
+    return dispatch_dk<64>(true, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
 }
 
 }  // namespace nr

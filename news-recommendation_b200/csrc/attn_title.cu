@@ -1,0 +1,404 @@
+// Title-level multi-head self-attention backward (reference src/model/general/attention/multihead_self.py:15-23 and
+// scaled_dot_product.py, through autograd) for the news encoder's shape: T = 20 words, d_k = 20, up to 15 heads.
+//
+//   dA = dCtx V^T;  dS = A (dA - sum A dA)/sqrt(dk);  dQ = dS K;  dK = dS^T Q;  dV = A^T dCtx        (A recomputed from Q, K)
+//
+// Why a second kernel next to attn.cu: the head-level kernel there moves every 20 x 20 head tile with 8-byte cp.async
+// pieces (a 40-byte head row has no 16-byte phase) and is bound by the LSU data pipe -- 418 shared-memory wavefronts per
+// head, a third of them the asynchronous copies themselves (ncu, profiles/ncu_r01_attention_final.csv).  Here a CTA owns
+// WHOLE TITLES: one TMA box brings the 20 full Q|K|V rows of a title (all heads, contiguous, sector aligned), a second one
+// the 20 dCtx rows, and one TMA store writes the 20 dQ|dK|dV rows back.  Warp h owns head h.  No copy instruction touches
+// the LSU pipe; what is left are the ldmatrix fragment loads and a 2.3 KB per-warp scratch for A / dS (126 wavefronts).
+//
+// The 16-byte phase: with Q | K | V sections at columns 0, sec, 2*sec (sec % 8 == 0, nr_ops.h) head h starts 40*h bytes into
+// its section in all four operands: 16-byte aligned for even h, 8 bytes off for odd h.  ldmatrix needs aligned 16-byte row
+// pieces, so a head's 20 columns are covered by three aligned 8-column groups starting at gb = 40h - 8*(h & 1):
+//     even h:  [0,16) as one k16 step, [16,24) as a k8 step whose columns 20..23 belong to head h+1
+//     odd  h:  [-4,4) as a k8 step whose columns -4..-1 belong to head h-1, [4,20) as one k16 step
+// Foreign columns are zeroed in the fragment registers (select, so that NaN payloads cannot leak) when they are a
+// contraction index and simply not stored when they are an output column.  Rows 20..23 of a tile (k8 steps over the title
+// rows) are whatever follows the tile in shared memory: the matching fragment lanes are zeroed the same way.
+//
+// Shared-memory row pitches are (odd multiple of 16) bytes: eight consecutive rows start in eight distinct bank quads, so
+// every ldmatrix phase is conflict free; the TMA boxes are simply declared wider than the rows (zero filled / dropped).
+#include <algorithm>
+
+#define NR_WATCHDOG_SYMBOL g_attn_dev_error
+#include "nr_fused.cuh"
+#include "nr_mma.cuh"
+#include "nr_ops.h"
+
+namespace nr {
+
+extern int g_launches;
+
+int read_attn_device_error(int* out4) {
+    return static_cast<int>(cudaMemcpyFromSymbol(out4, fused::g_attn_dev_error, sizeof(int) * 4));
+}
+
+namespace title {
+
+using namespace fused;
+using namespace mma;
+
+constexpr int kT = 20;           // words per title
+constexpr int kDk = 20;          // head width
+constexpr int kMaxHeads = 15;    // compute warps per CTA (+ 1 TMA warp = 512 threads)
+constexpr int kIn = 2;           // titles in flight (input stages)
+constexpr int kOut = 2;          // result tiles (a TMA store drains one while the warps fill the other)
+constexpr int kScrPitch = 48;    // bytes per scratch row: 24 bf16 key columns
+constexpr int kScrTile = 24 * kScrPitch;
+constexpr int kScrWarp = 2 * kScrTile;  // A | dS of one head
+
+struct Params {
+    int n_seq, heads;
+    uint32_t sec2;        // section stride in bytes
+    uint32_t pq, pc;      // shared-memory row pitch of the Q|K|V tile / the dCtx tile (bytes)
+    uint32_t qkv_tile;    // bytes reserved for the Q|K|V tile of a stage (128-byte multiple)
+    uint32_t in_stage;    // qkv_tile + dCtx tile
+    uint32_t out_stage;   // == qkv_tile
+    uint32_t tx;          // bytes one stage's two boxes deliver
+    float rs, sc;         // 1/sqrt(dk), log2(e)/sqrt(dk)
+};
+
+__device__ __forceinline__ uint32_t sel(bool keep, uint32_t v) { return keep ? v : 0u; }
+
+__global__ void __launch_bounds__((kMaxHeads + 1) * 32, 1)
+mhsa_title_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_dc,
+                      const __grid_constant__ CUtensorMap tm_out, const Params p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const uint32_t in_base = base, out_base = base + kIn * p.in_stage, scr_base = out_base + kOut * p.out_stage;
+    const uint32_t bar_off = kIn * p.in_stage + kOut * p.out_stage + p.heads * kScrWarp;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(base_ptr + bar_off);
+    uint64_t* const full = bars;                 // [kIn]   TMA -> warps
+    uint64_t* const empty = bars + kIn;          // [kIn]   warps -> TMA (stage consumed)
+    uint64_t* const ofull = bars + 2 * kIn;      // [kOut]  warps -> TMA (results written)
+    uint64_t* const oempty = bars + 2 * kIn + kOut;  // [kOut]  TMA -> warps (store has drained the tile)
+
+    // every byte a fragment load can touch is initialised: slack rows / padding columns read finite zeros before the first TMA
+    for (uint32_t i = tid; i < bar_off / 16; i += blockDim.x) reinterpret_cast<uint4*>(base_ptr)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int i = 0; i < kIn; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], p.heads);
+        }
+        for (int i = 0; i < kOut; ++i) {
+            mbar_init(&ofull[i], p.heads);
+            mbar_init(&oempty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    fence_proxy_async();  // the zero fill above is ordered before any TMA write to the same bytes
+    __syncthreads();
+
+    const int n_my = (p.n_seq - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    if (warp == p.heads) {
+        // ---------------- TMA warp: loads two titles ahead, stores each finished tile ----------------
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_qkv);
+            tma_prefetch_desc(&tm_dc);
+            tma_prefetch_desc(&tm_out);
+            auto load = [&](int it) {
+                const int s = it % kIn;
+                const int row = (static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * kT;
+                mbar_arrive_expect_tx(&full[s], p.tx);
+                tma_load_2d(base_ptr + s * p.in_stage, &tm_qkv, &full[s], 0, row);
+                tma_load_2d(base_ptr + s * p.in_stage + p.qkv_tile, &tm_dc, &full[s], 0, row);
+            };
+            for (int it = 0; it < kIn && it < n_my; ++it) load(it);
+            for (int j = 0; j < n_my; ++j) {
+                const int o = j % kOut;
+                f_wait(&ofull[o], (j / kOut) & 1, 70);
+                tma_store_2d(&tm_out, base_ptr + kIn * p.in_stage + o * p.out_stage, 0,
+                             (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * kT);
+                bulk_commit();
+                if (j + kIn < n_my) {
+                    f_wait(&empty[j % kIn], (j / kIn) & 1, 71);
+                    load(j + kIn);
+                }
+                bulk_wait_read<0>();
+                mbar_arrive(&oempty[o]);
+            }
+            bulk_wait_all();
+        }
+        return;
+    }
+
+    // ---------------- compute warps: warp h owns head h of every title of this CTA ----------------
+    const int h = warp;
+    const bool odd = (h & 1) != 0;
+    const uint32_t gb = 40u * h - (odd ? 8u : 0u);  // first aligned 8-column group of the head (bytes into the section)
+    const uint32_t k16b = gb + (odd ? 16u : 0u);    // the 16-column contraction step
+    const uint32_t k8b = gb + (odd ? 0u : 32u);     // the 8-column contraction step (4 live + 4 foreign columns)
+    const bool v8 = odd ? (t4 >= 2) : (t4 < 2);     // this lane's two columns of the 8-column step are the head's own
+    const bool c0ok = !odd || t4 >= 2;              // output columns of group 0 / group 2 that belong to the head
+    const bool c2ok = odd || t4 < 2;
+    const bool lo2 = t4 < 2;                        // key columns 16 + 2*t4 (+1) < 20; also: rows 16 + 2*t4 (+1) < 20
+    const uint32_t pq = p.pq, pc = p.pc;
+    const uint32_t r15q = (lane & 15) * pq, r7q = (lane & 7) * pq, r15c = (lane & 15) * pc, r7c = (lane & 7) * pc;
+    const uint32_t hi = (lane >> 4) * 16u, mid = ((lane >> 3) & 1) * 16u;
+    const uint32_t ps = scr_base + h * kScrWarp, dsb = ps + kScrTile;  // A | dS scratch of this head
+    const uint32_t at0 = ((lane & 7) + (lane >> 4) * 8) * kScrPitch + mid;  // x4.trans, key rows 0..15 as m
+    const uint32_t at8 = (16 + (lane & 7)) * kScrPitch;                      // rows 16..23 (the k8 step over query rows)
+    const uint32_t at1 = (lane & 15) * kScrPitch + 32u;                      // x2.trans, key rows 16..23 as m
+    const uint32_t st_scr = g * kScrPitch + t4 * 4u;
+    const float rs = p.rs, sc = p.sc;
+
+    for (int it = 0; it < n_my; ++it) {
+        const int s = it % kIn, o = it % kOut;
+        const uint32_t Q = in_base + s * p.in_stage, K = Q + p.sec2, V = K + p.sec2, G = Q + p.qkv_tile;
+        const uint32_t ob = out_base + o * p.out_stage;
+        f_wait(&full[s], (it / kIn) & 1, 72);
+
+        // ---- phase A (query rows i): A, dS -> scratch; dQ -> result tile ----
+        uint32_t kb16[3][2], kb8[3], vb16[3][2], vb8[3], kt16[3][2], kt8[3];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            lds_x2(kb16[nt], K + k16b + nt * 8 * pq + r7q + mid);
+            lds_x2(vb16[nt], V + k16b + nt * 8 * pq + r7q + mid);
+            lds_x1(&kb8[nt], K + k8b + nt * 8 * pq + r7q);
+            lds_x1(&vb8[nt], V + k8b + nt * 8 * pq + r7q);
+            kb8[nt] = sel(v8, kb8[nt]);
+            vb8[nt] = sel(v8, vb8[nt]);
+            lds_x2_t(kt16[nt], K + gb + 16 * nt + r15q);
+            lds_x1_t(&kt8[nt], K + gb + 16 * nt + 16 * pq + r7q);
+            kt8[nt] = sel(lo2, kt8[nt]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            uint32_t aq[4], ag[4], aq8[2], ag8[2];
+            if (mt == 0) {
+                lds_x4(aq, Q + k16b + r15q + hi);
+                lds_x4(ag, G + k16b + r15c + hi);
+                lds_x2(aq8, Q + k8b + r15q);
+                lds_x2(ag8, G + k8b + r15c);
+            } else {  // rows 16..23 only: the second half of this row block is dead
+                uint32_t t[2];
+                lds_x2(t, Q + k16b + 16 * pq + r7q + mid);
+                aq[0] = t[0], aq[1] = 0u, aq[2] = t[1], aq[3] = 0u;
+                lds_x2(t, G + k16b + 16 * pc + r7c + mid);
+                ag[0] = t[0], ag[1] = 0u, ag[2] = t[1], ag[3] = 0u;
+                lds_x1(&aq8[0], Q + k8b + 16 * pq + r7q);
+                lds_x1(&ag8[0], G + k8b + 16 * pc + r7c);
+                aq8[1] = ag8[1] = 0u;
+            }
+            aq8[0] = sel(v8, aq8[0]), aq8[1] = sel(v8, aq8[1]);
+            ag8[0] = sel(v8, ag8[0]), ag8[1] = sel(v8, ag8[1]);
+            float sm[3][4], dp[3][4];
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                sm[nt][0] = sm[nt][1] = sm[nt][2] = sm[nt][3] = 0.f;
+                dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+                mma_bf16(sm[nt], aq, kb16[nt]);     // S  = Q K^T
+                mma_bf16_k8(sm[nt], aq8, &kb8[nt]);
+                mma_bf16(dp[nt], ag, vb16[nt]);     // dA = dCtx V^T
+                mma_bf16_k8(dp[nt], ag8, &vb8[nt]);
+            }
+            // softmax over the 20 live key columns (fp32, exp(S)/(sum exp(S) + 1e-8) in its stable form), then dS
+            const bool row0 = mt == 0 || g < 4;  // rows 16 + g < 20
+            constexpr float kNegInf = -__builtin_huge_valf();
+            float m0 = kNegInf, m1 = kNegInf;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const bool ok = nt < 2 || lo2;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sm[nt][e] = ok ? sm[nt][e] : kNegInf;
+                m0 = fmaxf(m0, fmaxf(sm[nt][0], sm[nt][1]));
+                if (mt == 0) m1 = fmaxf(m1, fmaxf(sm[nt][2], sm[nt][3]));
+            }
+            m0 = quad_max(m0) * sc;
+            if (mt == 0) m1 = quad_max(m1) * sc;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    sm[nt][e] = exp2f(fmaf(sm[nt][e], sc, -m0));
+                    l0 += sm[nt][e];
+                    if (mt == 0) {
+                        sm[nt][2 + e] = exp2f(fmaf(sm[nt][2 + e], sc, -m1));
+                        l1 += sm[nt][2 + e];
+                    }
+                }
+            }
+            l0 = quad_sum(l0);
+            const float i0 = 1.f / (l0 + 1e-8f * exp2f(-m0));
+            float i1 = 0.f;
+            if (mt == 0) {
+                l1 = quad_sum(l1);
+                i1 = 1.f / (l1 + 1e-8f * exp2f(-m1));
+            }
+            float del0 = 0.f, del1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const bool ok = nt < 2 || lo2;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    sm[nt][e] = (ok && row0) ? sm[nt][e] * i0 : 0.f;
+                    del0 += ok ? sm[nt][e] * dp[nt][e] : 0.f;
+                    if (mt == 0) {
+                        sm[nt][2 + e] = ok ? sm[nt][2 + e] * i1 : 0.f;
+                        del1 += ok ? sm[nt][2 + e] * dp[nt][2 + e] : 0.f;
+                    } else {
+                        sm[nt][2 + e] = 0.f;
+                    }
+                }
+            }
+            del0 = quad_sum(del0);
+            if (mt == 0) del1 = quad_sum(del1);
+            uint32_t a16[4], a8[2];
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const bool ok = nt < 2 || lo2;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    dp[nt][e] = (ok && row0) ? sm[nt][e] * (dp[nt][e] - del0) * rs : 0.f;
+                    dp[nt][2 + e] = (mt == 0 && ok) ? sm[nt][2 + e] * (dp[nt][2 + e] - del1) * rs : 0.f;
+                }
+                const uint32_t p01 = pack_bf16x2(sm[nt][0], sm[nt][1]), d01 = pack_bf16x2(dp[nt][0], dp[nt][1]);
+                const uint32_t p23 = pack_bf16x2(sm[nt][2], sm[nt][3]), d23 = pack_bf16x2(dp[nt][2], dp[nt][3]);
+                const uint32_t so = st_scr + mt * 16 * kScrPitch + nt * 16;
+                sts32(ps + so, p01);   // rows 20..23 are written as zeros: they are contraction indices of phase B
+                sts32(dsb + so, d01);
+                if (mt == 0) {
+                    sts32(ps + so + 8 * kScrPitch, p23);
+                    sts32(dsb + so + 8 * kScrPitch, d23);
+                }
+                if (nt == 0) a16[0] = d01, a16[1] = d23;
+                if (nt == 1) a16[2] = d01, a16[3] = d23;
+                if (nt == 2) a8[0] = d01, a8[1] = d23;
+            }
+            // dQ = dS K  (A = dS straight from the registers)
+            if (mt == 0 && it >= kOut) f_wait(&oempty[o], ((it / kOut) - 1) & 1, 73);  // the store of title it-2 has drained this tile
+#pragma unroll
+            for (int nd = 0; nd < 3; ++nd) {
+                float dq[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16(dq, a16, kt16[nd]);
+                mma_bf16_k8(dq, a8, &kt8[nd]);
+                const bool cok = nd == 1 || (nd == 0 ? c0ok : c2ok);
+                const uint32_t oa = ob + (mt * 16 + g) * pq + gb + 16 * nd + 4 * t4;
+                if (cok && row0) sts32(oa, pack_bf16x2(dq[0], dq[1]));
+                if (mt == 0 && cok) sts32(oa + 8 * pq, pack_bf16x2(dq[2], dq[3]));
+            }
+        }
+        __syncwarp();
+        // ---- phase B (key rows j): dK = dS^T Q, dV = A^T dCtx ----
+        uint32_t qt16[3][2], qt8[3], gt16[3][2], gt8[3];
+#pragma unroll
+        for (int nd = 0; nd < 3; ++nd) {
+            lds_x2_t(qt16[nd], Q + gb + 16 * nd + r15q);
+            lds_x2_t(gt16[nd], G + gb + 16 * nd + r15c);
+            lds_x1_t(&qt8[nd], Q + gb + 16 * nd + 16 * pq + r7q);
+            lds_x1_t(&gt8[nd], G + gb + 16 * nd + 16 * pc + r7c);
+            qt8[nd] = sel(lo2, qt8[nd]);
+            gt8[nd] = sel(lo2, gt8[nd]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            uint32_t ad[4], ap[4], ad8[2], ap8[2];
+            if (mt == 0) {
+                lds_x4_t(ad, dsb + at0);
+                lds_x4_t(ap, ps + at0);
+                lds_x2_t(ad8, dsb + at8 + mid);
+                lds_x2_t(ap8, ps + at8 + mid);
+            } else {
+                uint32_t t[2];
+                lds_x2_t(t, dsb + at1);
+                ad[0] = t[0], ad[1] = 0u, ad[2] = t[1], ad[3] = 0u;
+                lds_x2_t(t, ps + at1);
+                ap[0] = t[0], ap[1] = 0u, ap[2] = t[1], ap[3] = 0u;
+                lds_x1_t(&ad8[0], dsb + at8 + 32u);
+                lds_x1_t(&ap8[0], ps + at8 + 32u);
+                ad8[1] = ap8[1] = 0u;
+            }
+            const bool row0 = mt == 0 || g < 4;
+#pragma unroll
+            for (int nd = 0; nd < 3; ++nd) {
+                float dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16(dk, ad, qt16[nd]);
+                mma_bf16_k8(dk, ad8, &qt8[nd]);
+                mma_bf16(dv, ap, gt16[nd]);
+                mma_bf16_k8(dv, ap8, &gt8[nd]);
+                const bool cok = nd == 1 || (nd == 0 ? c0ok : c2ok);
+                const uint32_t oa = ob + p.sec2 + (mt * 16 + g) * pq + gb + 16 * nd + 4 * t4;
+                if (cok && row0) {
+                    sts32(oa, pack_bf16x2(dk[0], dk[1]));
+                    sts32(oa + p.sec2, pack_bf16x2(dv[0], dv[1]));
+                }
+                if (mt == 0 && cok) {
+                    sts32(oa + 8 * pq, pack_bf16x2(dk[2], dk[3]));
+                    sts32(oa + p.sec2 + 8 * pq, pack_bf16x2(dv[2], dv[3]));
+                }
+            }
+        }
+        fence_proxy_async();  // the result tile is read by the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[s]);
+            mbar_arrive(&ofull[o]);
+        }
+    }
+}
+
+static uint32_t odd16_pitch(uint32_t row_bytes) {  // smallest pitch >= row_bytes that is an odd multiple of 16 bytes
+    uint32_t q = (row_bytes + 15u) / 16u;
+    if ((q & 1u) == 0) ++q;
+    return q * 16u;
+}
+
+}  // namespace title
+
+bool mhsa_title_bwd_supported(int T, int dk, int heads, int sec, int ld_qkv, int ld_dctx, int ld_dqkv) {
+    using namespace title;
+    if (T != kT || dk != kDk || heads < 1 || heads > kMaxHeads) return false;
+    if (sec % 8 != 0 || sec < heads * dk || ld_qkv % 8 != 0 || ld_dctx % 8 != 0 || ld_dqkv != ld_qkv) return false;
+    if (ld_qkv < 3 * sec || ld_dctx < heads * dk) return false;
+    return odd16_pitch(static_cast<uint32_t>(3 * sec) * 2u) <= 2048u && odd16_pitch(static_cast<uint32_t>(ld_dctx) * 2u) <= 2048u;
+}
+
+int mhsa_title_bwd(const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int heads, void* dqkv,
+                   int ld_dqkv, cudaStream_t stream) {
+    using namespace title;
+    NR_REQUIRE(mhsa_title_bwd_supported(kT, kDk, heads, sec, ld_qkv, ld_dctx, ld_dqkv), "mhsa_title_bwd: unsupported layout");
+    NR_REQUIRE(n_seq * kT < (1ll << 31), "mhsa_title_bwd: too many rows");
+    if (n_seq == 0) return 0;
+    Params p;
+    p.n_seq = static_cast<int>(n_seq);
+    p.heads = heads;
+    p.sec2 = static_cast<uint32_t>(sec) * 2u;
+    const uint32_t qkv_row = 3u * p.sec2;                     // bytes of a row that carry sections
+    const uint32_t dc_row = static_cast<uint32_t>(ld_dctx) * 2u;
+    p.pq = odd16_pitch(qkv_row);
+    p.pc = odd16_pitch(dc_row);
+    p.qkv_tile = (kT * p.pq + 127u) & ~127u;
+    const uint32_t dc_tile = (kT * p.pc + 127u) & ~127u;
+    p.in_stage = p.qkv_tile + dc_tile;
+    p.out_stage = p.qkv_tile;
+    p.tx = kT * p.pq + kT * p.pc;
+    p.rs = 1.0f / sqrtf(static_cast<float>(kDk));
+    p.sc = p.rs * 1.4426950408889634f;
+    const size_t smem = 128 + static_cast<size_t>(kIn) * p.in_stage + static_cast<size_t>(kOut) * p.out_stage +
+                       static_cast<size_t>(heads) * kScrWarp + (2 * kIn + 2 * kOut) * sizeof(uint64_t) + 64;
+    NR_REQUIRE(smem <= 227 * 1024, "mhsa_title_bwd: %zu bytes of shared memory", smem);
+    const long long rows = n_seq * kT;
+    CUtensorMap tq, tc, to;
+    NR_PROPAGATE(make_tmap_bytes_2d(&tq, qkv, rows, qkv_row, static_cast<int64_t>(ld_qkv) * 2, static_cast<int>(p.pq), kT));
+    NR_PROPAGATE(make_tmap_bytes_2d(&tc, dctx, rows, dc_row, static_cast<int64_t>(ld_dctx) * 2, static_cast<int>(p.pc), kT));
+    NR_PROPAGATE(make_tmap_bytes_2d(&to, dqkv, rows, qkv_row, static_cast<int64_t>(ld_dqkv) * 2, static_cast<int>(p.pq), kT));
+    static bool attr_set = false;
+    if (!attr_set) {
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_title_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = static_cast<int>(std::min<long long>(n_seq, num_sms()));
+    mhsa_title_bwd_kernel<<<grid, (heads + 1) * 32, smem, stream>>>(tq, tc, to, p);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace nr

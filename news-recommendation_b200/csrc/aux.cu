@@ -534,7 +534,7 @@ int rows_to_bf16_hilo(const float* src, long long n_seq, int T, int D, long long
 // 2d): one CTA per (sequence, head), thread i owns query row i (T <= 64): scores, exp-softmax with the +1e-8, P.V -- all in
 // fp32 registers / shared memory.  The context leaves as bf16 hi + lo planes (pitch ldc, ones column at d in the hi plane).
 constexpr int kF32MaxT = 64, kF32MaxDk = 32;
-__global__ void __launch_bounds__(64) mhsa_f32_fwd_kernel(const float* __restrict__ qkv, int ld, int T, int heads, int dk,
+__global__ void __launch_bounds__(64) mhsa_f32_fwd_kernel(const float* __restrict__ qkv, int ld, int sec, int T, int heads, int dk,
                                                           __nv_bfloat16* __restrict__ c_hi, __nv_bfloat16* __restrict__ c_lo, int ldc) {
     __shared__ float sk[kF32MaxT][kF32MaxDk + 1], sv[kF32MaxT][kF32MaxDk + 1];
     const int seq = blockIdx.x / heads, h = blockIdx.x - seq * heads;
@@ -542,8 +542,8 @@ __global__ void __launch_bounds__(64) mhsa_f32_fwd_kernel(const float* __restric
     const float* base = qkv + static_cast<size_t>(seq) * T * ld + h * dk;
     for (int i = threadIdx.x; i < T * dk; i += blockDim.x) {
         const int r = i / dk, c = i - r * dk;
-        sk[r][c] = base[static_cast<size_t>(r) * ld + d + c];
-        sv[r][c] = base[static_cast<size_t>(r) * ld + 2 * d + c];
+        sk[r][c] = base[static_cast<size_t>(r) * ld + sec + c];
+        sv[r][c] = base[static_cast<size_t>(r) * ld + 2 * sec + c];
     }
     __syncthreads();
     const int i = threadIdx.x;
@@ -594,13 +594,13 @@ __global__ void __launch_bounds__(64) mhsa_f32_fwd_kernel(const float* __restric
         }
     }
 }
-int mhsa_f32_fwd(const float* qkv, int ld, long long n_seq, int T, int heads, int dk, void* c_hi, void* c_lo, int ldc,
+int mhsa_f32_fwd(const float* qkv, int ld, int sec, long long n_seq, int T, int heads, int dk, void* c_hi, void* c_lo, int ldc,
                  cudaStream_t stream) {
     if (n_seq == 0) return 0;
     NR_REQUIRE(T >= 1 && T <= kF32MaxT && dk >= 1 && dk <= kF32MaxDk && ldc >= heads * dk + 1 && n_seq * heads < (1ll << 31),
                "mhsa_f32_fwd: T=%d dk=%d ldc=%d", T, dk, ldc);
     ProfScope ps("mhsa_f32_fwd", static_cast<int>(n_seq), T, heads * dk, stream);
-    mhsa_f32_fwd_kernel<<<static_cast<int>(n_seq * heads), 64, 0, stream>>>(qkv, ld, T, heads, dk, static_cast<__nv_bfloat16*>(c_hi),
+    mhsa_f32_fwd_kernel<<<static_cast<int>(n_seq * heads), 64, 0, stream>>>(qkv, ld, sec, T, heads, dk, static_cast<__nv_bfloat16*>(c_hi),
                                                                            static_cast<__nv_bfloat16*>(c_lo), ldc);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());

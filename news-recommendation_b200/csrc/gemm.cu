@@ -196,6 +196,28 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
     return 0;
 }
 
+// Untyped 2-D tensor map: rows of `row_bytes` valid bytes at pitch `pitch_bytes`, moved as 8-byte elements (so that a box
+// can be up to 2 KB wide), box = box_bytes x box_rows, no swizzle.  box_bytes may exceed row_bytes: the tail is zero
+// filled on loads and dropped on stores (it lets the caller choose a bank-conflict-free row pitch in shared memory).
+int make_tmap_bytes_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes, int64_t pitch_bytes, int box_bytes,
+                       int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    NR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+    NR_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && pitch_bytes % 16 == 0 && row_bytes % 8 == 0 && row_bytes >= 8,
+               "TMA bytes map: base %p / pitch %lld / row %lld misaligned", base, (long long)pitch_bytes, (long long)row_bytes);
+    NR_REQUIRE(box_bytes % 16 == 0 && box_bytes >= 16 && box_bytes <= 2048 && box_rows >= 1 && box_rows <= 256 && rows >= 1,
+               "TMA bytes map: bad box %d B x %d", box_bytes, box_rows);
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(row_bytes / 8), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_bytes / 8), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (bytes) failed with CUresult %d (rows=%lld row=%lld pitch=%lld box=%dx%d)", (int)r,
+               (long long)rows, (long long)row_bytes, (long long)pitch_bytes, box_bytes, box_rows);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // gemm_nt planning
 // ------------------------------------------------------------------------------------------------

@@ -23,8 +23,11 @@ namespace nr {
 
 extern int g_launches;
 
+int read_attn_device_error(int* out4);
 int read_gru_device_error(int* out4) {
-    return static_cast<int>(cudaMemcpyFromSymbol(out4, fused::g_gru_dev_error, sizeof(int) * 4));
+    const int rc = static_cast<int>(cudaMemcpyFromSymbol(out4, fused::g_gru_dev_error, sizeof(int) * 4));
+    if (rc != 0 || out4[0] != 0) return rc;
+    return read_attn_device_error(out4);  // the title-level attention kernel keeps its own record (attn_title.cu)
 }
 
 namespace gru {

@@ -406,5 +406,7 @@ __device__ __forceinline__ uint64_t dropout_bits4(uint64_t seed, uint64_t group)
 // box, rows of box_cols * 2 bytes, a multiple of 16).
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems, int box_cols,
                       int box_rows, int swizzle_bytes = 128);
+int make_tmap_bytes_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t row_bytes, int64_t pitch_bytes, int box_bytes,
+                       int box_rows);
 
 }  // namespace nr

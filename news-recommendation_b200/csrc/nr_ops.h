@@ -56,11 +56,16 @@ int rows_to_bf16(const float* src, long long n_seq, int T, int D, long long s_se
 // X[row(seg,t)] = table_bf16[ids[seg*T+t]] (bit-exact copy), ones column at D, optional dropout, optional padded layout
 int gather_rows(const long long* ids, long long n_tok, int T, const void* table, int V, int D, int ld_table, void* X,
                 int ld_x, int padded, DropoutCfg drop, int* bad_id_flag, cudaStream_t stream);
-// multi-head self attention core on packed Q|K|V bf16 [n_seq*T x ld_qkv]  (d = heads*dk)
-int mhsa_core_fwd(const void* qkv, int ld_qkv, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
+// multi-head self attention core on packed Q|K|V bf16 [n_seq*T x ld_qkv]: sections start at columns 0, sec, 2*sec
+// (sec >= d = heads*dk; dQKV uses the same sections)
+int mhsa_core_fwd(const void* qkv, int ld_qkv, int sec, long long n_seq, int T, int heads, int dk, void* ctx, int ld_ctx,
                   DropoutCfg drop, cudaStream_t stream);
-int mhsa_core_bwd(const void* qkv, int ld_qkv, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
+int mhsa_core_bwd(const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int T, int heads, int dk,
                   void* dqkv, int ld_dqkv, cudaStream_t stream);
+// title-level backward (attn_title.cu): T = 20, d_k = 20, <= 15 heads, sections with a 16-byte phase (sec % 8 == 0)
+bool mhsa_title_bwd_supported(int T, int dk, int heads, int sec, int ld_qkv, int ld_dctx, int ld_dqkv);
+int mhsa_title_bwd(const void* qkv, int ld_qkv, int sec, const void* dctx, int ld_dctx, long long n_seq, int heads, void* dqkv,
+                   int ld_dqkv, cudaStream_t stream);
 // dscore_r = w_r (dw_r - sum_seg w dw), dw_r = dOut[seg] . X_r
 int pool_dscore(const void* X, int lda, int D, long long n_seg, int seg_len, const float* w, const float* dout, int ldo,
                 float* dscore, cudaStream_t stream);
@@ -94,7 +99,7 @@ int gru_fwd_persistent(int B, int S, int Hd, int ldh, int ldg, const float* gi, 
 // precise user encoder (NRMS precise mode): hi/lo K-concatenated operand rows, fp32 attention with hi/lo context planes
 int rows_to_bf16_hilo(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col, void* dst,
                       int ld, cudaStream_t stream);
-int mhsa_f32_fwd(const float* qkv, int ld, long long n_seq, int T, int heads, int dk, void* c_hi, void* c_lo, int ldc,
+int mhsa_f32_fwd(const float* qkv, int ld, int sec, long long n_seq, int T, int heads, int dk, void* c_hi, void* c_lo, int ldc,
                  cudaStream_t stream);
 // scores[i] = news[cand[i]] . user[s] for seg_offsets[s] <= i < seg_offsets[s+1]  (batched evaluate.py:245-265)
 int segment_dot(const float* news, long long n_news, int D, const long long* cand, long long n_cand, const long long* seg_offsets,

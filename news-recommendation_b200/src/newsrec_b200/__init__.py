@@ -109,8 +109,8 @@ SIGNATURES = {
     "nr_gather_rows": (_i, [_vp, _ll, _i, _vp, _i, _i, _i, _vp, _i, _f, _ull, _vp, _vp]),
     "nr_linear": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "nr_gemm_tn": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "nr_mhsa_core_fwd": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _i, _f, _ull, _vp]),
-    "nr_mhsa_core_bwd": (_i, [_vp, _i, _vp, _i, _ll, _i, _i, _i, _vp, _i, _vp]),
+    "nr_mhsa_core_fwd": (_i, [_vp, _i, _i, _ll, _i, _i, _i, _vp, _i, _f, _ull, _vp]),
+    "nr_mhsa_core_bwd": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _i, _vp, _i, _vp]),
     "nr_additive_attention_fwd": (_i, [_vp, _ll, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "nr_additive_attention_bwd_workspace": (_ll, [_ll, _i, _i]),
     "nr_additive_attention_bwd": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i,

@@ -99,14 +99,35 @@ def cast_pad(src: torch.Tensor, ld: int, transpose: bool = False) -> torch.Tenso
     return dst
 
 
+def qkv_pitches(d):
+    """(sec, ld3) of the projected rows Q | K | V: sections at columns 0, sec, 2*sec with sec = round_up(d, 8) so that every
+    section has the same 16-byte phase (abi.cu qkv_section); row pitch ld3 = round_up(3*sec, 16)."""
+    sec = ru8(d)
+    return sec, ru16(3 * sec)
+
+
+def stack_qkv(mq, mk, mv):
+    """W_Q | W_K | W_V (or the biases) stacked on dim 0 with zero rows up to the section stride after each."""
+    d = mq.shape[0]
+    pad = qkv_pitches(d)[0] - d
+    parts = []
+    for m in (mq, mk, mv):
+        m = m.float()
+        parts.append(m)
+        if pad:
+            parts.append(m.new_zeros((pad,) + tuple(m.shape[1:])))
+    return torch.cat(parts, dim=0)
+
+
 def mhsa_operands(cache: OperandCache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
     d, q = Wq.shape[0], Wa.shape[0]
-    ldx, ld3, ldq = ru8(d + 1), ru16(3 * d), ru16(q)
+    ldx, ldq = ru8(d + 1), ru16(q)
+    ld3 = qkv_pitches(d)[1]
 
     def build(Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
-        wqkv = torch.cat((Wq, Wk, Wv), dim=0)
+        wqkv = stack_qkv(Wq, Wk, Wv)
         return dict(wqkv=cast_pad(wqkv, ldx), wqkvT=cast_pad(wqkv, ld3, transpose=True),
-                    bqkv=torch.cat((bq, bk, bv)).float().contiguous(),
+                    bqkv=stack_qkv(bq, bk, bv).contiguous(),
                     wa=cast_pad(Wa, ldx), waT=cast_pad(Wa, ldq, transpose=True),
                     ba=ba.float().contiguous(), qv=qv.float().contiguous())
 
@@ -146,7 +167,8 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         lib = load_library()
         dev = require_cuda()
         d, q = Wq.shape[0], Wa.shape[0]
-        ldx, ld3 = ru8(d + 1), ru16(3 * d)
+        ldx = ru8(d + 1)
+        sec, ld3 = qkv_pitches(d)
         ops = mhsa_operands(cache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv)
         a = MhsaEncoderFwdArgs()
         if ids is not None:
@@ -191,9 +213,9 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         keep = None
         if precise_dense:
             kcat = cache.get(prefix + ".kcat", (Wq, Wk, Wv), lambda Wq, Wk, Wv: cast_pad(
-                torch.cat((torch.nn.functional.pad(torch.cat((Wq, Wk, Wv), 0).float(), (0, ldx - d)),) * 2, dim=1), 2 * ldx))
+                torch.cat((torch.nn.functional.pad(stack_qkv(Wq, Wk, Wv), (0, ldx - d)),) * 2, dim=1), 2 * ldx))
             C_lo = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
-            keep = (torch.empty((n_tok, 2 * ldx), dtype=torch.bfloat16, device=dev), torch.empty((n_tok, 3 * d), dtype=torch.float32, device=dev))
+            keep = (torch.empty((n_tok, 2 * ldx), dtype=torch.bfloat16, device=dev), torch.empty((n_tok, 3 * sec), dtype=torch.float32, device=dev))
             a.wqkv_kcat_bf16, a.X_kcat_bf16, a.QKV_f32, a.C_lo_bf16 = _p(kcat), _p(keep[0]), _p(keep[1]), _p(C_lo)
         a.X_bf16, a.QKV_bf16, a.C_bf16, a.w, a.out = _p(X), _p(QKV), _p(Cx), _p(w), _p(out)
         a.bad_id_flag = _p(bad_flag)
@@ -214,7 +236,8 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         m = ctx.meta
         dev = X.device
         d, q, T, n_seq = m["d"], m["q"], m["T"], m["n_seq"]
-        ldx, ld3, ldq = ru8(d + 1), ru16(3 * d), ru16(q)
+        ldx, ldq = ru8(d + 1), ru16(q)
+        sec, ld3 = qkv_pitches(d)
         ops = m["ops"]
         dout = dout.contiguous().float()
         emb_w, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv = m["params"]
@@ -226,11 +249,11 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         direct = all(g is not None for g in sinks)
         if direct:
             ws_grads = m["cache"].get(m["prefix"] + ".grad_ws", (), lambda: dict(
-                dWqkv=torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev),
+                dWqkv=torch.zeros((3 * sec, ldx), dtype=torch.float32, device=dev),
                 dWa=torch.zeros((q, ldx), dtype=torch.float32, device=dev)))
             dWqkv, dWa, dqv = ws_grads["dWqkv"], ws_grads["dWa"], sinks[8]
         else:
-            dWqkv = torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev)
+            dWqkv = torch.zeros((3 * sec, ldx), dtype=torch.float32, device=dev)
             dWa = torch.zeros((q, ldx), dtype=torch.float32, device=dev)
             dqv = torch.zeros((q,), dtype=torch.float32, device=dev)
         demb = ddense = None
@@ -264,12 +287,12 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         g_emb = None if emb_direct else demb
         if direct:
             for i in range(3):
-                check(lib.nr_accumulate_ext_grad(_p(dWqkv[i * d:(i + 1) * d]), d, ldx, d, _p(sinks[2 * i]), _p(sinks[2 * i + 1]),
+                check(lib.nr_accumulate_ext_grad(_p(dWqkv[i * sec:i * sec + d]), d, ldx, d, _p(sinks[2 * i]), _p(sinks[2 * i + 1]),
                                                  _stream()), "nr_accumulate_ext_grad")
             check(lib.nr_accumulate_ext_grad(_p(dWa), q, ldx, d, _p(sinks[6]), _p(sinks[7]), _stream()), "nr_accumulate_ext_grad")
             return (None, g_dense, g_emb) + (None,) * 15
-        gW = [dWqkv[i * d:(i + 1) * d, :d].contiguous() for i in range(3)]
-        gb = [dWqkv[i * d:(i + 1) * d, d].contiguous() for i in range(3)]
+        gW = [dWqkv[i * sec:i * sec + d, :d].contiguous() for i in range(3)]
+        gb = [dWqkv[i * sec:i * sec + d, d].contiguous() for i in range(3)]
         return (None, g_dense, g_emb, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2],
                 dWa[:, :d].contiguous(), dWa[:, d].contiguous(), dqv, None, None, None, None, None, None)
 
@@ -380,7 +403,7 @@ class MhsaFn(torch.autograd.Function):
         check(lib.nr_linear(_p(X), N * T, ldx, _p(ops["wqkv"]), 3 * d, ldx, d, 1, 0, 128, _p(ops["bqkv"]), 0, _p(QKV), ld3, 1,
                             _stream()), "nr_linear")
         Cx = torch.empty((N * T, ldx), dtype=torch.bfloat16, device=dev)
-        check(lib.nr_mhsa_core_fwd(_p(QKV), ld3, N, T, heads, d // heads, _p(Cx), ldx, 0.0, 0, _stream()), "nr_mhsa_core_fwd")
+        check(lib.nr_mhsa_core_fwd(_p(QKV), ld3, d, N, T, heads, d // heads, _p(Cx), ldx, 0.0, 0, _stream()), "nr_mhsa_core_fwd")
         ctx.save_for_backward(X, QKV)
         ctx.meta = dict(N=N, T=T, d=d, heads=heads, ops=ops)
         return Cx[:, :d].float().view(N, T, d)
@@ -397,7 +420,7 @@ class MhsaFn(torch.autograd.Function):
         dC = torch.empty((N * T, ldx), dtype=torch.bfloat16, device=dev)
         check(lib.nr_rows_to_bf16(_p(g), N * T, d, d, 1, _p(dC), ldx, _stream()), "nr_rows_to_bf16")
         dQKV = torch.empty((N * T, ld3), dtype=torch.bfloat16, device=dev)
-        check(lib.nr_mhsa_core_bwd(_p(QKV), ld3, _p(dC), ldx, N, T, heads, d // heads, _p(dQKV), ld3, _stream()),
+        check(lib.nr_mhsa_core_bwd(_p(QKV), ld3, d, _p(dC), ldx, N, T, heads, d // heads, _p(dQKV), ld3, _stream()),
               "nr_mhsa_core_bwd")
         dW = torch.zeros((3 * d, ldx), dtype=torch.float32, device=dev)
         check(lib.nr_gemm_tn(_p(dQKV), N * T, 3 * d, ld3, _p(X), N * T, d + 1, ldx, 0, d + 1, 0, _p(dW), ldx, _stream()),

@@ -161,29 +161,35 @@ def check_gemm_tn(Kr=1000, Ma=900, Nb=301, shift=0):
 
 
 # ------------------------------------------------------------------------------------------------
-def check_mhsa_core(n_seq=7, T=20, heads=15, dk=20):
+def check_mhsa_core(n_seq=7, T=20, heads=15, dk=20, sectioned=False):
+    """sectioned: Q | K | V at columns 0, sec, 2*sec with sec = round_up(d, 8) (the encoders' layout; padding columns
+    carry garbage on the way in and must come back as zeros in dQ|dK|dV), else dense sections (sec = d)."""
     lib = load_library()
     d = heads * dk
-    ld3, ldx = ru16(3 * d), ru8(d + 1)
+    sec = ru8(d) if sectioned else d
+    ld3, ldx = ru16(3 * sec), ru8(d + 1)
     qkv = _rand_bf16((n_seq * T, 3 * d), 21, 1.5).requires_grad_(True)
     Q, K, V = [t.view(n_seq, T, heads, dk).transpose(1, 2) for t in qkv.split(d, dim=1)]
     ctx = O.scaled_dot_product_attention(Q, K, V, O.BF16).transpose(1, 2).reshape(n_seq * T, d)
     g = _rand_bf16((n_seq * T, d), 22)
     ctx.backward(g)
     qd = torch.zeros(n_seq * T, ld3)
-    qd[:, :3 * d] = qkv.detach()
+    for i in range(3):
+        qd[:, i * sec:i * sec + d] = qkv.detach()[:, i * d:(i + 1) * d]
     qd = qd.to(torch.bfloat16).to(DEV)
     cd = torch.full((n_seq * T, ldx), 9.0, dtype=torch.bfloat16, device=DEV)
-    check(lib.nr_mhsa_core_fwd(_p(qd), ld3, n_seq, T, heads, dk, _p(cd), ldx, 0.0, 0, _stream()), "mhsa_fwd")
+    check(lib.nr_mhsa_core_fwd(_p(qd), ld3, sec, n_seq, T, heads, dk, _p(cd), ldx, 0.0, 0, _stream()), "mhsa_fwd")
     gd = torch.zeros(n_seq * T, ldx)
     gd[:, :d] = g
     gd = gd.to(torch.bfloat16).to(DEV)
     dq = torch.full((n_seq * T, ld3), 9.0, dtype=torch.bfloat16, device=DEV)
-    check(lib.nr_mhsa_core_bwd(_p(qd), ld3, _p(gd), ldx, n_seq, T, heads, dk, _p(dq), ld3, _stream()), "mhsa_bwd")
+    check(lib.nr_mhsa_core_bwd(_p(qd), ld3, sec, _p(gd), ldx, n_seq, T, heads, dk, _p(dq), ld3, _stream()), "mhsa_bwd")
     torch.cuda.synchronize()
-    c = cd.float().cpu()
+    c, dqc = cd.float().cpu(), dq.float().cpu()
+    got = torch.cat([dqc[:, i * sec:i * sec + d] for i in range(3)], dim=1)
+    pads = torch.cat([dqc[:, i * sec + d:(i + 1) * sec] for i in range(3)], dim=1)
     return {"fwd_rel": relerr(c[:, :d], bf16r(ctx.detach())), "ones_col": bool((c[:, d] == 1).all()),
-            "bwd_rel": relerr(dq.float().cpu()[:, :3 * d], bf16r(qkv.grad))}
+            "bwd_rel": relerr(got, bf16r(qkv.grad)), "pad_zero": bool((pads == 0).all())}
 
 
 def check_additive(N=37, S=20, D=300, q=200):
@@ -527,13 +533,13 @@ def _encoder_fwd_raw(ids, dense, sd, prefix, heads, V, fused=False, p_drop=0.0, 
     """Direct nr_mhsa_encoder_fwd call returning every intermediate buffer (for differential triage).
     fused=True passes the head-packed operands + the lo plane, i.e. selects the one-kernel front end."""
     from newsrec_b200 import MhsaEncoderFwdArgs
-    from newsrec_b200.ops import pack_head_blocks
+    from newsrec_b200.ops import pack_head_blocks, qkv_pitches, stack_qkv
     lib = load_library()
     d, q = 300, 200
-    ldx, ld3 = ru8(d + 1), ru16(3 * d)
+    ldx, ld3 = ru8(d + 1), qkv_pitches(d)[1]
     g = lambda k: sd[f"{prefix}.{k}"].to(DEV)
-    wqkv = torch.cat([g(f"multihead_self_attention.W_{n}.weight") for n in "QKV"], 0)
-    ops = dict(wqkv=cast_pad(wqkv, ldx), bqkv=torch.cat([g(f"multihead_self_attention.W_{n}.bias") for n in "QKV"]).contiguous(),
+    wqkv = stack_qkv(*[g(f"multihead_self_attention.W_{n}.weight") for n in "QKV"])
+    ops = dict(wqkv=cast_pad(wqkv, ldx), bqkv=stack_qkv(*[g(f"multihead_self_attention.W_{n}.bias") for n in "QKV"]).contiguous(),
                wa=cast_pad(g("additive_attention.linear.weight"), ldx), ba=g("additive_attention.linear.bias").contiguous(),
                qv=g("additive_attention.attention_query_vector").contiguous())
     a = MhsaEncoderFwdArgs()

@@ -69,10 +69,14 @@ def test_tcgen05_matches_simt_triage_backend():
 
 
 @pytest.mark.parametrize("kw", [dict(n_seq=7, T=20), dict(n_seq=3, T=50), dict(n_seq=2000, T=20), dict(n_seq=5, T=16, heads=30, dk=10),
-                                dict(n_seq=5, T=33, heads=20, dk=15), dict(n_seq=4, T=64, heads=10, dk=30), dict(n_seq=9, T=7, heads=12, dk=25)])
+                                dict(n_seq=5, T=33, heads=20, dk=15), dict(n_seq=4, T=64, heads=10, dk=30), dict(n_seq=9, T=7, heads=12, dk=25),
+                                # the encoders' sectioned Q|K|V rows (sec = round_up(d, 8)); T=20, d_k=20 takes the title-level kernel
+                                dict(n_seq=7, T=20, sectioned=True), dict(n_seq=1, T=20, sectioned=True), dict(n_seq=2000, T=20, sectioned=True),
+                                dict(n_seq=301, T=20, heads=4, sectioned=True), dict(n_seq=40, T=20, heads=9, sectioned=True),
+                                dict(n_seq=3, T=50, sectioned=True), dict(n_seq=9, T=7, heads=12, dk=25, sectioned=True)])
 def test_attention_core(kw):
     r = G.check_mhsa_core(**kw)
-    assert r["ones_col"] and r["fwd_rel"] < 1e-3 and r["bwd_rel"] < 1e-3, r
+    assert r["ones_col"] and r["pad_zero"] and r["fwd_rel"] < 1e-3 and r["bwd_rel"] < 1e-3, r
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(N=9, S=50), dict(N=50, S=4, D=400), dict(N=1, S=20), dict(N=13, S=32, D=296),

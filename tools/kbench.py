@@ -18,7 +18,8 @@ lib = load_library()
 dev = torch.device("cuda", 0)
 n_seq, T, d, heads, q = 512 * 55, 20, 300, 15, 200
 n_tok = n_seq * T
-ldx, ld3, ldq = ru8(d + 1), ru16(3 * d), ru16(q)
+sec = ru8(d)  # Q | K | V sections at columns 0, sec, 2*sec (ops.qkv_pitches)
+ldx, ld3, ldq = ru8(d + 1), ru16(3 * sec), ru16(q)
 bf = lambda *s: (torch.randn(*s, device=dev) * 0.5).to(torch.bfloat16)
 X, QKV, Cx, dC, dQKV = bf(n_tok, ldx), bf(n_tok, ld3), bf(n_tok, ldx), bf(n_tok, ldx), bf(n_tok, ld3)
 Wqkv, WqkvT, Wa, WaT = bf(3 * d, ldx), bf(d, ld3), bf(q, ldx), bf(d, ldq)
@@ -36,9 +37,9 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 st = _stream()
 
 OPS = {
-    "mhsa_fwd": lambda: lib.nr_mhsa_core_fwd(_p(QKV), ld3, n_seq, T, heads, d // heads, _p(Cx), ldx, 0.0, 0, st),
-    "mhsa_fwd_drop": lambda: lib.nr_mhsa_core_fwd(_p(QKV), ld3, n_seq, T, heads, d // heads, _p(Cx), ldx, 0.2, 1234, st),
-    "mhsa_bwd": lambda: lib.nr_mhsa_core_bwd(_p(QKV), ld3, _p(dC), ldx, n_seq, T, heads, d // heads, _p(dQKV), ld3, st),
+    "mhsa_fwd": lambda: lib.nr_mhsa_core_fwd(_p(QKV), ld3, sec, n_seq, T, heads, d // heads, _p(Cx), ldx, 0.0, 0, st),
+    "mhsa_fwd_drop": lambda: lib.nr_mhsa_core_fwd(_p(QKV), ld3, sec, n_seq, T, heads, d // heads, _p(Cx), ldx, 0.2, 1234, st),
+    "mhsa_bwd": lambda: lib.nr_mhsa_core_bwd(_p(QKV), ld3, sec, _p(dC), ldx, n_seq, T, heads, d // heads, _p(dQKV), ld3, st),
     "qkv": lambda: lib.nr_linear(_p(X), n_tok, ldx, _p(Wqkv), 3 * d, ldx, d, 1, 0, 128, _p(bias3), 0, _p(QKV), ld3, 1, st),
     "pool": lambda: lib.nr_additive_attention_fwd(_p(Cx), n_seq, T, d, ldx, _p(Wa), q, ldx, _p(ba), _p(qv), _p(out), d, _p(w), st),
     "tn900": lambda: lib.nr_gemm_tn(_p(dQKV), n_tok, 3 * d, ld3, _p(X), n_tok, d + 1, ldx, 0, d + 1, 0, _p(dW), ldx, st),
