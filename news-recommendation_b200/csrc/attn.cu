@@ -730,6 +730,13 @@ __global__ void __launch_bounds__(WPS * 32, (TP <= 32 ? (CDK == 20 ? 4 : 3) : (C
             tile_store(k, gout + sec + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
             tile_store(v, gout + 2 * sec + h * dk, ld_d, T, dk, piece, ctid, cnt, PT);
         }
+        if (h == 0 && sec > d) {  // section padding of dQ | dK | dV: zeros (it is a contraction index of the projection backward)
+            const int pw = sec - d;
+            for (int i = ctid; i < T * 3 * pw; i += cnt) {
+                const int r = i / (3 * pw), rem = i - r * 3 * pw, sct = rem / pw;
+                gout[static_cast<size_t>(r) * ld_d + sct * sec + d + (rem - sct * pw)] = __float2bfloat16_rn(0.f);
+            }
+        }
         phase_sync();
         stage = (stage + 1) % STG;
     }
@@ -849,6 +856,8 @@ int mhsa_core_fwd(const void* qkv, int ld_qkv, int sec, long long n_seq, int T, 
     NR_REQUIRE(ld_ctx >= heads * dk + 1, "mhsa: context pitch %d has no room for the ones column", ld_ctx);
     NR_REQUIRE(sec >= heads * dk && ld_qkv >= 3 * sec, "mhsa: Q|K|V section stride %d / pitch %d too small for d=%d", sec, ld_qkv, heads * dk);
     ProfScope ps("mhsa_core_fwd", static_cast<int>(n_seq), T, heads * dk, stream);
+    if (mhsa_title_fwd_supported(T, dk, heads, sec, ld_qkv, ld_ctx))  // the news encoder's shape: whole titles per CTA, TMA in / out
+        return mhsa_title_fwd(qkv, ld_qkv, sec, n_seq, heads, ctx, ld_ctx, drop, stream);
     if (T <= 32) return dispatch_dk<32>(false, qkv, ld_qkv, sec, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
     return dispatch_dk<64>(false, qkv, ld_qkv, sec, nullptr, 0, n_seq, T, heads, dk, ctx, ld_ctx, drop, stream);
 }
@@ -864,11 +873,6 @@ int mhsa_core_bwd(const void* qkv, int ld_qkv, int sec, const void* dctx, int ld
     const DropoutCfg nodrop{0.f, 0};
     if (mhsa_title_bwd_supported(T, dk, heads, sec, ld_qkv, ld_dctx, ld_dqkv))  // the news encoder's shape: whole titles per CTA, TMA in / out
         return mhsa_title_bwd(qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, heads, dqkv, ld_dqkv, stream);
-    if (sec > heads * dk) {  // the head-level kernels below write head columns only: the section padding of dQ|dK|dV must be zero
-        for (int i = 0; i < 3; ++i)
-            NR_CHECK_CUDA(cudaMemset2DAsync(static_cast<__nv_bfloat16*>(dqkv) + i * sec + heads * dk, sizeof(__nv_bfloat16) * ld_dqkv, 0,
-                                            sizeof(__nv_bfloat16) * (sec - heads * dk), static_cast<size_t>(n_seq) * T, stream));
-    }
     if (T <= 32) return dispatch_dk<32>(true, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
     return dispatch_dk<64>(true, qkv, ld_qkv, sec, dctx, ld_dctx, n_seq, T, heads, dk, dqkv, ld_dqkv, nodrop, stream);
 }

@@ -344,6 +344,222 @@ mhsa_title_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// forward:  S = QK^T/sqrt(dk);  A = exp(S)/(sum exp(S) + 1e-8);  ctx = dropout(A V)      (same CTA / warp decomposition)
+// Two CTAs per SM (64 registers): a stage is only the Q|K|V tile, the result tile is the 20 context rows (ones column at d
+// and the zero tail are constants of the tile, written once).
+// ------------------------------------------------------------------------------------------------------------------------
+struct FwdParams {
+    int n_seq, heads, ld_ctx;
+    uint32_t sec2, pq, pc, qkv_tile, out_stage, tx;
+    float sc, dscale;
+    uint32_t thresh;
+    uint64_t seed;
+};
+
+__global__ void __launch_bounds__((kMaxHeads + 1) * 32, 2)
+mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx, const FwdParams p) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const uint32_t in_base = base, out_base = base + kIn * p.qkv_tile;
+    const uint32_t bar_off = kIn * p.qkv_tile + kOut * p.out_stage;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(base_ptr + bar_off);
+    uint64_t* const full = bars;
+    uint64_t* const empty = bars + kIn;
+    uint64_t* const ofull = bars + 2 * kIn;
+    uint64_t* const oempty = bars + 2 * kIn + kOut;
+    for (uint32_t i = tid; i < bar_off / 16; i += blockDim.x) reinterpret_cast<uint4*>(base_ptr)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (tid < kOut * kT)  // the ones column of the context rows (bias trick of the pooling GEMM)
+        *reinterpret_cast<__nv_bfloat16*>(base_ptr + kIn * p.qkv_tile + (tid / kT) * p.out_stage + (tid % kT) * p.pc + p.heads * kDk * 2) =
+            __float2bfloat16_rn(1.0f);
+    if (tid == 0) {
+        for (int i = 0; i < kIn; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], p.heads);
+        }
+        for (int i = 0; i < kOut; ++i) {
+            mbar_init(&ofull[i], p.heads);
+            mbar_init(&oempty[i], 1);
+        }
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    const int n_my = (p.n_seq - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    if (warp == p.heads) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_qkv);
+            tma_prefetch_desc(&tm_ctx);
+            auto load = [&](int it) {
+                const int s = it % kIn;
+                mbar_arrive_expect_tx(&full[s], p.tx);
+                tma_load_2d(base_ptr + s * p.qkv_tile, &tm_qkv, &full[s], 0,
+                            (static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * kT);
+            };
+            for (int it = 0; it < kIn && it < n_my; ++it) load(it);
+            for (int j = 0; j < n_my; ++j) {
+                const int o = j % kOut;
+                f_wait(&ofull[o], (j / kOut) & 1, 80);
+                tma_store_2d(&tm_ctx, base_ptr + kIn * p.qkv_tile + o * p.out_stage, 0,
+                             (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * kT);
+                bulk_commit();
+                if (j + kIn < n_my) {
+                    f_wait(&empty[j % kIn], (j / kIn) & 1, 81);
+                    load(j + kIn);
+                }
+                bulk_wait_read<0>();
+                mbar_arrive(&oempty[o]);
+            }
+            bulk_wait_all();
+        }
+        return;
+    }
+
+    const int h = warp;
+    const bool odd = (h & 1) != 0;
+    const uint32_t gb = 40u * h - (odd ? 8u : 0u);
+    const uint32_t k16b = gb + (odd ? 16u : 0u), k8b = gb + (odd ? 0u : 32u);
+    const bool v8 = odd ? (t4 >= 2) : (t4 < 2);
+    const bool c0ok = !odd || t4 >= 2, c2ok = odd || t4 < 2, lo2 = t4 < 2;
+    const uint32_t pq = p.pq, pc = p.pc;
+    const uint32_t r15q = (lane & 15) * pq, r7q = (lane & 7) * pq;
+    const uint32_t hi = (lane >> 4) * 16u, mid = ((lane >> 3) & 1) * 16u;
+    const float sc = p.sc;
+    const bool drop = p.thresh != 0u;
+
+    for (int it = 0; it < n_my; ++it) {
+        const int s = it % kIn, o = it % kOut;
+        const uint32_t Q = in_base + s * p.qkv_tile, K = Q + p.sec2, V = K + p.sec2;
+        const uint32_t ob = out_base + o * p.out_stage;
+        const long long row_base = static_cast<long long>(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * kT;
+        f_wait(&full[s], (it / kIn) & 1, 82);
+        uint32_t kb16[3][2], kb8[3], vt16[3][2], vt8[3];
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) {
+            lds_x2(kb16[nt], K + k16b + nt * 8 * pq + r7q + mid);
+            lds_x1(&kb8[nt], K + k8b + nt * 8 * pq + r7q);
+            kb8[nt] = sel(v8, kb8[nt]);
+            lds_x2_t(vt16[nt], V + gb + 16 * nt + r15q);
+            lds_x1_t(&vt8[nt], V + gb + 16 * nt + 16 * pq + r7q);
+            vt8[nt] = sel(lo2, vt8[nt]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            uint32_t aq[4], aq8[2];
+            if (mt == 0) {
+                lds_x4(aq, Q + k16b + r15q + hi);
+                lds_x2(aq8, Q + k8b + r15q);
+            } else {
+                uint32_t t[2];
+                lds_x2(t, Q + k16b + 16 * pq + r7q + mid);
+                aq[0] = t[0], aq[1] = 0u, aq[2] = t[1], aq[3] = 0u;
+                lds_x1(&aq8[0], Q + k8b + 16 * pq + r7q);
+                aq8[1] = 0u;
+            }
+            aq8[0] = sel(v8, aq8[0]), aq8[1] = sel(v8, aq8[1]);
+            float sm[3][4];
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                sm[nt][0] = sm[nt][1] = sm[nt][2] = sm[nt][3] = 0.f;
+                mma_bf16(sm[nt], aq, kb16[nt]);
+                mma_bf16_k8(sm[nt], aq8, &kb8[nt]);
+            }
+            const bool row0 = mt == 0 || g < 4;
+            constexpr float kNegInf = -__builtin_huge_valf();
+            float m0 = kNegInf, m1 = kNegInf;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const bool ok = nt < 2 || lo2;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sm[nt][e] = ok ? sm[nt][e] : kNegInf;
+                m0 = fmaxf(m0, fmaxf(sm[nt][0], sm[nt][1]));
+                if (mt == 0) m1 = fmaxf(m1, fmaxf(sm[nt][2], sm[nt][3]));
+            }
+            m0 = quad_max(m0) * sc;
+            if (mt == 0) m1 = quad_max(m1) * sc;
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    sm[nt][e] = exp2f(fmaf(sm[nt][e], sc, -m0));
+                    l0 += sm[nt][e];
+                    if (mt == 0) {
+                        sm[nt][2 + e] = exp2f(fmaf(sm[nt][2 + e], sc, -m1));
+                        l1 += sm[nt][2 + e];
+                    }
+                }
+            }
+            l0 = quad_sum(l0);
+            const float i0 = 1.f / (l0 + 1e-8f * exp2f(-m0));
+            float i1 = 0.f;
+            if (mt == 0) {
+                l1 = quad_sum(l1);
+                i1 = 1.f / (l1 + 1e-8f * exp2f(-m1));
+            }
+            uint32_t a16[4], a8[2];
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const bool ok = nt < 2 || lo2;
+                const uint32_t p01 = pack_bf16x2((ok && row0) ? sm[nt][0] * i0 : 0.f, (ok && row0) ? sm[nt][1] * i0 : 0.f);
+                const uint32_t p23 = pack_bf16x2((mt == 0 && ok) ? sm[nt][2] * i1 : 0.f, (mt == 0 && ok) ? sm[nt][3] * i1 : 0.f);
+                if (nt == 0) a16[0] = p01, a16[1] = p23;
+                if (nt == 1) a16[2] = p01, a16[3] = p23;
+                if (nt == 2) a8[0] = p01, a8[1] = p23;
+            }
+            if (mt == 0 && it >= kOut) f_wait(&oempty[o], ((it / kOut) - 1) & 1, 83);
+#pragma unroll
+            for (int nd = 0; nd < 3; ++nd) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16(c, a16, vt16[nd]);
+                mma_bf16_k8(c, a8, &vt8[nd]);
+                const bool cok = nd == 1 || (nd == 0 ? c0ok : c2ok);
+                const uint32_t oa = ob + (mt * 16 + g) * pc + gb + 16 * nd + 4 * t4;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    if (hf == 1 && mt == 1) continue;
+                    if (cok && (hf == 1 || row0)) sts32(oa + hf * 8 * pc, pack_bf16x2(c[2 * hf], c[2 * hf + 1]));
+                }
+            }
+        }
+        if (drop) {
+            // dropout acts on the bf16 context (multihead_self.py:23 -> news_encoder.py:43): second pass over the head's 20 x 20 block in
+            // 8-byte pieces, ONE counter hash per 4 aligned columns (hashing per fragment pair in the loop above costs 3x the
+            // hashes and made the kernel issue bound: 0.41 ms against 0.26 ms without dropout, ncu profiles/)
+            __syncwarp();
+            const uint64_t gbase = (static_cast<uint64_t>(row_base) * p.ld_ctx + 20u * h) >> 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t i = lane + 32 * k;
+                if (i < kT * 5) {
+                    const uint32_t r = (i * 205u) >> 10, c4 = i - 5u * r;  // i / 5 for i < 128
+                    const uint32_t a = ob + r * pc + 40u * h + 8u * c4;
+                    uint32_t u0, u1;
+                    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(u0), "=r"(u1) : "r"(a));
+                    const uint64_t bits = dropout_bits4(p.seed, gbase + r * (static_cast<uint32_t>(p.ld_ctx) >> 2) + c4);
+                    float2 x = unpack_bf16x2(u0), y = unpack_bf16x2(u1);
+                    x.x *= ((bits & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
+                    x.y *= (((bits >> 16) & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
+                    y.x *= (((bits >> 32) & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
+                    y.y *= (((bits >> 48) & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(pack_bf16x2(x.x, x.y)), "r"(pack_bf16x2(y.x, y.y)) : "memory");
+                }
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[s]);
+            mbar_arrive(&ofull[o]);
+        }
+    }
+}
+
 static uint32_t odd16_pitch(uint32_t row_bytes) {  // smallest pitch >= row_bytes that is an odd multiple of 16 bytes
     uint32_t q = (row_bytes + 15u) / 16u;
     if ((q & 1u) == 0) ++q;
@@ -396,6 +612,54 @@ int mhsa_title_bwd(const void* qkv, int ld_qkv, int sec, const void* dctx, int l
     }
     const int grid = static_cast<int>(std::min<long long>(n_seq, num_sms()));
     mhsa_title_bwd_kernel<<<grid, (heads + 1) * 32, smem, stream>>>(tq, tc, to, p);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool mhsa_title_fwd_supported(int T, int dk, int heads, int sec, int ld_qkv, int ld_ctx) {
+    using namespace title;
+    if (T != kT || dk != kDk || heads < 1 || heads > kMaxHeads) return false;
+    if (sec % 8 != 0 || sec < heads * dk || ld_qkv % 8 != 0 || ld_ctx % 8 != 0 || ld_qkv < 3 * sec || ld_ctx < heads * dk + 1) return false;
+    return odd16_pitch(static_cast<uint32_t>(3 * sec) * 2u) <= 2048u && odd16_pitch(static_cast<uint32_t>(ld_ctx) * 2u) <= 2048u;
+}
+
+int mhsa_title_fwd(const void* qkv, int ld_qkv, int sec, long long n_seq, int heads, void* ctx, int ld_ctx, DropoutCfg drop,
+                   cudaStream_t stream) {
+    using namespace title;
+    NR_REQUIRE(mhsa_title_fwd_supported(kT, kDk, heads, sec, ld_qkv, ld_ctx), "mhsa_title_fwd: unsupported layout");
+    NR_REQUIRE(n_seq * kT < (1ll << 31), "mhsa_title_fwd: too many rows");
+    if (n_seq == 0) return 0;
+    FwdParams p;
+    p.n_seq = static_cast<int>(n_seq);
+    p.heads = heads;
+    p.ld_ctx = ld_ctx;
+    p.sec2 = static_cast<uint32_t>(sec) * 2u;
+    const uint32_t qkv_row = 3u * p.sec2, ctx_row = static_cast<uint32_t>(ld_ctx) * 2u;
+    p.pq = odd16_pitch(qkv_row);
+    p.pc = odd16_pitch(ctx_row);
+    p.qkv_tile = (kT * p.pq + 127u) & ~127u;
+    p.out_stage = (kT * p.pc + 127u) & ~127u;
+    p.tx = kT * p.pq;
+    p.sc = 1.4426950408889634f / sqrtf(static_cast<float>(kDk));
+    p.thresh = static_cast<uint32_t>(drop.p * 65536.0f + 0.5f);
+    p.dscale = drop.p > 0.f ? 1.f / (1.f - drop.p) : 1.f;
+    p.seed = drop.seed;
+    // fragment loads of rows 20..23 of the last stage run into the result tiles, those of ... stay inside the allocation
+    const size_t smem = 128 + static_cast<size_t>(kIn) * p.qkv_tile + static_cast<size_t>(kOut) * p.out_stage +
+                       (2 * kIn + 2 * kOut) * sizeof(uint64_t) + 64;
+    NR_REQUIRE(smem <= 113 * 1024, "mhsa_title_fwd: %zu bytes of shared memory", smem);
+    const long long rows = n_seq * kT;
+    CUtensorMap tq, tc;
+    NR_PROPAGATE(make_tmap_bytes_2d(&tq, qkv, rows, qkv_row, static_cast<int64_t>(ld_qkv) * 2, static_cast<int>(p.pq), kT));
+    NR_PROPAGATE(make_tmap_bytes_2d(&tc, ctx, rows, ctx_row, static_cast<int64_t>(ld_ctx) * 2, static_cast<int>(p.pc), kT));
+    static bool attr_set = false;
+    if (!attr_set) {
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_title_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        attr_set = true;
+    }
+    const int grid = static_cast<int>(std::min<long long>(n_seq, 2ll * num_sms()));
+    mhsa_title_fwd_kernel<<<grid, (heads + 1) * 32, smem, stream>>>(tq, tc, p);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;
