@@ -104,6 +104,13 @@ int nr_dot_score_fwd(const float* cand, const float* user, int B, int C, int D, 
 int nr_dot_score_bwd(const float* cand, const float* user, const float* dlogits, int B, int C, int D, float* dcand,
                      float* duser, void* stream);
 
+/* ---- reference: src/dataset.py:64-85 + default_collate (the slot-major batch the model receives, src/train.py:183-190) --
+   slots[0 .. n_clicked) are the browsed-news tensors, then n_candidates candidate tensors, each int64 [B][L] contiguous and
+   readable by the device (device memory or page-locked host memory, nr_slots_device_readable == 1).  One launch writes the
+   impression-major block out[(b*n_clicked + h)*L + t], then out[B*n_clicked*L + (b*n_candidates + c)*L + t]. */
+int nr_slots_device_readable(const void* const* slots, int n);
+int nr_pack_slots(const void* const* slots, int n_clicked, int n_candidates, int B, int L, long long* out, void* stream);
+
 /* Batched form of the evaluator's scoring loop (src/evaluate.py:245-265 calls get_prediction once per impression and
  * synchronises on .tolist() each time): the news vectors live in ONE device matrix news[n_news][D]; the candidates of
  * impression s are cand[seg_offsets[s] .. seg_offsets[s+1]) (indices into news), user[s] its user vector;

@@ -137,6 +137,18 @@ int nr_accumulate_ext_grad(float* ext, int rows, int ld, int D, float* dW, float
     return accumulate_ext_grad(ext, rows, ld, D, dW, db, S(stream));
 }
 
+// ---- batch feed ------------------------------------------------------------------------------------
+int nr_slots_device_readable(const void* const* slots, int n) {
+    if (slots == nullptr || n <= 0) return 0;
+    return slots_device_readable(slots, n);
+}
+int nr_pack_slots(const void* const* slots, int n_clicked, int n_candidates, int B, int L, long long* out, void* stream) {
+    NR_REQUIRE(slots && out && n_clicked >= 0 && n_candidates >= 0 && B >= 0 && L >= 1, "nr_pack_slots: bad arguments");
+    for (int i = 0; i < n_clicked + n_candidates; ++i) NR_REQUIRE(slots[i] != nullptr, "nr_pack_slots: slot %d is null", i);
+    prof_context("feed");
+    return pack_slots(slots, n_clicked, n_candidates, B, L, out, S(stream));
+}
+
 // ---- NRMS encoders ---------------------------------------------------------------------------------
 // Q | K | V sections of the projected rows start at columns 0, sec, 2*sec with sec = round_up(d, 8): every section (and so
 // every head of every section) has the same 16-byte phase, which the title-level attention kernels rely on.  The packed

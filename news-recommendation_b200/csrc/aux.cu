@@ -656,4 +656,60 @@ int segment_dot(const float* news, long long n_news, int D, const long long* can
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batch feed: the reference hands the model slot-major lists of per-slot (B, L) int64 tensors (default_collate over
+// src/dataset.py:64-85; pinned by the DataLoader, src/train.py:165-171).  ONE launch reads the payload of every slot
+// straight from page-locked host memory (unified addressing: the kernel's loads cross PCIe, no host staging copy, no
+// per-slot cudaMemcpyAsync) and writes the impression-major block the encoders consume:
+//   out[(b*H + h)*L + t] = clicked[h][b][t]            rows [0, B*H)
+//   out[B*H*L + (b*C + c)*L + t] = candidates[c][b][t]  rows [B*H, B*(H+C))
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlotTable = 64;
+struct SlotTable {
+    const long long* p[kSlotTable];
+};
+__global__ void __launch_bounds__(256) pack_slots_kernel(SlotTable tab, int n, int slot0, int H, int C, int B, int L, long long* __restrict__ out) {
+    const long long per = static_cast<long long>(B) * L, total = per * n;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int sl = static_cast<int>(i / per);
+        const long long rem = i - sl * per;
+        const int b = static_cast<int>(rem / L), t = static_cast<int>(rem - static_cast<long long>(b) * L);
+        const int s = slot0 + sl;
+        const long long v = tab.p[sl][rem];
+        const long long dst = s < H ? (static_cast<long long>(b) * H + s) * L + t
+                                    : static_cast<long long>(B) * H * L + (static_cast<long long>(b) * C + (s - H)) * L + t;
+        out[dst] = v;
+    }
+}
+// 1 when every pointer is readable by a kernel on the current device (device / managed memory, or page-locked host memory
+// whose device alias is the same address)
+int slots_device_readable(const void* const* slots, int n) {
+    for (int i = 0; i < n; ++i) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, slots[i]) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) continue;
+        if (at.type != cudaMemoryTypeHost || at.devicePointer != slots[i]) return 0;
+    }
+    return 1;
+}
+int pack_slots(const void* const* slots, int H, int C, int B, int L, long long* out, cudaStream_t stream) {
+    const int n_slots = H + C;
+    if (n_slots == 0 || B == 0 || L == 0) return 0;
+    ProfScope ps("pack_slots", n_slots, B, L, stream);
+    for (int s0 = 0; s0 < n_slots; s0 += kSlotTable) {
+        SlotTable tab;
+        const int n = std::min(kSlotTable, n_slots - s0);
+        for (int i = 0; i < kSlotTable; ++i) tab.p[i] = static_cast<const long long*>(slots[s0 + std::min(i, n - 1)]);
+        const long long total = static_cast<long long>(n) * B * L;
+        const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 32));
+        pack_slots_kernel<<<blocks, 256, 0, stream>>>(tab, n, s0, H, C, B, L, out);
+        ++g_launches;
+        NR_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
 }  // namespace nr

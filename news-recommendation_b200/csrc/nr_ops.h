@@ -108,6 +108,8 @@ int mhsa_f32_fwd(const float* qkv, int ld, int sec, long long n_seq, int T, int 
 int segment_dot(const float* news, long long n_news, int D, const long long* cand, long long n_cand, const long long* seg_offsets,
                 long long n_seg, const float* user, float* scores, int* bad_flag, cudaStream_t stream);
 
+int slots_device_readable(const void* const* slots, int n);
+int pack_slots(const void* const* slots, int H, int C, int B, int L, long long* out, cudaStream_t stream);
 int num_sms();
 
 // ---- live per-kernel timing (bench.py): CUDA events on the launching stream around every kernel ------

@@ -3,6 +3,8 @@
 the device in ONE async H2D transfer and re-ordered there into impression-major blocks."""
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 
@@ -27,6 +29,39 @@ class SlotPacker:
 
     def __init__(self):
         self._bufs = {}
+        self._inflight = []  # (event, slot tensors): page-locked inputs a pack kernel may still be reading
+
+    def _pack_direct(self, clicked, candidates, dev):
+        """One launch that reads every (B, ...) int64 slot tensor straight from page-locked host memory (or device memory)
+        and writes the impression-major block -- no host staging copy, no per-slot H2D copies, no device-side stack /
+        transpose / cat (nr_pack_slots, csrc/aux.cu).  None when the inputs do not qualify."""
+        from . import check, load_library
+        tensors = list(clicked) + list(candidates)
+        t0 = tensors[0]
+        if torch.device(dev).type != "cuda" or t0.dtype != torch.int64 or t0.dim() < 1:
+            return None
+        for t in tensors:
+            if t.dtype != torch.int64 or t.shape != t0.shape or not t.is_contiguous() or not (t.is_cuda or t.is_pinned()):
+                return None
+        lib = load_library()
+        n = len(tensors)
+        table = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        if not lib.nr_slots_device_readable(table, n):
+            return None
+        B = t0.shape[0]
+        L = 1
+        for x in t0.shape[1:]:
+            L *= int(x)
+        out = torch.empty((B * n,) + tuple(t0.shape[1:]), dtype=torch.int64, device=dev)
+        if out.numel():
+            stream = torch.cuda.current_stream()
+            check(lib.nr_pack_slots(table, len(clicked), len(candidates), B, L, C.c_void_p(out.data_ptr()), C.c_void_p(stream.cuda_stream)),
+                  "nr_pack_slots")
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self._inflight = [(e, ts) for e, ts in self._inflight if not e.query()]
+            self._inflight.append((ev, tensors))  # keep the host tensors alive (and out of the pinned pool) until the kernel has read them
+        return out, B
 
     def _stack(self, tensors, dev):
         t0 = tensors[0]
@@ -61,6 +96,9 @@ class SlotPacker:
     def pack(self, clicked, candidates, field, dev):
         """-> (ids (B*H + B*C, ...), B): rows [0, B*H) are the browsed news impression-major, then the candidates."""
         H = len(clicked)
+        direct = self._pack_direct([x[field] for x in clicked], [x[field] for x in candidates], dev)
+        if direct is not None:
+            return direct
         slots = self._stack([x[field] for x in clicked] + [x[field] for x in candidates], dev)  # (H+C, B, ...)
         B = slots.shape[1]
         tail = slots.shape[2:]

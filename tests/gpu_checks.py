@@ -824,3 +824,21 @@ def check_predict_impressions(n_news=500, D=300, n_imp=200, seed=3):
         ref.append(model.get_prediction(news[idx], users[s]))
     ref = torch.cat(ref)
     return {"rel": relerr(got, ref), "n": int(got.numel())}
+
+
+def check_pack_slots(B=37, H=50, Cn=5, tail=(20,), where="pinned"):
+    """SlotPacker.pack through the one-launch batch feed (nr_pack_slots) against the stack / transpose / cat it replaces."""
+    from newsrec_b200.pack import SlotPacker
+    gen = torch.Generator().manual_seed(B * 131 + H)
+    mk = lambda: torch.randint(0, 70000, (B,) + tuple(tail), generator=gen, dtype=torch.int64)
+    place = {"pinned": lambda t: t.pin_memory(), "device": lambda t: t.to(DEV), "pageable": lambda t: t}[where]
+    clicked = [{"f": place(mk())} for _ in range(H)]
+    cand = [{"f": place(mk())} for _ in range(Cn)]
+    pk = SlotPacker()
+    direct = pk._pack_direct([x["f"] for x in clicked], [x["f"] for x in cand], DEV)
+    ids, Bo = pk.pack(clicked, cand, "f", DEV)
+    torch.cuda.synchronize()
+    ref = torch.cat((torch.stack([x["f"].cpu() for x in clicked], 1).reshape(B * H, *tail),
+                     torch.stack([x["f"].cpu() for x in cand], 1).reshape(B * Cn, *tail)), 0)
+    return {"equal": bool(torch.equal(ids.cpu(), ref)), "B": Bo, "direct": direct is not None,
+            "direct_equal": direct is None or bool(torch.equal(direct[0].cpu(), ref))}

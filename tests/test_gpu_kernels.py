@@ -112,3 +112,13 @@ def test_gru_last_hidden_history_50_mixed_lengths(kw):
     r = G.check_gru(**kw)
     assert r["fwd_rel"] < 1e-3, r
     assert r["dx_rel"] < 5e-3 and r["dh0_rel"] < 5e-3 and r["dweight_ih_l0"] < 5e-3 and r["dweight_hh_l0"] < 5e-3, r
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(where="device"), dict(where="pageable"), dict(tail=()), dict(B=1, H=3, Cn=2, tail=(50,)),
+                                dict(B=5, H=70, Cn=9, tail=(7,)), dict(B=512, H=50, Cn=5)])
+def test_batch_feed_pack_slots(kw):
+    """Bit-exact: slot-major (B, ...) int64 tensors -> impression-major id block in one launch (pinned host or device inputs;
+    pageable inputs take the staged copy)."""
+    r = G.check_pack_slots(**kw)
+    assert r["equal"] and r["direct_equal"] and r["B"] == kw.get("B", 37), r
+    assert r["direct"] == (kw.get("where", "pinned") != "pageable"), r
