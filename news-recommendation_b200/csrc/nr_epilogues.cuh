@@ -43,9 +43,18 @@ struct Dropout {
     uint64_t seed;
     // multiplier for element (row, col) of a matrix with pitch ld; cols are visited in aligned groups of 4
     __device__ __forceinline__ void mask4(long long row, int ld, int col4, float* m) const {
-        const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(row) * ld + col4) >> 2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) m[i] = (((bits >> (16 * i)) & 0xffffu) >= thresh) ? scale : 0.f;
+        mask4_group((static_cast<uint64_t>(row) * ld + col4) >> 2, m);
+    }
+    // the same for a precomputed group index ((row * ld + col) >> 2; callers that walk a row keep row * ld / 4 in a register);
+    // 32-bit field tests: the 64-bit shifts / compares of the straightforward form were a quarter of the instructions of the
+    // dropout-carrying epilogues (ncu source page, profiles/)
+    __device__ __forceinline__ void mask4_group(uint64_t group, float* m) const {
+        const uint64_t bits = dropout_bits4(seed, group);
+        const uint32_t lo = static_cast<uint32_t>(bits), hi = static_cast<uint32_t>(bits >> 32);
+        m[0] = ((lo & 0xffffu) >= thresh) ? scale : 0.f;
+        m[1] = ((lo >> 16) >= thresh) ? scale : 0.f;
+        m[2] = ((hi & 0xffffu) >= thresh) ? scale : 0.f;
+        m[3] = ((hi >> 16) >= thresh) ? scale : 0.f;
     }
 };
 
@@ -484,10 +493,11 @@ struct EpiDPoolIn {
                         x[j + 2] = fmaf(wr, d4.z, x[j + 2]); x[j + 3] = fmaf(wr, d4.w, x[j + 3]);
                     }
                     if (drop.p > 0.f) {
+                        const uint64_t g0 = (static_cast<uint64_t>(c.grow) * ld + c.col0 + ch * 32) >> 2;  // ld, col0 are multiples of 4
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             float m[4];
-                            drop.mask4(c.grow, ld, c.col0 + ch * 32 + j, m);
+                            drop.mask4_group(g0 + (j >> 2), m);
                             x[j] *= m[0]; x[j + 1] *= m[1]; x[j + 2] *= m[2]; x[j + 3] *= m[3];
                         }
                     }

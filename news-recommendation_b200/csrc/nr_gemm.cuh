@@ -21,7 +21,7 @@
 namespace nr {
 
 constexpr int kTnThreads = 192;     // gemm_tn
-constexpr int kEpiWarps = 8;                    // gemm_nt epilogue warps: 4 TMEM lane quarters x kEpiParts column parts
+constexpr int kEpiWarps = 8;  // gemm_nt epilogue warps: 4 TMEM lane quarters x kEpiParts column parts
 constexpr int kEpiParts = kEpiWarps / 4;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kGemmThreads = kEpiThreads + 64;  // + TMA producer warp + MMA warp

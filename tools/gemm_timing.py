@@ -22,7 +22,7 @@ dev = torch.device("cuda", 0)
 lib = newsrec_b200.load_library()
 model = NRMS(cfgmod.NRMSConfig).to(dev)
 model.train()
-cand, clicked = bench.synth_slots(B, 7, device=dev)
+_, cand, clicked = bench.synth_slots("NRMS", B, 7, device=dev)
 label = torch.zeros(B, dtype=torch.long, device=dev)
 
 

@@ -25,7 +25,7 @@ model = NRMS(cfgmod.NRMSConfig).to(dev)
 model.train()
 for B in [int(x) for x in sys.argv[1:]] or [16, 64, 256, 512]:
     faulthandler.dump_traceback_later(int(__import__("os").environ.get("PROBE_WATCHDOG", "40")), exit=True)
-    cand, clicked = bench.synth_slots(B, 7, device=dev)
+    _, cand, clicked = bench.synth_slots("NRMS", B, 7, device=dev)
     label = torch.zeros(B, dtype=torch.long, device=dev)
     for it in range(2):
         t0 = time.time()
