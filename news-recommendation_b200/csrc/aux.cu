@@ -135,12 +135,13 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(const long 
         if (p > 0.f) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const uint64_t bits = dropout_bits4(seed, (static_cast<uint64_t>(xr) * ld + col + 4 * h) >> 2);
+                const uint64_t bits = dropout_bits4(seed, static_cast<uint64_t>(xr) * (ld >> 2) + (col >> 2) + h);  // ld % 8 == 0
+                const uint32_t lo = static_cast<uint32_t>(bits), hi = static_cast<uint32_t>(bits >> 32);
                 float2 f0 = unpack_bf16x2(w[2 * h]), f1 = unpack_bf16x2(w[2 * h + 1]);
-                f0.x *= ((bits & 0xffffu) >= thresh) ? scale : 0.f;
-                f0.y *= (((bits >> 16) & 0xffffu) >= thresh) ? scale : 0.f;
-                f1.x *= (((bits >> 32) & 0xffffu) >= thresh) ? scale : 0.f;
-                f1.y *= (((bits >> 48) & 0xffffu) >= thresh) ? scale : 0.f;
+                f0.x *= ((lo & 0xffffu) >= thresh) ? scale : 0.f;
+                f0.y *= ((lo >> 16) >= thresh) ? scale : 0.f;
+                f1.x *= ((hi & 0xffffu) >= thresh) ? scale : 0.f;
+                f1.y *= ((hi >> 16) >= thresh) ? scale : 0.f;
                 w[2 * h] = pack_bf16x2(f0.x, f0.y);
                 w[2 * h + 1] = pack_bf16x2(f1.x, f1.y);
             }
