@@ -122,10 +122,8 @@ struct EpiStore {
 #endif
         const int lane = c.tid & 31;
         WarpTileStore ts;
-        if (use_tma) {
-            ts.attach(c.scratch + 256, c.tid >> 5);
-            ts.begin_tile(lane);
-        }
+        ts.attach(c.scratch + 256, c.tid >> 5);
+        if (use_tma) ts.begin_tile(lane);
         float b[32];
         epi_chunks(
             acc, c,
@@ -139,7 +137,11 @@ struct EpiStore {
             [&](int ch, float* x) {
                 const int lc0 = ch * 32;
                 const bool whole = use_tma && lc0 + 32 <= c.ncols;  // warp-uniform
-                if (!whole && !v) return;
+                // row-mapped bf16 output (conv forward: padded rows -> compact rows): full chunks leave through the staging tile
+                // as coalesced stores (WarpTileStore::put_rows) instead of one 16/32-byte store per lane and row
+                const bool coop = !use_tma && out_bf16 && lc0 + 32 <= c.ncols && c.col0 + lc0 + 32 <= N && (ld & 7) == 0 &&
+                                  ((c.col0 + lc0) & 7) == 0;  // warp-uniform
+                if (!whole && !coop && !v) return;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] += b[j];
                 if (relu) {
@@ -159,6 +161,13 @@ struct EpiStore {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
                     ts.put(&tm_out, w, c.col0 + lc0, c.grow - lane, lane);
+                    return;
+                }
+                if (coop) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+                    ts.put_rows(static_cast<__nv_bfloat16*>(out), ld, w, c.col0 + lc0, v ? static_cast<int>(orow) : -1, lane);
                     return;
                 }
 #pragma unroll

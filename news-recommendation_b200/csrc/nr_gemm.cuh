@@ -172,6 +172,25 @@ struct WarpTileStore {
         }
         ++nput;
     }
+    // Row-mapped destinations (no tensor map fits them): the same staging tile leaves as coalesced 16-byte stores, 8 rows x 64
+    // contiguous bytes per instruction.  my_orow = destination row of this lane's accumulator row, -1 for "drop the row".
+    __device__ __forceinline__ void put_rows(__nv_bfloat16* base, int ld, const uint32_t* w, int col, int my_orow, int lane) {
+        uint8_t* b = buf;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(b + lane * 64 + ((q ^ (lane >> 1)) & 3) * 16) =
+                make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = (lane >> 2) + 8 * k, q = lane & 3;
+            const int orr = __shfl_sync(0xffffffffu, my_orow, r);
+            if (orr >= 0)
+                *(reinterpret_cast<uint4*>(base + static_cast<long long>(orr) * ld + col) + q) =
+                    *reinterpret_cast<const uint4*>(b + r * 64 + ((q ^ (r >> 1)) & 3) * 16);
+        }
+        __syncwarp();
+    }
     static __device__ __forceinline__ void drain(int lane) {  // before the CTA exits
         if (lane == 0) bulk_wait_all();
     }
