@@ -1,7 +1,7 @@
 """Where do the gemm_nt CTAs wait?  One NRMS training step at the bench size with the per-role cycle counters of
 nr_debug_set_gemm_timing switched on; prints, per GEMM launch, the share of the kernel each role spent waiting.
 
-    python tools/gemm_timing.py [batch]
+    python tools/gemm_timing.py [NRMS|NAML|LSTUR|TANR] [batch]
 """
 import os
 import sys
@@ -12,23 +12,29 @@ sys.path.insert(0, os.path.join(ROOT, "news-recommendation_b200", "src"))
 
 import torch  # noqa: E402
 
+import importlib  # noqa: E402
+
 import bench  # noqa: E402
 import config as cfgmod  # noqa: E402
 import newsrec_b200  # noqa: E402
-from model.NRMS import NRMS  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+args = [a for a in sys.argv[1:]]
+name = args[0] if args and not args[0].isdigit() else "NRMS"
+B = int(args[-1]) if args and args[-1].isdigit() else 512
 dev = torch.device("cuda", 0)
 lib = newsrec_b200.load_library()
-model = NRMS(cfgmod.NRMSConfig).to(dev)
+Model = getattr(importlib.import_module("model." + name), name)
+over = {"long_short_term_method": "ini"} if name == "LSTUR" else {}
+model = Model(type("Cfg", (getattr(cfgmod, name + "Config"),), over)).to(dev)
 model.train()
-_, cand, clicked = bench.synth_slots("NRMS", B, 7, device=dev)
+extra, cand, clicked = bench.synth_slots(name, B, 7, device=dev)
 label = torch.zeros(B, dtype=torch.long, device=dev)
 
 
 def step():
     model.zero_grad(set_to_none=True)
-    loss = torch.nn.functional.cross_entropy(model(cand, clicked), label)
+    out = model(extra[0], extra[1].clone(), cand, clicked) if name == "LSTUR" else model(cand, clicked)
+    loss = torch.nn.functional.cross_entropy(out[0], label) + 0.1 * out[1] if isinstance(out, tuple) else torch.nn.functional.cross_entropy(out, label)
     loss.backward()
     torch.cuda.synchronize()
 
