@@ -276,8 +276,6 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
     const DropoutCfg cdrop = {a->ids != nullptr ? a->p_drop : 0.f, a->seed ^ 0x5bd1e995u};
     NR_PROPAGATE(gemm_pool_dinput(dpre, M, a->ldq, a->q, a->waT_bf16, a->d, a->ldq, a->w, a->dout, a->d, a->T, dC, a->ldx,
                                   kIdentity, 0, cdrop, nullptr, 0, st));
-    NR_PROPAGATE(gemm_tn_accumulate(dpre, M, a->q, a->ldq, a->C_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWa_ext,
-                                    a->ldx, st));
     // --- attention backward ---
     NR_PROPAGATE(mhsa_core_bwd(QKV, a->ld3, sec, dC, a->ldx, a->n_seq, a->T, a->heads, a->d / a->heads, dQKV, a->ld3, st));
     // --- projection backward: the input first (the embedding gradient is 97 % of a data-parallel step's all-reduce: the
@@ -292,6 +290,10 @@ int nr_mhsa_encoder_bwd(const nr_mhsa_encoder_bwd_args* a, void* stream) {
         NR_PROPAGATE(gemm_store(dQKV, M, a->ld3, a->wqkvT_bf16, a->d, a->ld3, 3 * sec, 1, 0, 128, nullptr, 0, a->ddense, a->d,
                                 0, kIdentity, 0, kNoDrop, -1, 0, st));
     }
+    // both weight-gradient GEMMs run AFTER the embedding gradient is complete: together they are the window (~0.4 ms) under which
+    // the caller's all-reduce of that gradient hides
+    NR_PROPAGATE(gemm_tn_accumulate(dpre, M, a->q, a->ldq, a->C_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWa_ext,
+                                    a->ldx, st));
     NR_PROPAGATE(gemm_tn_accumulate(dQKV, M, 3 * sec, a->ld3, a->X_bf16, M, a->d + 1, a->ldx, 0, a->d + 1, 0, a->dWqkv_ext,
                                     a->ldx, st));
     return 0;
