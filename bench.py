@@ -180,6 +180,8 @@ def kernel_work(name):
         return 2.0 * a * b * c, 2.0 * a * (b + c)
     if op == "mhsa_core_fwd":                              # [n_seq, T, d]
         return 4.0 * a * b * b * c, 2.0 * a * b * c * 4
+    if op == "mhsa_core_fwd_hilo":                         # accurate mode: + V low plane in, + context low plane out, 3 P.V products
+        return 8.0 * a * b * b * c, 2.0 * a * b * c * 6
     if op == "mhsa_core_bwd":
         return 10.0 * a * b * b * c, 2.0 * a * b * c * 7
     if op == "mhsa_fused_fwd":                             # [n_seq, T, d]: gather + Q|K|V + attention; reads ids + table rows, writes C hi/lo (+X)
@@ -453,7 +455,9 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "l2": "3 rotating batches; per-step intermediates (> 1 GB) exceed the 126 MB L2", "dropout": 0.2},
+                   "l2": "3 rotating batches; per-step intermediates (> 1 GB) exceed the 126 MB L2", "dropout": 0.2,
+                   **({"precision": ("fused" if getattr(cfg, "fused_news_encoder", False) else getattr(cfg, "precision", "fast"))}
+                      if model_name == "NRMS" else {})},
         "e2e": {"value": e2e, "unit": "impressions/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": n_tok_bytes, "d2h_bytes_per_step": 4,
                 "path": "model(candidate_news, clicked_news) with CPU slot lists (the call of the reference's train.py:202), loss.item() every step"},

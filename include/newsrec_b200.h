@@ -172,7 +172,12 @@ typedef struct {
     const void* wqkv_kcat_bf16;  /* [3d][2*ldx]: columns [0,d) = W, [ldx, ldx+d) = W again, zeros elsewhere            */
     void* X_kcat_bf16;           /* [n_seq*T][2*ldx] workspace: hi | lo operand rows                                   */
     float* QKV_f32;              /* [n_seq*T][3*sec] workspace                                                           */
+    /* accurate NEWS variant on the unfused kernels (selected by ids != NULL and V_lo_bf16 != NULL; needs C_lo_bf16 and
+     * nr_mhsa_accurate_supported): V, the attention probabilities and the context are hi/lo bf16 pairs; X_bf16 and QKV_bf16
+     * (the hi planes) are written as usual and saved for the backward. */
+    void* V_lo_bf16;             /* [n_seq*T][sec] low plane of the V section                                            */
 } nr_mhsa_encoder_fwd_args;
+int nr_mhsa_accurate_supported(int T, int d, int heads); /* 1: the accurate news variant exists for this shape */
 int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream);
 /* 1 if the fused front end handles (tokens per title, model width, heads): the reference's news level, T = 20, d_k = 20 */
 int nr_mhsa_fused_supported(int T, int d, int heads);

@@ -163,6 +163,12 @@ static int check_mhsa_shape(long long n_seq, int T, int d, int heads, int q, int
     return 0;
 }
 
+int nr_mhsa_accurate_supported(int T, int d, int heads) {
+    if (heads < 1 || d % heads != 0) return 0;
+    const int sec = qkv_section(d);
+    return mhsa_title_fwd_supported(T, d / heads, heads, sec, (3 * sec + 15) & ~15, (d + 8) & ~7) ? 1 : 0;
+}
+
 int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
     NR_REQUIRE(a != nullptr, "nr_mhsa_encoder_fwd: null args");
     NR_PROPAGATE(check_mhsa_shape(a->n_seq, a->T, a->d, a->heads, a->q, a->ldx, a->ld3));
@@ -201,6 +207,28 @@ int nr_mhsa_encoder_fwd(const nr_mhsa_encoder_fwd_args* a, void* stream) {
         NR_PROPAGATE(gemm_store(a->X_kcat_bf16, M, 2 * a->ldx, a->wqkv_kcat_bf16, 3 * qkv_section(a->d), 2 * a->ldx, 2 * a->ldx, 1, 0, 128,
                                 a->bqkv, 0, a->QKV_f32, 3 * qkv_section(a->d), 0, kIdentity, 0, kNoDrop, -1, 0, st));
         NR_PROPAGATE(mhsa_f32_fwd(a->QKV_f32, 3 * qkv_section(a->d), qkv_section(a->d), a->n_seq, a->T, a->heads, a->d / a->heads, a->C_bf16, a->C_lo_bf16, a->ldx, st));
+        NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
+                                        a->w, st, a->C_lo_bf16));
+        return 0;
+    }
+    if (a->ids != nullptr && a->V_lo_bf16 != nullptr) {
+        // accurate news encoder on the unfused sequence: V, the attention probabilities and the context travel as hi/lo bf16
+        // pairs (the projection GEMM emits the low plane of the V section, the title-level attention kernel splits the
+        // probabilities in registers and writes both context planes, the pooled sum reads both)
+        const int sec = qkv_section(a->d);
+        NR_REQUIRE(a->C_lo_bf16 != nullptr && a->table_bf16 && a->bad_id_flag && a->V >= 1,
+                   "nr_mhsa_encoder_fwd: the accurate variant needs C_lo_bf16 (+ table / bad_id_flag)");
+        NR_REQUIRE(mhsa_title_fwd_supported(a->T, a->d / a->heads, a->heads, sec, a->ld3, a->ldx),
+                   "nr_mhsa_encoder_fwd: the accurate variant needs the title-level attention kernel (T=20, d_k=20, <=15 heads); see nr_mhsa_accurate_supported");
+        NR_PROPAGATE(gather_rows(a->ids, M, a->T, a->table_bf16, a->V, a->d, a->ldx, a->X_bf16, a->ldx, 0,
+                                 DropoutCfg{a->p_drop, a->seed}, a->bad_id_flag, st));
+        NR_PROPAGATE(gemm_store(a->X_bf16, M, a->ldx, a->wqkv_bf16, 3 * sec, a->ldx, a->d, 1, 0, 128, a->bqkv, 0, a->QKV_bf16, a->ld3, 1,
+                                kIdentity, 0, kNoDrop, -1, 0, st, a->V_lo_bf16, sec, 2 * sec));
+        const DropoutCfg cd = {a->p_drop, a->seed ^ 0x5bd1e995u};
+        {
+            ProfScope ps("mhsa_core_fwd_hilo", static_cast<int>(a->n_seq), a->T, a->d, st);
+            NR_PROPAGATE(mhsa_title_fwd(a->QKV_bf16, a->ld3, sec, a->n_seq, a->heads, a->C_bf16, a->ldx, cd, st, a->V_lo_bf16, sec, a->C_lo_bf16));
+        }
         NR_PROPAGATE(gemm_additive_pool(a->C_bf16, M, a->ldx, a->d, a->wa_bf16, a->q, a->ldx, a->ba, a->qv, a->T, a->out, a->d,
                                         a->w, st, a->C_lo_bf16));
         return 0;

@@ -349,23 +349,29 @@ mhsa_title_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 // forward:  S = QK^T/sqrt(dk);  A = exp(S)/(sum exp(S) + 1e-8);  ctx = dropout(A V)      (same CTA / warp decomposition)
 // Two CTAs per SM (64 registers): a stage is only the Q|K|V tile, the result tile is the 20 context rows (ones column at d
 // and the zero tail are constants of the tile, written once).
+// HILO (the accurate mode): V arrives as a hi/lo bf16 pair (second TMA box: the low plane the projection
+// GEMM wrote), the probabilities are split into a hi/lo pair in registers, ctx = A_hi V_hi + A_lo V_hi + A_hi V_lo in fp32 and
+// leaves as a hi/lo pair of planes -- the three bf16 roundings that put the plain path 6e-3 from the fp32 result (V 3.6e-3,
+// context 1.9e-3, probabilities 1.1e-3 on the golden case) drop to ~1e-5 each.  One CTA per SM (149 KB of tiles).
 // ------------------------------------------------------------------------------------------------------------------------
 struct FwdParams {
     int n_seq, heads, ld_ctx;
-    uint32_t sec2, pq, pc, qkv_tile, out_stage, tx;
+    uint32_t sec2, pq, pc, pv, qkv_tile, in_stage, out_tile, out_stage, tx;
     float sc, dscale;
     uint32_t thresh;
     uint64_t seed;
 };
 
-__global__ void __launch_bounds__((kMaxHeads + 1) * 32, 2)
-mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ctx, const FwdParams p) {
+template <bool HILO>
+__global__ void __launch_bounds__((kMaxHeads + 1) * 32, HILO ? 1 : 2)
+mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_vlo,
+                      const __grid_constant__ CUtensorMap tm_ctx, const __grid_constant__ CUtensorMap tm_clo, const FwdParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-    const uint32_t in_base = base, out_base = base + kIn * p.qkv_tile;
-    const uint32_t bar_off = kIn * p.qkv_tile + kOut * p.out_stage;
+    const uint32_t in_base = base, out_base = base + kIn * p.in_stage;
+    const uint32_t bar_off = kIn * p.in_stage + kOut * p.out_stage;
     uint64_t* const bars = reinterpret_cast<uint64_t*>(base_ptr + bar_off);
     uint64_t* const full = bars;
     uint64_t* const empty = bars + kIn;
@@ -373,8 +379,8 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     uint64_t* const oempty = bars + 2 * kIn + kOut;
     for (uint32_t i = tid; i < bar_off / 16; i += blockDim.x) reinterpret_cast<uint4*>(base_ptr)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    if (tid < kOut * kT)  // the ones column of the context rows (bias trick of the pooling GEMM)
-        *reinterpret_cast<__nv_bfloat16*>(base_ptr + kIn * p.qkv_tile + (tid / kT) * p.out_stage + (tid % kT) * p.pc + p.heads * kDk * 2) =
+    if (tid < kOut * kT)  // the ones column of the context rows (bias trick of the pooling GEMM); hi plane only
+        *reinterpret_cast<__nv_bfloat16*>(base_ptr + kIn * p.in_stage + (tid / kT) * p.out_stage + (tid % kT) * p.pc + p.heads * kDk * 2) =
             __float2bfloat16_rn(1.0f);
     if (tid == 0) {
         for (int i = 0; i < kIn; ++i) {
@@ -395,18 +401,24 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         if (lane == 0) {
             tma_prefetch_desc(&tm_qkv);
             tma_prefetch_desc(&tm_ctx);
+            if (HILO) {
+                tma_prefetch_desc(&tm_vlo);
+                tma_prefetch_desc(&tm_clo);
+            }
             auto load = [&](int it) {
                 const int s = it % kIn;
+                const int row = (static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * kT;
                 mbar_arrive_expect_tx(&full[s], p.tx);
-                tma_load_2d(base_ptr + s * p.qkv_tile, &tm_qkv, &full[s], 0,
-                            (static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * kT);
+                tma_load_2d(base_ptr + s * p.in_stage, &tm_qkv, &full[s], 0, row);
+                if (HILO) tma_load_2d(base_ptr + s * p.in_stage + p.qkv_tile, &tm_vlo, &full[s], 0, row);
             };
             for (int it = 0; it < kIn && it < n_my; ++it) load(it);
             for (int j = 0; j < n_my; ++j) {
                 const int o = j % kOut;
+                const int row = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * kT;
                 f_wait(&ofull[o], (j / kOut) & 1, 80);
-                tma_store_2d(&tm_ctx, base_ptr + kIn * p.qkv_tile + o * p.out_stage, 0,
-                             (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * kT);
+                tma_store_2d(&tm_ctx, base_ptr + kIn * p.in_stage + o * p.out_stage, 0, row);
+                if (HILO) tma_store_2d(&tm_clo, base_ptr + kIn * p.in_stage + o * p.out_stage + p.out_tile, 0, row);
                 bulk_commit();
                 if (j + kIn < n_my) {
                     f_wait(&empty[j % kIn], (j / kIn) & 1, 81);
@@ -426,7 +438,7 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
     const uint32_t k16b = gb + (odd ? 16u : 0u), k8b = gb + (odd ? 0u : 32u);
     const bool v8 = odd ? (t4 >= 2) : (t4 < 2);
     const bool c0ok = !odd || t4 >= 2, c2ok = odd || t4 < 2, lo2 = t4 < 2;
-    const uint32_t pq = p.pq, pc = p.pc;
+    const uint32_t pq = p.pq, pc = p.pc, pv = p.pv;
     const uint32_t r15q = (lane & 15) * pq, r7q = (lane & 7) * pq;
     const uint32_t hi = (lane >> 4) * 16u, mid = ((lane >> 3) & 1) * 16u;
     const float sc = p.sc;
@@ -434,11 +446,11 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 
     for (int it = 0; it < n_my; ++it) {
         const int s = it % kIn, o = it % kOut;
-        const uint32_t Q = in_base + s * p.qkv_tile, K = Q + p.sec2, V = K + p.sec2;
+        const uint32_t Q = in_base + s * p.in_stage, K = Q + p.sec2, V = K + p.sec2, VL = Q + p.qkv_tile;
         const uint32_t ob = out_base + o * p.out_stage;
         const long long row_base = static_cast<long long>(static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x)) * kT;
         f_wait(&full[s], (it / kIn) & 1, 82);
-        uint32_t kb16[3][2], kb8[3], vt16[3][2], vt8[3];
+        uint32_t kb16[3][2], kb8[3], vt16[3][2], vt8[3], vl16[HILO ? 3 : 1][2], vl8[HILO ? 3 : 1];
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) {
             lds_x2(kb16[nt], K + k16b + nt * 8 * pq + r7q + mid);
@@ -447,6 +459,11 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             lds_x2_t(vt16[nt], V + gb + 16 * nt + r15q);
             lds_x1_t(&vt8[nt], V + gb + 16 * nt + 16 * pq + r7q);
             vt8[nt] = sel(lo2, vt8[nt]);
+            if (HILO) {
+                lds_x2_t(vl16[nt], VL + gb + 16 * nt + (lane & 15) * pv);
+                lds_x1_t(&vl8[nt], VL + gb + 16 * nt + 16 * pv + (lane & 7) * pv);
+                vl8[nt] = sel(lo2, vl8[nt]);
+            }
         }
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -502,20 +519,34 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 l1 = quad_sum(l1);
                 i1 = 1.f / (l1 + 1e-8f * exp2f(-m1));
             }
-            uint32_t a16[4], a8[2];
+            uint32_t a16[4], a8[2], b16[HILO ? 4 : 1], b8[HILO ? 2 : 1];  // probabilities: hi plane, (HILO) lo plane
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
                 const bool ok = nt < 2 || lo2;
-                const uint32_t p01 = pack_bf16x2((ok && row0) ? sm[nt][0] * i0 : 0.f, (ok && row0) ? sm[nt][1] * i0 : 0.f);
-                const uint32_t p23 = pack_bf16x2((mt == 0 && ok) ? sm[nt][2] * i1 : 0.f, (mt == 0 && ok) ? sm[nt][3] * i1 : 0.f);
+                const float q0 = (ok && row0) ? sm[nt][0] * i0 : 0.f, q1 = (ok && row0) ? sm[nt][1] * i0 : 0.f;
+                const float q2 = (mt == 0 && ok) ? sm[nt][2] * i1 : 0.f, q3 = (mt == 0 && ok) ? sm[nt][3] * i1 : 0.f;
+                const uint32_t p01 = pack_bf16x2(q0, q1), p23 = pack_bf16x2(q2, q3);
                 if (nt == 0) a16[0] = p01, a16[1] = p23;
                 if (nt == 1) a16[2] = p01, a16[3] = p23;
                 if (nt == 2) a8[0] = p01, a8[1] = p23;
+                if (HILO) {
+                    const float2 h01 = unpack_bf16x2(p01), h23 = unpack_bf16x2(p23);
+                    const uint32_t l01 = pack_bf16x2(q0 - h01.x, q1 - h01.y), l23 = pack_bf16x2(q2 - h23.x, q3 - h23.y);
+                    if (nt == 0) b16[0] = l01, b16[1] = l23;
+                    if (nt == 1) b16[2] = l01, b16[3] = l23;
+                    if (nt == 2) b8[0] = l01, b8[1] = l23;
+                }
             }
             if (mt == 0 && it >= kOut) f_wait(&oempty[o], ((it / kOut) - 1) & 1, 83);
 #pragma unroll
             for (int nd = 0; nd < 3; ++nd) {
                 float c[4] = {0.f, 0.f, 0.f, 0.f};
+                if (HILO) {  // small terms first
+                    mma_bf16(c, b16, vt16[nd]);
+                    mma_bf16_k8(c, b8, &vt8[nd]);
+                    mma_bf16(c, a16, vl16[nd]);
+                    mma_bf16_k8(c, a8, &vl8[nd]);
+                }
                 mma_bf16(c, a16, vt16[nd]);
                 mma_bf16_k8(c, a8, &vt8[nd]);
                 const bool cok = nd == 1 || (nd == 0 ? c0ok : c2ok);
@@ -523,12 +554,19 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     if (hf == 1 && mt == 1) continue;
-                    if (cok && (hf == 1 || row0)) sts32(oa + hf * 8 * pc, pack_bf16x2(c[2 * hf], c[2 * hf + 1]));
+                    if (cok && (hf == 1 || row0)) {
+                        const uint32_t hv = pack_bf16x2(c[2 * hf], c[2 * hf + 1]);
+                        sts32(oa + hf * 8 * pc, hv);
+                        if (HILO) {
+                            const float2 hf2 = unpack_bf16x2(hv);
+                            sts32(oa + p.out_tile + hf * 8 * pc, pack_bf16x2(c[2 * hf] - hf2.x, c[2 * hf + 1] - hf2.y));
+                        }
+                    }
                 }
             }
         }
         if (drop) {
-            // dropout acts on the bf16 context (multihead_self.py:23 -> news_encoder.py:43): second pass over the head's 20 x 20 block in
+            // dropout acts on the context (multihead_self.py:23 -> news_encoder.py:43): second pass over the head's 20 x 20 block in
             // 8-byte pieces, ONE counter hash per 4 aligned columns (hashing per fragment pair in the loop above costs 3x the
             // hashes and made the kernel issue bound: 0.41 ms against 0.26 ms without dropout, ncu profiles/)
             __syncwarp();
@@ -542,12 +580,24 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                     uint32_t u0, u1;
                     asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(u0), "=r"(u1) : "r"(a));
                     const uint64_t bits = dropout_bits4(p.seed, gbase + r * (static_cast<uint32_t>(p.ld_ctx) >> 2) + c4);
+                    const uint32_t blo = static_cast<uint32_t>(bits), bhi = static_cast<uint32_t>(bits >> 32);
+                    const float m0 = ((blo & 0xffffu) >= p.thresh) ? p.dscale : 0.f, m1 = ((blo >> 16) >= p.thresh) ? p.dscale : 0.f;
+                    const float m2 = ((bhi & 0xffffu) >= p.thresh) ? p.dscale : 0.f, m3 = ((bhi >> 16) >= p.thresh) ? p.dscale : 0.f;
                     float2 x = unpack_bf16x2(u0), y = unpack_bf16x2(u1);
-                    x.x *= ((bits & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
-                    x.y *= (((bits >> 16) & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
-                    y.x *= (((bits >> 32) & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
-                    y.y *= (((bits >> 48) & 0xffffu) >= p.thresh) ? p.dscale : 0.f;
-                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(pack_bf16x2(x.x, x.y)), "r"(pack_bf16x2(y.x, y.y)) : "memory");
+                    if (HILO) {
+                        uint32_t w0, w1;
+                        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(a + p.out_tile));
+                        const float2 xl = unpack_bf16x2(w0), yl = unpack_bf16x2(w1);
+                        x.x = (x.x + xl.x) * m0, x.y = (x.y + xl.y) * m1, y.x = (y.x + yl.x) * m2, y.y = (y.y + yl.y) * m3;
+                        const uint32_t h0 = pack_bf16x2(x.x, x.y), h1 = pack_bf16x2(y.x, y.y);
+                        const float2 hx = unpack_bf16x2(h0), hy = unpack_bf16x2(h1);
+                        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(h0), "r"(h1) : "memory");
+                        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a + p.out_tile), "r"(pack_bf16x2(x.x - hx.x, x.y - hx.y)),
+                                     "r"(pack_bf16x2(y.x - hy.x, y.y - hy.y)) : "memory");
+                    } else {
+                        x.x *= m0, x.y *= m1, y.x *= m2, y.y *= m3;
+                        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(pack_bf16x2(x.x, x.y)), "r"(pack_bf16x2(y.x, y.y)) : "memory");
+                    }
                 }
             }
         }
@@ -624,42 +674,63 @@ bool mhsa_title_fwd_supported(int T, int dk, int heads, int sec, int ld_qkv, int
     return odd16_pitch(static_cast<uint32_t>(3 * sec) * 2u) <= 2048u && odd16_pitch(static_cast<uint32_t>(ld_ctx) * 2u) <= 2048u;
 }
 
+// v_lo / ctx_lo both non-null: the accurate (hi/lo) variant.  v_lo bf16 [rows][ld_vlo] = low plane of the V section (column 0
+// = first V column); ctx_lo bf16 [rows][ld_ctx] = low plane of the context (no ones column).
 int mhsa_title_fwd(const void* qkv, int ld_qkv, int sec, long long n_seq, int heads, void* ctx, int ld_ctx, DropoutCfg drop,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const void* v_lo, int ld_vlo, void* ctx_lo) {
     using namespace title;
     NR_REQUIRE(mhsa_title_fwd_supported(kT, kDk, heads, sec, ld_qkv, ld_ctx), "mhsa_title_fwd: unsupported layout");
     NR_REQUIRE(n_seq * kT < (1ll << 31), "mhsa_title_fwd: too many rows");
+    const bool hilo = v_lo != nullptr || ctx_lo != nullptr;
+    NR_REQUIRE(!hilo || (v_lo != nullptr && ctx_lo != nullptr && ld_vlo % 8 == 0 && ld_vlo >= heads * kDk),
+               "mhsa_title_fwd: the hi/lo variant needs both low planes (ld_vlo=%d)", ld_vlo);
     if (n_seq == 0) return 0;
     FwdParams p;
     p.n_seq = static_cast<int>(n_seq);
     p.heads = heads;
     p.ld_ctx = ld_ctx;
     p.sec2 = static_cast<uint32_t>(sec) * 2u;
-    const uint32_t qkv_row = 3u * p.sec2, ctx_row = static_cast<uint32_t>(ld_ctx) * 2u;
+    const uint32_t qkv_row = 3u * p.sec2, ctx_row = static_cast<uint32_t>(ld_ctx) * 2u, vlo_row = static_cast<uint32_t>(ld_vlo) * 2u;
     p.pq = odd16_pitch(qkv_row);
     p.pc = odd16_pitch(ctx_row);
+    p.pv = hilo ? odd16_pitch(vlo_row) : 0u;
     p.qkv_tile = (kT * p.pq + 127u) & ~127u;
-    p.out_stage = (kT * p.pc + 127u) & ~127u;
-    p.tx = kT * p.pq;
+    p.in_stage = p.qkv_tile + (hilo ? ((kT * p.pv + 127u) & ~127u) : 0u);
+    p.out_tile = (kT * p.pc + 127u) & ~127u;
+    p.out_stage = (hilo ? 2u : 1u) * p.out_tile;
+    p.tx = kT * p.pq + (hilo ? kT * p.pv : 0u);
     p.sc = 1.4426950408889634f / sqrtf(static_cast<float>(kDk));
     p.thresh = static_cast<uint32_t>(drop.p * 65536.0f + 0.5f);
     p.dscale = drop.p > 0.f ? 1.f / (1.f - drop.p) : 1.f;
     p.seed = drop.seed;
-    // fragment loads of rows 20..23 of the last stage run into the result tiles, those of ... stay inside the allocation
-    const size_t smem = 128 + static_cast<size_t>(kIn) * p.qkv_tile + static_cast<size_t>(kOut) * p.out_stage +
+    // fragment loads of rows 20..23 of a tile run into whatever follows it (the low-plane tile, the next stage, the result
+    // tiles): always inside the allocation, always initialised
+    const size_t smem = 128 + static_cast<size_t>(kIn) * p.in_stage + static_cast<size_t>(kOut) * p.out_stage +
                        (2 * kIn + 2 * kOut) * sizeof(uint64_t) + 64;
-    NR_REQUIRE(smem <= 113 * 1024, "mhsa_title_fwd: %zu bytes of shared memory", smem);
+    const size_t cap = hilo ? 227 * 1024 : 113 * 1024;
+    NR_REQUIRE(smem <= cap, "mhsa_title_fwd: %zu bytes of shared memory", smem);
     const long long rows = n_seq * kT;
-    CUtensorMap tq, tc;
+    CUtensorMap tq, tc, tv, tl;
     NR_PROPAGATE(make_tmap_bytes_2d(&tq, qkv, rows, qkv_row, static_cast<int64_t>(ld_qkv) * 2, static_cast<int>(p.pq), kT));
     NR_PROPAGATE(make_tmap_bytes_2d(&tc, ctx, rows, ctx_row, static_cast<int64_t>(ld_ctx) * 2, static_cast<int>(p.pc), kT));
+    if (hilo) {
+        NR_PROPAGATE(make_tmap_bytes_2d(&tv, v_lo, rows, vlo_row, static_cast<int64_t>(ld_vlo) * 2, static_cast<int>(p.pv), kT));
+        NR_PROPAGATE(make_tmap_bytes_2d(&tl, ctx_lo, rows, ctx_row, static_cast<int64_t>(ld_ctx) * 2, static_cast<int>(p.pc), kT));
+    } else {
+        tv = tq;
+        tl = tc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_title_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_title_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+        NR_CHECK_CUDA(cudaFuncSetAttribute(mhsa_title_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int grid = static_cast<int>(std::min<long long>(n_seq, 2ll * num_sms()));
-    mhsa_title_fwd_kernel<<<grid, (heads + 1) * 32, smem, stream>>>(tq, tc, p);
+    const int grid = static_cast<int>(std::min<long long>(n_seq, (hilo ? 1ll : 2ll) * num_sms()));
+    if (hilo)
+        mhsa_title_fwd_kernel<true><<<grid, (heads + 1) * 32, smem, stream>>>(tq, tv, tc, tl, p);
+    else
+        mhsa_title_fwd_kernel<false><<<grid, (heads + 1) * 32, smem, stream>>>(tq, tv, tc, tl, p);
     ++g_launches;
     NR_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -514,7 +514,8 @@ static Dropout to_drop(const DropoutCfg& c) {
 
 int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
                int rows_per_tile, const float* bias, int relu, void* out, int ld_out, int out_bf16, RowMapCfg rm,
-               int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream) {
+               int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream, void* lo_out, int ld_lo,
+               int lo_col0) {
     if (M == 0) return 0;
     GemmNTPlan plan;
     NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0, EpiStore::kScratchBytes, 0));
@@ -523,6 +524,20 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
     memset(&e, 0, sizeof(e));
     e.use_tma = (out_bf16 && rm.seg_in == 0 && rows_per_tile == kTileM && N >= 32) ? 1 : 0;
     if (e.use_tma) NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_out, out, M, N, ld_out, 32, 32, 64));
+    e.lo_col0 = -1;
+    if (lo_out != nullptr) {
+        NR_REQUIRE(e.use_tma && lo_col0 >= 0 && lo_col0 < N && ld_lo % 8 == 0 && ld_lo >= N - lo_col0 && drop.p == 0.f,
+                   "gemm_store: the low plane needs the TMA epilogue (identity rows, bf16) and no dropout (N=%d lo_col0=%d ld_lo=%d)", N, lo_col0, ld_lo);
+        for (int sl = 0; sl < plan.p.n_slices; ++sl) {  // a 32-column chunk never straddles the first low-plane column
+            const int c0 = sl * plan.p.n_stride;
+            NR_REQUIRE(!(c0 < lo_col0 && lo_col0 < c0 + plan.p.n_stride) || (lo_col0 - c0) % 32 == 0,
+                       "gemm_store: low-plane start %d is not chunk aligned in the slice at column %d", lo_col0, c0);
+        }
+        NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_lo, lo_out, M, N - lo_col0, ld_lo, 32, 32, 64));
+        e.lo_col0 = lo_col0;
+        e.lo_out = static_cast<__nv_bfloat16*>(lo_out);
+        e.ld_lo = ld_lo;
+    }
     e.out = out;
     e.ld = ld_out;
     e.out_bf16 = out_bf16;

@@ -87,6 +87,10 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* o, const float* y, i
 struct EpiStore {
     static constexpr int kScratchBytes = 1024 + kTileStoreBytes;
     CUtensorMap tm_out;  // bf16 output as a TMA tensor (32 x 32 boxes, SWIZZLE_64B); valid when use_tma
+    CUtensorMap tm_lo;   // low plane of the columns >= lo_col0 (bf16(y - bf16(y))), its column 0 = output column lo_col0
+    int lo_col0;         // < 0: no low plane
+    __nv_bfloat16* lo_out;  // the same plane for the (rare) partial chunks that leave through plain stores; pitch ld_lo
+    int ld_lo;
     int use_tma;         // identity row map + bf16 output: full 32-column chunks leave through WarpTileStore
     void* out;
     int ld;
@@ -161,6 +165,14 @@ struct EpiStore {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
                     ts.put(&tm_out, w, c.col0 + lc0, c.grow - lane, lane);
+                    if (lo_col0 >= 0 && c.col0 + lc0 >= lo_col0) {  // warp-uniform (the host checked the chunk alignment)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 h = unpack_bf16x2(w[j]);
+                            w[j] = pack_bf16x2(x[2 * j] - h.x, x[2 * j + 1] - h.y);
+                        }
+                        ts.put(&tm_lo, w, c.col0 + lc0 - lo_col0, c.grow - lane, lane);
+                    }
                     return;
                 }
                 if (coop) {
@@ -184,6 +196,14 @@ struct EpiStore {
                         } else {
                             store_bf16x8(o, y, min(nvalid, 8));
                             if (nvalid > 8) store_bf16x8(o + 8, y + 8, nvalid - 8);
+                        }
+                        if (lo_col0 >= 0 && col >= lo_col0) {  // low plane of a partial chunk (identity rows)
+                            float yl[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) yl[j] = y[j] - bf16_round(y[j]);
+                            __nv_bfloat16* ol = lo_out + orow * ld_lo + (col - lo_col0);
+                            store_bf16x8(ol, yl, min(nvalid, 8));
+                            if (nvalid > 8) store_bf16x8(ol + 8, yl + 8, nvalid - 8);
                         }
                     } else {
                         float* o = static_cast<float*>(out) + orow * ld + col;

@@ -7,7 +7,7 @@ from model.general.attention.additive import AdditiveAttention
 from model.general.attention.multihead_self import MultiHeadSelfAttention
 from newsrec_b200 import require_cuda
 from newsrec_b200.guard import BadIdFlag
-from newsrec_b200.ops import MhsaPoolEncoderFn, OperandCache
+from newsrec_b200.ops import MhsaPoolEncoderFn, OperandCache, precision_mode
 
 
 class NewsEncoder(nn.Module):
@@ -36,7 +36,7 @@ class NewsEncoder(nn.Module):
                                        *self.multihead_self_attention.qkv_parameters(),
                                        a.linear.weight, a.linear.bias, a.attention_query_vector,
                                        self.config.num_attention_heads, p, self._cache, "news", self.bad_id_flag(dev),
-                                       bool(getattr(self.config, "fused_news_encoder", False)))
+                                       precision_mode(self.config))
 
     def forward(self, news):
         """news: {"title": (batch, num_words_title) int64} -> (batch, word_embedding_dim)"""

@@ -4,7 +4,7 @@ import torch.nn as nn
 
 from model.general.attention.additive import AdditiveAttention
 from model.general.attention.multihead_self import MultiHeadSelfAttention
-from newsrec_b200.ops import MhsaPoolEncoderFn, OperandCache
+from newsrec_b200.ops import MhsaPoolEncoderFn, OperandCache, precision_mode
 
 
 class UserEncoder(nn.Module):
@@ -21,4 +21,4 @@ class UserEncoder(nn.Module):
         return MhsaPoolEncoderFn.apply(None, user_vector, None, *self.multihead_self_attention.qkv_parameters(),
                                        a.linear.weight, a.linear.bias, a.attention_query_vector,
                                        self.config.num_attention_heads, 0.0, self._cache, "user", None,
-                                       bool(getattr(self.config, "fused_news_encoder", False)))  # precise mode: fp32-accurate forward
+                                       precision_mode(self.config))  # precise mode: fp32-accurate forward

@@ -26,6 +26,7 @@ class MhsaEncoderFwdArgs(C.Structure):
         ("X_bf16", _vp), ("QKV_bf16", _vp), ("C_bf16", _vp), ("w", _vp), ("out", _vp), ("bad_id_flag", _vp),
         ("wqkv_heads_bf16", _vp), ("bqkv_heads", _vp), ("C_lo_bf16", _vp),
         ("wqkv_kcat_bf16", _vp), ("X_kcat_bf16", _vp), ("QKV_f32", _vp),
+        ("V_lo_bf16", _vp),
     ]
 
 
@@ -121,6 +122,7 @@ SIGNATURES = {
     "nr_segment_dot": (_i, [_vp, _ll, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp]),
     "nr_accumulate_ext_grad": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "nr_dot_score_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "nr_mhsa_accurate_supported": (_i, [_i, _i, _i]),
     "nr_mhsa_encoder_fwd": (_i, [C.POINTER(MhsaEncoderFwdArgs), _vp]),
     "nr_mhsa_fused_supported": (_i, [_i, _i, _i]),
     "nr_mhsa_encoder_bwd_workspace": (_ll, [_ll, _i, _i, _i]),

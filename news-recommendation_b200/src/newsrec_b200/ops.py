@@ -99,6 +99,16 @@ def cast_pad(src: torch.Tensor, ld: int, transpose: bool = False) -> torch.Tenso
     return dst
 
 
+def precision_mode(config):
+    """"fast" | "accurate" | "fused" from a model config (config.py: precision, fused_news_encoder)."""
+    if bool(getattr(config, "fused_news_encoder", False)):
+        return "fused"
+    mode = str(getattr(config, "precision", "fast"))
+    if mode not in ("fast", "accurate", "fused"):
+        raise NewsrecError(f"config.precision must be 'fast', 'accurate' or 'fused' (got {mode!r})")
+    return mode
+
+
 def qkv_pitches(d):
     """(sec, ld3) of the projected rows Q | K | V: sections at columns 0, sec, 2*sec with sec = round_up(d, 8) so that every
     section has the same 16-byte phase (abi.cu qkv_section); row pitch ld3 = round_up(3*sec, 16)."""
@@ -191,9 +201,18 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         # the fused front end (gather -> Q|K|V -> attention in ONE kernel, V / context as hi/lo bf16 pairs) is the PRECISE
         # mode of the news level: 2.6e-3 instead of 7e-3 against the reference's fp32 logits, at ~3.6x the time of the
         # unfused gather | GEMM | attention sequence -- opt-in (config.fused_news_encoder / NEWSREC_FUSED=1)
-        fused = ids is not None and (precise or os.environ.get("NEWSREC_FUSED") == "1") and bool(lib.nr_mhsa_fused_supported(T, d, heads))
-        precise_dense = ids is None and precise  # user encoder of the precise mode: fp32-accurate forward (abi.cu)
-        X = QKV = C_lo = None
+        # precision modes (config.precision):
+        #   "fast"      bf16 storage of every activation (Q|K|V, probabilities, context): fastest, ~6e-3 from the fp32 result
+        #   "accurate"  V / probabilities / context as hi/lo bf16 pairs on the same unfused kernels + fp32-accurate user
+        #               encoder: within the blueprint's 1e-3 of the fp32 oracle on bf16-rounded weights
+        #   "fused"     the one-kernel news front end (same numerics as "accurate", kept for reference; slower)
+        mode = precise if isinstance(precise, str) else ("fused" if precise else "fast")
+        if os.environ.get("NEWSREC_FUSED") == "1":
+            mode = "fused"
+        fused = ids is not None and mode == "fused" and bool(lib.nr_mhsa_fused_supported(T, d, heads))
+        accurate = ids is not None and not fused and mode in ("accurate", "fused") and bool(lib.nr_mhsa_accurate_supported(T, d, heads))
+        precise_dense = ids is None and mode in ("accurate", "fused")  # user encoder: fp32-accurate forward (abi.cu)
+        X = QKV = C_lo = V_lo = None
         if need_bwd or not fused:  # X only exists in HBM when a backward pass (or the unfused sequence) reads it
             X = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
         if not fused and not precise_dense:  # the precise paths keep no bf16 Q|K|V; their backward recomputes it from X
@@ -210,6 +229,10 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
                            lambda Wq, bq, Wk, bk, Wv, bv: pack_head_blocks(Wq, bq, Wk, bk, Wv, bv, heads, ldx))
             C_lo = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
             a.wqkv_heads_bf16, a.bqkv_heads, a.C_lo_bf16 = _p(hb[0]), _p(hb[1]), _p(C_lo)
+        if accurate:
+            C_lo = torch.empty((n_tok, ldx), dtype=torch.bfloat16, device=dev)
+            V_lo = torch.empty((n_tok, sec), dtype=torch.bfloat16, device=dev)
+            a.C_lo_bf16, a.V_lo_bf16 = _p(C_lo), _p(V_lo)
         keep = None
         if precise_dense:
             kcat = cache.get(prefix + ".kcat", (Wq, Wk, Wv), lambda Wq, Wk, Wv: cast_pad(

@@ -261,8 +261,9 @@ def check_gru(B=37, S=50, D=900, Hd=900, seed=3):
 def nrms_model_and_params(V, seed, heads=15, dropout=0.2, fused=False):
     import config as cfgmod
     from model.NRMS import NRMS
+    # fused: False = fast mode, True = the one-kernel front end, "accurate" = hi/lo pairs on the unfused kernels
     cfg = type("Cfg", (cfgmod.NRMSConfig,), dict(num_words=V, num_attention_heads=heads, dropout_probability=dropout,
-                                                 fused_news_encoder=fused))
+                                                 fused_news_encoder=fused is True, precision="accurate" if fused == "accurate" else "fast"))
     sd = O.det_state_dict(O.nrms_shapes(V), seed)
     model = NRMS(cfg)
     model.load_state_dict(sd)
@@ -654,7 +655,8 @@ def build_model(case, V=120, ncat=15, nusers=40, H=6, dropout=0.2, fused=False):
     name = {"nrms": "NRMS", "naml": "NAML", "naml_f400": "NAML", "tanr": "TANR", "lstur_ini": "LSTUR", "lstur_con": "LSTUR"}[case]
     over = dict(num_words=V, num_categories=ncat, num_users=nusers, num_clicked_news_a_user=H, dropout_probability=dropout)
     if name == "NRMS":
-        over["fused_news_encoder"] = fused
+        over["fused_news_encoder"] = fused is True
+        over["precision"] = "accurate" if fused == "accurate" else "fast"
     if case == "naml_f400":
         over["num_filters"] = 400
     if case.startswith("lstur"):
@@ -688,7 +690,7 @@ def check_golden(case, fused=False):
     from golden_util import case_params, load_case, oracle_forward, unique_params
     g = load_case(case)
     p_b = case_params(case, g)
-    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, fused)
+    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, bool(fused))
     (O.click_loss(logits_b) + (0.1 * topic_b if topic_b is not None else 0.0)).backward()
     p_x = case_params(case, g)
     logits_x, topic_x = oracle_forward(case, g, p_x, O.EXACT)

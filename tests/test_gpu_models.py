@@ -37,6 +37,18 @@ def test_golden_case(case):
         assert r["topic_loss_rel_vs_reference"] < 1e-3, r
 
 
+def test_nrms_accurate_mode_golden_case():
+    """config.precision = "accurate": V / attention probabilities / context as hi/lo bf16 pairs on the unfused kernels (the
+    projection GEMM emits the low plane of V, the title-level attention kernel splits the probabilities and writes both
+    context planes) + fp32-accurate user encoder forward.  Meets the blueprint's tolerance: logits within 1e-3 of the fp32
+    oracle on bf16-rounded weights / embeddings."""
+    r = G.check_golden("nrms", fused="accurate")
+    assert r["logits_vs_oracle_bf16"] < 1e-3, r
+    assert r["logits_vs_weights_only_oracle"] < 1e-3, r
+    assert r["logits_vs_reference_fp32"] < 3.5e-3, r
+    assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
+
+
 def test_nrms_precise_mode_golden_case():
     """config.fused_news_encoder -- the PRECISE mode: one-kernel news front end (V / context / probabilities as hi/lo bf16
     pairs) + fp32-accurate user encoder forward.  It meets the blueprint's tolerance: logits within 1e-3 of the fp32 oracle
@@ -49,7 +61,7 @@ def test_nrms_precise_mode_golden_case():
     assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
 
 
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fused", [False, True, "accurate"])
 def test_nrms_mind_shaped_batch_vs_oracle(fused):
     r = G.check_nrms_random(fused=fused)
     assert r["logits_vs_oracle_bf16"] < 1e-3, r
@@ -80,7 +92,7 @@ def test_nrms_train_mode_dropout_statistics():
     assert r["mean_train_vs_eval_rel"] < 0.3, r
 
 
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fused", [False, True, "accurate"])
 def test_nrms_train_mode_matches_masked_oracle(fused):
     """The benchmarked configuration (train mode, dropout 0.2), forward and backward, at the eval-mode tolerances
     (default kernel sequence and the fused precise mode: both draw the same masks from the same counter hash)."""
