@@ -683,11 +683,19 @@ def golden_inputs(case, g):
     return mk("cand"), mk("clicked")
 
 
-def check_golden(case, fused=False):
+def default_nrms_mode():
+    """False ("fast") or "accurate": what the NRMS drop-in does when the config says nothing (config.py / NEWSREC_PRECISION)."""
+    import config as cfgmod
+    return "accurate" if getattr(cfgmod.NRMSConfig, "precision", "fast") == "accurate" else False
+
+
+def check_golden(case, fused=None):
     """A committed golden case (minted from the live reference): CUDA drop-in vs the reference's fp32 outputs, vs the
     oracle under the bf16 storage contract, and -- per gradient -- against the exact fp32 oracle next to the error the
     bf16 contract itself has (kernel_err <= ~1.5 x contract_err is the pass criterion)."""
     from golden_util import case_params, load_case, oracle_forward, unique_params
+    if fused is None:  # the shipped default
+        fused = default_nrms_mode() if case == "nrms" else False
     g = load_case(case)
     p_b = case_params(case, g)
     logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, bool(fused))

@@ -15,12 +15,12 @@ import gpu_checks as G
 pytestmark = pytest.mark.gpu
 CASES = ["nrms", "naml", "naml_f400", "tanr", "lstur_ini", "lstur_con"]
 # Norm-wise error of the logits against the fp32 oracle evaluated on bf16-rounded weights / embeddings -- the tolerance
-# definition of the blueprint, target 1e-3.  The CNN families meet it.  NRMS does not on the default path:
-# its error is the bf16 storage of V and of the attention context (every token of a title sees the SAME rounding error of
-# V_j, so the pooling does not average it out -- DESIGN.md 3a); the precise mode (hi/lo V / context) removes that part and
-# is left with the bf16 probabilities.  LSTUR's error is the bf16 hidden state fed back 6..50 times.  The bounds are the
-# measured values with ~30 % head room, so that a regression shows.
-WEIGHTS_ONLY_BOUND = {"nrms": 8e-3, "naml": 1e-3, "naml_f400": 1e-3, "tanr": 1e-3, "lstur_ini": 3e-3, "lstur_con": 1.5e-3}
+# definition of the blueprint, target 1e-3.  NRMS meets it in its default ("accurate") precision mode: V,
+# the attention probabilities and the context travel as hi/lo bf16 pairs (the plain bf16 storage of exactly these three is
+# what puts the "fast" mode at 6e-3: every token of a title sees the SAME rounding error of V_j, so the pooling does not
+# average it out -- DESIGN.md section 4).  The CNN families meet it as they are.  LSTUR (ini) does not yet: bf16 conv output
+# 1.1e-3 + bf16 news vectors entering the GRU 1.1e-3 + bf16 hidden state fed back 5.5e-4.  Bounds = measured + ~30 %.
+WEIGHTS_ONLY_BOUND = {"nrms": 1e-3, "naml": 1e-3, "naml_f400": 1e-3, "tanr": 1e-3, "lstur_ini": 3e-3, "lstur_con": 1e-3}
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -35,6 +35,16 @@ def test_golden_case(case):
     assert not any(k.startswith("missing_grad:") for k in r), r
     if "topic_loss_rel_vs_reference" in r:
         assert r["topic_loss_rel_vs_reference"] < 1e-3, r
+
+
+def test_nrms_fast_mode_golden_case():
+    """config.precision = "fast" (NEWSREC_PRECISION=fast): every activation stored bf16 -- 18 % less time per step, 6e-3 from
+    the fp32 oracle on bf16 weights; parity against the oracle under that storage contract stays at 1e-3."""
+    r = G.check_golden("nrms", fused=False)
+    assert r["logits_vs_oracle_bf16"] < 1e-3, r
+    assert r["logits_vs_weights_only_oracle"] < 8e-3, r
+    assert r["logits_vs_reference_fp32"] < 1.25 * r["oracle_bf16_vs_reference_fp32"] + 1e-4, r
+    assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
 
 
 def test_nrms_accurate_mode_golden_case():
