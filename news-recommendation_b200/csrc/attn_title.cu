@@ -46,6 +46,7 @@ constexpr int kDk = 20;          // head width
 constexpr int kMaxHeads = 15;    // compute warps per CTA (+ 1 TMA warp = 512 threads)
 constexpr int kIn = 2;           // titles in flight (input stages)
 constexpr int kOut = 2;          // result tiles (a TMA store drains one while the warps fill the other)
+constexpr int kInHilo = 2;       // input stages of the hi/lo forward variant (a third one measured 3 % slower: the variant is MMA / issue bound)
 constexpr int kScrPitch = 48;    // bytes per scratch row: 24 bf16 key columns
 constexpr int kScrTile = 24 * kScrPitch;
 constexpr int kScrWarp = 2 * kScrTile;  // A | dS of one head
@@ -366,6 +367,7 @@ template <bool HILO>
 __global__ void __launch_bounds__((kMaxHeads + 1) * 32, HILO ? 1 : 2)
 mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_vlo,
                       const __grid_constant__ CUtensorMap tm_ctx, const __grid_constant__ CUtensorMap tm_clo, const FwdParams p) {
+    constexpr int kIn = HILO ? kInHilo : title::kIn;  // one CTA per SM in the hi/lo variant: a third title in flight
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -705,8 +707,9 @@ int mhsa_title_fwd(const void* qkv, int ld_qkv, int sec, long long n_seq, int he
     p.seed = drop.seed;
     // fragment loads of rows 20..23 of a tile run into whatever follows it (the low-plane tile, the next stage, the result
     // tiles): always inside the allocation, always initialised
-    const size_t smem = 128 + static_cast<size_t>(kIn) * p.in_stage + static_cast<size_t>(kOut) * p.out_stage +
-                       (2 * kIn + 2 * kOut) * sizeof(uint64_t) + 64;
+    const int n_in = hilo ? kInHilo : kIn;
+    const size_t smem = 128 + static_cast<size_t>(n_in) * p.in_stage + static_cast<size_t>(kOut) * p.out_stage +
+                       (2 * n_in + 2 * kOut) * sizeof(uint64_t) + 64;
     const size_t cap = hilo ? 227 * 1024 : 113 * 1024;
     NR_REQUIRE(smem <= cap, "mhsa_title_fwd: %zu bytes of shared memory", smem);
     const long long rows = n_seq * kT;
