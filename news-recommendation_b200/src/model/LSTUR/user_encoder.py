@@ -20,7 +20,8 @@ class UserEncoder(nn.Module):
     def forward(self, user, clicked_news_length, clicked_news_vector):
         """user (batch, hidden) device fp32; clicked_news_length (batch,) int64; clicked_news_vector (batch, H, 3F)"""
         dev = require_cuda()
-        clicked_news_length[clicked_news_length == 0] = 1  # in place, like the reference (:27)
+        clicked_news_length.clamp_(min=1)  # in place, like the reference's `length[length == 0] = 1` (:27) -- without the
+        # device synchronisation a boolean-mask assignment needs when the lengths already live on the GPU
         g = self.gru
         if self.config.long_short_term_method == "ini":
             return GruLastHiddenFn.apply(clicked_news_vector, clicked_news_length, user, g.weight_ih_l0, g.weight_hh_l0,

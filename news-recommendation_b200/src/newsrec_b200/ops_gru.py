@@ -29,7 +29,7 @@ class GruLastHiddenFn(torch.autograd.Function):
             whhT=cast_pad(Whh, ldb, transpose=True), bih=bih.float().contiguous(), bhh=bhh.float().contiguous()))
         x = x.float()
         h0 = h0.float().contiguous()
-        lengths = lengths.to(dev).long().contiguous()
+        lengths = lengths.to(dev, non_blocking=True).long().contiguous()  # a blocking copy here would drain the news encoder's kernels
         xb = torch.empty((B * S, ldd), dtype=torch.bfloat16, device=dev)
         gi = torch.empty((B * S, ldg), dtype=torch.float32, device=dev)
         gh = torch.empty((S, B, ldg), dtype=torch.float32, device=dev)

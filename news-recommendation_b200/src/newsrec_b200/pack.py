@@ -41,8 +41,8 @@ class SlotPacker:
         if torch.device(dev).type != "cuda" or t0.dtype != torch.int64 or t0.dim() < 1:
             return None
         for t in tensors:
-            if t.dtype != torch.int64 or t.shape != t0.shape or not t.is_contiguous() or not (t.is_cuda or t.is_pinned()):
-                return None
+            if t.dtype != torch.int64 or t.shape != t0.shape or not t.is_contiguous():
+                return None  # (page-locked or not is decided by nr_slots_device_readable below: Tensor.is_pinned() costs ~10 us per slot)
         lib = load_library()
         n = len(tensors)
         table = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
