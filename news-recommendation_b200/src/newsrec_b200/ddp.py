@@ -65,6 +65,7 @@ class FlatGradients:
         for p in self.params:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
+            setattr(p.grad, "_newsrec_direct_grad", True)  # opt-in: the kernels accumulate straight into this view (ops.grad_sink)
             off += pad4(n)
         self.big_numel = pad4(self.params[0].numel())
         self._side = None

@@ -78,11 +78,26 @@ class OperandCache:
     def clear(self):
         self._store.clear()
 
+    def invalidate_operands(self):
+        """Drop every entry derived from parameters (what an optimizer step does implicitly by bumping their version
+        counters); parameter-independent workspaces stay.  bench.py calls it every step so that the timed step pays for
+        the operand refresh of real training."""
+        for name in [n for n, (key, _) in self._store.items() if key]:
+            del self._store[name]
+
+
+DIRECT_GRAD_MARK = "_newsrec_direct_grad"
+
 
 def grad_sink(p):
-    """The parameter's own gradient storage if the kernels can accumulate into it directly, else None."""
+    """The parameter's own gradient storage if the kernels may accumulate into it directly, else None.
+    Direct accumulation bypasses AccumulateGrad (tensor / DDP hooks do not fire, torch.autograd.grad returns nothing for the
+    parameter), so it is an explicit opt-in: the owner of the gradient storage marks it (ddp.FlatGradients does); a .grad that
+    merely exists -- e.g. after optimizer.zero_grad(set_to_none=False) -- takes the ordinary return path."""
     g = getattr(p, "grad", None)
-    if g is None or not p.requires_grad or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device \
+    if g is None or not getattr(g, DIRECT_GRAD_MARK, False):
+        return None
+    if not p.requires_grad or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device \
             or g.shape != p.shape or g.data_ptr() % 16 != 0:  # 16-byte vector reductions (red.global.add.v4.f32)
         return None
     return g
@@ -264,8 +279,8 @@ class MhsaPoolEncoderFn(torch.autograd.Function):
         ops = m["ops"]
         dout = dout.contiguous().float()
         emb_w, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv = m["params"]
-        # Parameters whose .grad already exists as contiguous fp32 storage (ddp.FlatGradients, or a plain earlier
-        # backward) are accumulated IN PLACE by the kernels and get None from this Function: no zero fill, no slice
+        # Parameters whose .grad storage is marked for direct accumulation (ddp.FlatGradients; see grad_sink) are
+        # accumulated IN PLACE by the kernels and get None from this Function: no zero fill, no slice
         # copies, no AccumulateGrad adds (together ~50 small framework kernels and 3 passes over the 85 MB embedding
         # gradient per step).  Anything else takes the allocate-and-return path.
         sinks = [grad_sink(t) for t in (Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv)]

@@ -170,6 +170,10 @@ def test_flat_gradient_views_start_on_16_byte_boundaries():
     assert grad_sink(q) is None
     q.grad = torch.zeros(8)[::2]
     assert grad_sink(q) is None
+    # direct accumulation is an opt-in of the storage's owner: a .grad that merely exists (a plain earlier backward,
+    # optimizer.zero_grad(set_to_none=False)) is NOT written in place -- AccumulateGrad and its hooks keep working
+    q.grad = torch.zeros(4)
+    assert grad_sink(q) is None
 
 
 def test_flat_gradient_all_reduce_equals_single_process_mean_gloo():
