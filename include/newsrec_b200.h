@@ -241,6 +241,7 @@ typedef struct {
     float* w;                       /* [n_seq*T]                                                          */
     float* out;                     /* [n_seq][F]                                                         */
     int* bad_id_flag;
+    void* Y_lo_bf16;          /* optional [n_seq*T][ldf]: low plane of the conv output (accurate mode: the pooled sum reads Y + Y_lo) */
 } nr_cnn_encoder_fwd_args;
 int nr_cnn_encoder_fwd(const nr_cnn_encoder_fwd_args* a, void* stream);
 
@@ -315,6 +316,9 @@ typedef struct {
     float* hs;                      /* fp32 [S+1][B][Hd] hidden states                                    */
     void* hb;                       /* bf16 [S+1][B][ldh]                                                 */
     float* out;                     /* fp32 [B][Hd] last hidden state                                     */
+    /* accurate mode (both non-NULL): the input enters the projection as a hi/lo bf16 pair against K-concatenated weights */
+    const void* wih_kcat_bf16;      /* [3Hd][2*ldd]: columns [0,D) = W_ih, [ldd, ldd+D) = W_ih again, zeros elsewhere   */
+    void* x_kcat_bf16;              /* [B*S][2*ldd] workspace: hi | lo operand rows                                     */
 } nr_gru_fwd_args;
 int nr_gru_fwd(const nr_gru_fwd_args* a, void* stream);
 /* 1 if nr_gru_fwd runs the whole recurrence as ONE cooperative launch for this shape on this device (users in 128-row tiles x

@@ -46,9 +46,10 @@ int nr_cnn_encoder_fwd(const nr_cnn_encoder_fwd_args* a, void* stream) {
                              DropoutCfg{a->p_drop, a->seed}, a->bad_id_flag, st));
     const RowMapCfg to_compact = {Tp, 1, T, T, 0};
     NR_PROPAGATE(gemm_store(a->Xp_bf16, Mp, a->ldx, a->wconv_bf16, a->F, a->ldx, a->d, 3, a->F, (128 / Tp) * Tp, a->bconv, 1,
-                            a->Y_bf16, a->ldf, 1, to_compact, 0, DropoutCfg{a->p_drop, a->seed ^ 0x5bd1e995u}, a->F, a->ldf, st));
+                            a->Y_bf16, a->ldf, 1, to_compact, 0, DropoutCfg{a->p_drop, a->seed ^ 0x5bd1e995u}, a->F, a->ldf, st,
+                            a->Y_lo_bf16, a->ldf, 0));
     NR_PROPAGATE(gemm_additive_pool(a->Y_bf16, static_cast<int>(n_tok), a->ldf, a->F, a->wa_bf16, a->q, a->ldf, a->ba, a->qv, T,
-                                    a->out, a->F, a->w, st));
+                                    a->out, a->F, a->w, st, a->Y_lo_bf16));
     return 0;
 }
 

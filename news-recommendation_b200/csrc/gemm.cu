@@ -526,14 +526,14 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
     if (e.use_tma) NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_out, out, M, N, ld_out, 32, 32, 64));
     e.lo_col0 = -1;
     if (lo_out != nullptr) {
-        NR_REQUIRE(e.use_tma && lo_col0 >= 0 && lo_col0 < N && ld_lo % 8 == 0 && ld_lo >= N - lo_col0 && drop.p == 0.f,
-                   "gemm_store: the low plane needs the TMA epilogue (identity rows, bf16) and no dropout (N=%d lo_col0=%d ld_lo=%d)", N, lo_col0, ld_lo);
+        NR_REQUIRE(out_bf16 && lo_col0 >= 0 && lo_col0 < N && ld_lo % 8 == 0 && ld_lo >= N - lo_col0 && (e.use_tma || lo_col0 % 8 == 0),
+                   "gemm_store: the low plane needs bf16 output and aligned columns (N=%d lo_col0=%d ld_lo=%d)", N, lo_col0, ld_lo);
         for (int sl = 0; sl < plan.p.n_slices; ++sl) {  // a 32-column chunk never straddles the first low-plane column
             const int c0 = sl * plan.p.n_stride;
             NR_REQUIRE(!(c0 < lo_col0 && lo_col0 < c0 + plan.p.n_stride) || (lo_col0 - c0) % 32 == 0,
                        "gemm_store: low-plane start %d is not chunk aligned in the slice at column %d", lo_col0, c0);
         }
-        NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_lo, lo_out, M, N - lo_col0, ld_lo, 32, 32, 64));
+        if (e.use_tma) NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_lo, lo_out, M, N - lo_col0, ld_lo, 32, 32, 64));
         e.lo_col0 = lo_col0;
         e.lo_out = static_cast<__nv_bfloat16*>(lo_out);
         e.ld_lo = ld_lo;

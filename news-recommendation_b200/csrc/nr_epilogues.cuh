@@ -180,6 +180,14 @@ struct EpiStore {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
                     ts.put_rows(static_cast<__nv_bfloat16*>(out), ld, w, c.col0 + lc0, v ? static_cast<int>(orow) : -1, lane);
+                    if (lo_col0 >= 0 && c.col0 + lc0 >= lo_col0 && (ld_lo & 7) == 0) {  // low plane, same (mapped) rows
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 h = unpack_bf16x2(w[j]);
+                            w[j] = pack_bf16x2(x[2 * j] - h.x, x[2 * j + 1] - h.y);
+                        }
+                        ts.put_rows(lo_out, ld_lo, w, c.col0 + lc0 - lo_col0, v ? static_cast<int>(orow) : -1, lane);
+                    }
                     return;
                 }
 #pragma unroll

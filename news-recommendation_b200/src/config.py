@@ -42,7 +42,10 @@ _PER_MODEL = {
     "NAML": dict(dataset_attributes={"news": ["category", "subcategory", "title", "abstract"], "record": []}, **_CNN),
     "LSTUR": dict(dataset_attributes={"news": ["category", "subcategory", "title"],
                                       "record": ["user", "clicked_news_length"]},
-                  long_short_term_method="ini", masking_probability=0.5, **_CNN),
+                  long_short_term_method="ini", masking_probability=0.5,
+                  # extension knob (see NRMS): "accurate" = conv output and GRU input as hi/lo bf16 pairs (1e-3 tolerance of the
+                  # blueprint for both long/short-term methods), "fast" = plain bf16 storage (ini: 1.8e-3)
+                  precision=os.environ.get("NEWSREC_PRECISION", "accurate"), **_CNN),
     "TANR": dict(dataset_attributes={"news": ["category", "title"], "record": []},
                  topic_classification_loss_weight=0.1, **_CNN),
 }

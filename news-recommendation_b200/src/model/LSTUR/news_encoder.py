@@ -31,7 +31,7 @@ class NewsEncoder(nn.Module):
         sub = EmbeddingF32Fn.apply(fields["subcategory"], self.category_embedding.weight, self._cat_flag.get(dev))
         p = self.config.dropout_probability if self.training else 0.0
         title = cnn_text_encode(fields["title"], self.word_embedding, self.title_CNN, self.title_attention, p, self._cache,
-                                "title", self._flag)
+                                "title", self._flag, accurate=getattr(self.config, "precision", "fast") == "accurate")
         return torch.cat([cat, sub, title], dim=1)
 
     def forward(self, news):

@@ -23,10 +23,11 @@ class UserEncoder(nn.Module):
         clicked_news_length.clamp_(min=1)  # in place, like the reference's `length[length == 0] = 1` (:27) -- without the
         # device synchronisation a boolean-mask assignment needs when the lengths already live on the GPU
         g = self.gru
+        acc = getattr(self.config, "precision", "fast") == "accurate"
         if self.config.long_short_term_method == "ini":
             return GruLastHiddenFn.apply(clicked_news_vector, clicked_news_length, user, g.weight_ih_l0, g.weight_hh_l0,
-                                         g.bias_ih_l0, g.bias_hh_l0, self._cache, "gru")
+                                         g.bias_ih_l0, g.bias_hh_l0, self._cache, "gru", acc)
         h0 = torch.zeros((clicked_news_vector.shape[0], g.weight_hh_l0.shape[1]), device=dev)
         last = GruLastHiddenFn.apply(clicked_news_vector, clicked_news_length, h0, g.weight_ih_l0, g.weight_hh_l0,
-                                     g.bias_ih_l0, g.bias_hh_l0, self._cache, "gru")
+                                     g.bias_ih_l0, g.bias_hh_l0, self._cache, "gru", acc)
         return torch.cat((last, user), dim=1)

@@ -13,9 +13,9 @@ def make_title_cnn(num_filters, window_size, word_embedding_dim):
     return nn.Conv2d(1, num_filters, (window_size, word_embedding_dim), padding=(int((window_size - 1) / 2), 0))
 
 
-def cnn_text_encode(ids, word_embedding, cnn, attention, p_drop, cache: OperandCache, prefix, flag: BadIdFlag):
+def cnn_text_encode(ids, word_embedding, cnn, attention, p_drop, cache: OperandCache, prefix, flag: BadIdFlag, accurate=False):
     """ids (n, T) int64 on the device -> (n, F) through the fused gather/conv/ReLU/pool kernel sequence."""
     dev = require_cuda()
     return CnnPoolEncoderFn.apply(ids, word_embedding.weight, cnn.weight, cnn.bias, attention.linear.weight,
                                   attention.linear.bias, attention.attention_query_vector, p_drop, cache, prefix,
-                                  flag.get(dev))
+                                  flag.get(dev), bool(accurate))

@@ -52,6 +52,7 @@ class CnnEncoderFwdArgs(C.Structure):
         ("wconv_bf16", _vp), ("bconv", _vp), ("wa_bf16", _vp), ("ba", _vp), ("qv", _vp),
         ("p_drop", _f), ("seed", _ull),
         ("Xp_bf16", _vp), ("Y_bf16", _vp), ("w", _vp), ("out", _vp), ("bad_id_flag", _vp),
+        ("Y_lo_bf16", _vp),
     ]
 
 
@@ -75,6 +76,7 @@ class GruFwdArgs(C.Structure):
         ("x", _vp), ("x_s_b", _ll), ("x_s_t", _ll), ("x_s_c", _ll),
         ("len", _vp), ("h0", _vp), ("wih_bf16", _vp), ("whh_bf16", _vp), ("bih", _vp), ("bhh", _vp),
         ("xb", _vp), ("gi", _vp), ("gh", _vp), ("hs", _vp), ("hb", _vp), ("out", _vp),
+        ("wih_kcat_bf16", _vp), ("x_kcat_bf16", _vp),
     ]
 
 

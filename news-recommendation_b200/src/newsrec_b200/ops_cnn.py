@@ -16,7 +16,7 @@ class CnnPoolEncoderFn(torch.autograd.Function):
     reference: NAML/news_encoder.py:21-37, LSTUR/news_encoder.py:56-72, TANR/news_encoder.py:40-52."""
 
     @staticmethod
-    def forward(ctx, ids, emb_w, Wc, bc, Wa, ba, qv, p_drop, cache, prefix, bad_flag):
+    def forward(ctx, ids, emb_w, Wc, bc, Wa, ba, qv, p_drop, cache, prefix, bad_flag, accurate=False):
         lib = load_library()
         dev = require_cuda()
         Fn, _, win, d = Wc.shape
@@ -48,6 +48,10 @@ class CnnPoolEncoderFn(torch.autograd.Function):
         a.wconv_bf16, a.bconv, a.wa_bf16, a.ba, a.qv = _p(ops["wconv"]), _p(ops["bconv"]), _p(ops["wa"]), _p(ops["ba"]), _p(ops["qv"])
         a.p_drop, a.seed = float(p_drop), seed
         a.Xp_bf16, a.Y_bf16, a.w, a.out, a.bad_id_flag = _p(Xp), _p(Y), _p(w), _p(out), _p(bad_flag)
+        Y_lo = None
+        if accurate:  # the conv output as a hi/lo bf16 pair: the pooled sum reads both planes
+            Y_lo = torch.empty((n_seq * T, ldf), dtype=torch.bfloat16, device=dev)
+            a.Y_lo_bf16 = _p(Y_lo)
         check(lib.nr_cnn_encoder_fwd(C.byref(a), _stream()), "nr_cnn_encoder_fwd")
         ctx.save_for_backward(Xp, Y, w, ids)
         ctx.meta = dict(n_seq=n_seq, T=T, d=d, F=Fn, q=q, p_drop=float(p_drop), seed=seed, ops=ops, V=emb_w.shape[0])
@@ -79,7 +83,7 @@ class CnnPoolEncoderFn(torch.autograd.Function):
         check(lib.nr_cnn_encoder_bwd(C.byref(a), _stream()), "nr_cnn_encoder_bwd")
         gWc = dWc[:, :, :d].permute(1, 0, 2).unsqueeze(1).contiguous()   # (F, 1, 3, d)
         gbc = dWc[1, :, d].contiguous()
-        return (None, demb, gWc, gbc, dWa[:, :Fn].contiguous(), dWa[:, Fn].contiguous(), dqv, None, None, None, None)
+        return (None, demb, gWc, gbc, dWa[:, :Fn].contiguous(), dWa[:, Fn].contiguous(), dqv, None, None, None, None, None)
 
 
 class LinearRowsFn(torch.autograd.Function):

@@ -251,7 +251,7 @@ def title_cnn(x, weight, bias, c: Contract = EXACT, y_mask=None):
     y = F.relu(y).transpose(1, 2)
     if y_mask is not None:
         y = y * y_mask.to(y.dtype)
-    return c.act(y)
+    return c.act_hilo(y)  # plain bf16 store; hi/lo pair under the accurate contract (LSTUR, config.precision)
 
 
 def cnn_text_encoder(ids, table, conv_w, conv_b, p, att_prefix, c: Contract = EXACT, drop=None):
@@ -420,7 +420,8 @@ def gru_last_hidden(x, lengths, h0, p, prefix, c: Contract = EXACT):
     w_hh = c.operand(p[f"{prefix}.weight_hh_l0"])
     b_ih, b_hh = p[f"{prefix}.bias_ih_l0"], p[f"{prefix}.bias_hh_l0"]
     Hd = w_hh.shape[1]
-    gi_all = c.grad(F.linear(c.operand(x) if c.acts else x, w_ih) + b_ih)  # (B,S,3Hd); dX = dGI.W_ih stays fp32
+    # (B,S,3Hd); dX = dGI.W_ih stays fp32.  Under the accurate contract x enters as a hi/lo bf16 pair (~16 mantissa bits: not rounded here)
+    gi_all = c.grad(F.linear(c.operand(x) if (c.acts and not c.hilo) else x, w_ih) + b_ih)
     h = h0
     for t in range(S):
         gh = c.grad(F.linear(c.operand(h) if (c.bf16 and c.acts) else h, w_hh) + b_hh)

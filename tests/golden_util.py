@@ -63,6 +63,8 @@ def oracle_forward(case, g, p, contract=O.EXACT, fused=False, drop=None, user_ke
         clicked = dict(title=clicked_t, category=t(g, "clicked_category"))
         return O.tanr_forward(cand, clicked, p, contract, drop=drop)
     method = case.split("_")[1]
+    if contract.bf16 and contract.acts and fused:  # LSTUR's accurate mode: conv output and GRU input as hi/lo bf16 pairs
+        contract = O.BF16_FUSED
     cand = dict(title=cand_t, category=t(g, "cand_category"), subcategory=t(g, "cand_subcategory"))
     clicked = dict(title=clicked_t, category=t(g, "clicked_category"), subcategory=t(g, "clicked_subcategory"))
     return O.lstur_forward(t(g, "user"), t(g, "clicked_news_length"), cand, clicked, p, method, contract, drop=drop,

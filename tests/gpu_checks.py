@@ -657,6 +657,8 @@ def build_model(case, V=120, ncat=15, nusers=40, H=6, dropout=0.2, fused=False):
     if name == "NRMS":
         over["fused_news_encoder"] = fused is True
         over["precision"] = "accurate" if fused == "accurate" else "fast"
+    if name == "LSTUR":
+        over["precision"] = "accurate" if fused else "fast"
     if case == "naml_f400":
         over["num_filters"] = 400
     if case.startswith("lstur"):
@@ -683,10 +685,10 @@ def golden_inputs(case, g):
     return mk("cand"), mk("clicked")
 
 
-def default_nrms_mode():
-    """False ("fast") or "accurate": what the NRMS drop-in does when the config says nothing (config.py / NEWSREC_PRECISION)."""
+def default_nrms_mode(name="NRMS"):
+    """False ("fast") or "accurate": what the NRMS / LSTUR drop-in does when the config says nothing (config.py / NEWSREC_PRECISION)."""
     import config as cfgmod
-    return "accurate" if getattr(cfgmod.NRMSConfig, "precision", "fast") == "accurate" else False
+    return "accurate" if getattr(getattr(cfgmod, name + "Config"), "precision", "fast") == "accurate" else False
 
 
 def check_golden(case, fused=None):
@@ -695,7 +697,7 @@ def check_golden(case, fused=None):
     bf16 contract itself has (kernel_err <= ~1.5 x contract_err is the pass criterion)."""
     from golden_util import case_params, load_case, oracle_forward, unique_params
     if fused is None:  # the shipped default
-        fused = default_nrms_mode() if case == "nrms" else False
+        fused = default_nrms_mode() if case == "nrms" else (default_nrms_mode("LSTUR") if case.startswith("lstur") else False)
     g = load_case(case)
     p_b = case_params(case, g)
     logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, bool(fused))
@@ -750,7 +752,7 @@ def check_golden(case, fused=None):
     return res
 
 
-def check_train_masked(case, p_drop=0.2, mask_p=0.5):
+def check_train_masked(case, p_drop=0.2, mask_p=0.5, fused=None):
     """TRAIN mode of a CNN family (NAML / TANR / LSTUR) on its golden inputs, forward AND backward, against the oracle under
     the SAME dropout masks (see check_nrms_train_masked): one seed per text-encoder call (NAML: title, then abstract), masks
     over the zero-padded gather layout and the compact conv-output layout.  LSTUR's user masking (F.dropout2d on the
@@ -759,7 +761,9 @@ def check_train_masked(case, p_drop=0.2, mask_p=0.5):
     from golden_util import case_params, case_shapes, load_case, oracle_forward, unique_params
     from newsrec_b200 import ops
     g = load_case(case)
-    model, cfg = build_model(case, dropout=p_drop)
+    if fused is None:  # the shipped default of the family (LSTUR: accurate = conv output / GRU input as hi/lo pairs)
+        fused = default_nrms_mode("LSTUR") if case.startswith("lstur") else False
+    model, cfg = build_model(case, dropout=p_drop, fused=fused)
     sd = O.tie_shared(O.det_state_dict(case_shapes(case), int(g["seed"])))
     model.load_state_dict(sd)
     model.train()
@@ -778,7 +782,7 @@ def check_train_masked(case, p_drop=0.2, mask_p=0.5):
         drop = dict(p=p_drop, seed=ops.peek_seeds(1)[0])
     tw = lambda t: (0.1 * t if t is not None else 0.0)
     p_b = case_params(case, g)
-    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, drop=drop, user_keep=user_keep)
+    logits_b, topic_b = oracle_forward(case, g, p_b, O.BF16, bool(fused), drop=drop, user_keep=user_keep)
     (O.click_loss(logits_b) + tw(topic_b)).backward()
     p_x = case_params(case, g)
     logits_x, topic_x = oracle_forward(case, g, p_x, O.EXACT, drop=drop, user_keep=user_keep)

@@ -18,9 +18,10 @@ CASES = ["nrms", "naml", "naml_f400", "tanr", "lstur_ini", "lstur_con"]
 # definition of the blueprint, target 1e-3.  NRMS meets it in its default ("accurate") precision mode: V,
 # the attention probabilities and the context travel as hi/lo bf16 pairs (the plain bf16 storage of exactly these three is
 # what puts the "fast" mode at 6e-3: every token of a title sees the SAME rounding error of V_j, so the pooling does not
-# average it out -- DESIGN.md section 4).  The CNN families meet it as they are.  LSTUR (ini) does not yet: bf16 conv output
-# 1.1e-3 + bf16 news vectors entering the GRU 1.1e-3 + bf16 hidden state fed back 5.5e-4.  Bounds = measured + ~30 %.
-WEIGHTS_ONLY_BOUND = {"nrms": 1e-3, "naml": 1e-3, "naml_f400": 1e-3, "tanr": 1e-3, "lstur_ini": 3e-3, "lstur_con": 1e-3}
+# average it out -- DESIGN.md section 4).  NAML / TANR meet it as they are.  LSTUR meets it in ITS default accurate mode: the
+# conv output and the news vectors entering the GRU are hi/lo pairs (plain bf16: 1.1e-3 each on the ini case); what is left
+# is the bf16 hidden state fed back through the recurrence (5.5e-4).
+WEIGHTS_ONLY_BOUND = {"nrms": 1e-3, "naml": 1e-3, "naml_f400": 1e-3, "tanr": 1e-3, "lstur_ini": 1e-3, "lstur_con": 1e-3}
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -44,6 +45,14 @@ def test_nrms_fast_mode_golden_case():
     assert r["logits_vs_oracle_bf16"] < 1e-3, r
     assert r["logits_vs_weights_only_oracle"] < 8e-3, r
     assert r["logits_vs_reference_fp32"] < 1.25 * r["oracle_bf16_vs_reference_fp32"] + 1e-4, r
+    assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
+
+
+@pytest.mark.parametrize("case", ["lstur_ini", "lstur_con"])
+def test_lstur_fast_mode_golden_case(case):
+    """LSTUR with config.precision = "fast" (plain bf16 conv output / GRU input): parity against the oracle under that contract."""
+    r = G.check_golden(case, fused=False)
+    assert r["logits_vs_oracle_bf16"] < 1e-3 and r["logits_vs_weights_only_oracle"] < 3e-3, r
     assert r["worst_grad_ratio_kernel_over_contract"] < 1.5 and r["emb_row0_grad_zero"], r
 
 
