@@ -316,9 +316,8 @@ typedef struct {
     float* hs;                      /* fp32 [S+1][B][Hd] hidden states                                    */
     void* hb;                       /* bf16 [S+1][B][ldh]                                                 */
     float* out;                     /* fp32 [B][Hd] last hidden state                                     */
-    /* accurate mode (both non-NULL): the input enters the projection as a hi/lo bf16 pair against K-concatenated weights */
-    const void* wih_kcat_bf16;      /* [3Hd][2*ldd]: columns [0,D) = W_ih, [ldd, ldd+D) = W_ih again, zeros elsewhere   */
-    void* x_kcat_bf16;              /* [B*S][2*ldd] workspace: hi | lo operand rows                                     */
+    /* accurate mode (non-NULL): the input enters the projection as a hi/lo bf16 pair, gi = x_hi.W^T + b + x_lo.W^T (two passes) */
+    void* x_lo_bf16;                /* [B*S][ldd] workspace: bf16(x - bf16(x))                                         */
 } nr_gru_fwd_args;
 int nr_gru_fwd(const nr_gru_fwd_args* a, void* stream);
 /* 1 if nr_gru_fwd runs the whole recurrence as ONE cooperative launch for this shape on this device (users in 128-row tiles x

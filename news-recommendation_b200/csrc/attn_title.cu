@@ -1,5 +1,5 @@
-// Title-level multi-head self-attention backward (reference src/model/general/attention/multihead_self.py:15-23 and
-// scaled_dot_product.py, through autograd) for the news encoder's shape: T = 20 words, d_k = 20, up to 15 heads.
+// Title-level multi-head self-attention, backward and forward (reference src/model/general/attention/multihead_self.py:15-23,
+// the backward through autograd) for the news encoder's shape: T = 20 words, d_k = 20, up to 15 heads.
 //
 //   dA = dCtx V^T;  dS = A (dA - sum A dA)/sqrt(dk);  dQ = dS K;  dK = dS^T Q;  dV = A^T dCtx        (A recomputed from Q, K)
 //
@@ -367,7 +367,7 @@ template <bool HILO>
 __global__ void __launch_bounds__((kMaxHeads + 1) * 32, HILO ? 1 : 2)
 mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_vlo,
                       const __grid_constant__ CUtensorMap tm_ctx, const __grid_constant__ CUtensorMap tm_clo, const FwdParams p) {
-    constexpr int kIn = HILO ? kInHilo : title::kIn;  // one CTA per SM in the hi/lo variant: a third title in flight
+    constexpr int kIn = HILO ? kInHilo : title::kIn;  // input stages (one CTA per SM in the hi/lo variant, two otherwise)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* const base_ptr = smem_raw + (base - smem_u32(smem_raw));

@@ -515,7 +515,7 @@ static Dropout to_drop(const DropoutCfg& c) {
 int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
                int rows_per_tile, const float* bias, int relu, void* out, int ld_out, int out_bf16, RowMapCfg rm,
                int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream, void* lo_out, int ld_lo,
-               int lo_col0) {
+               int lo_col0, int accumulate) {
     if (M == 0) return 0;
     GemmNTPlan plan;
     NR_PROPAGATE(plan_gemm_nt(&plan, A, M, lda, W, N, ldw, K, taps, w_tap_rows, rows_per_tile, num_sms(), 0, EpiStore::kScratchBytes, 0));
@@ -525,6 +525,8 @@ int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int
     e.use_tma = (out_bf16 && rm.seg_in == 0 && rows_per_tile == kTileM && N >= 32) ? 1 : 0;
     if (e.use_tma) NR_PROPAGATE(make_tmap_bf16_2d(&e.tm_out, out, M, N, ld_out, 32, 32, 64));
     e.lo_col0 = -1;
+    NR_REQUIRE(!accumulate || !out_bf16, "gemm_store: accumulation needs an fp32 output");
+    e.accumulate = accumulate;
     if (lo_out != nullptr) {
         NR_REQUIRE(out_bf16 && lo_col0 >= 0 && lo_col0 < N && ld_lo % 8 == 0 && ld_lo >= N - lo_col0 && (e.use_tma || lo_col0 % 8 == 0),
                    "gemm_store: the low plane needs bf16 output and aligned columns (N=%d lo_col0=%d ld_lo=%d)", N, lo_col0, ld_lo);

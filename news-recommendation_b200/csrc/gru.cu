@@ -131,14 +131,14 @@ int nr_gru_fwd(const nr_gru_fwd_args* a, void* stream) {
     prof_context("gru.fwd");
     // gi = X Wih^T + bih over all (user, step) rows
     NR_PROPAGATE(rows_to_bf16(a->x, B, S, D, a->x_s_b, a->x_s_t, a->x_s_c, a->xb, ldd, st));
-    if (a->wih_kcat_bf16 != nullptr && a->x_kcat_bf16 != nullptr) {
-        // accurate mode: [x_hi | x_lo] . [W_ih | W_ih]^T -- the news vectors enter at ~16 mantissa bits (xb, the hi rows, is
-        // still written: the backward's weight gradient reads it)
-        NR_PROPAGATE(rows_to_bf16_hilo(a->x, B, S, D, a->x_s_b, a->x_s_t, a->x_s_c, a->x_kcat_bf16, ldd, st));
-        NR_PROPAGATE(gemm_store(a->x_kcat_bf16, B * S, 2 * ldd, a->wih_kcat_bf16, 3 * Hd, 2 * ldd, 2 * ldd, 1, 0, 128, a->bih, 0, a->gi, ldg, 0,
-                                kIdentity, 0, kNoDrop, -1, 0, st));
-    } else {
-        NR_PROPAGATE(gemm_store(a->xb, B * S, ldd, a->wih_bf16, 3 * Hd, ldd, D, 1, 0, 128, a->bih, 0, a->gi, ldg, 0, kIdentity, 0, kNoDrop, -1, 0, st));
+    NR_PROPAGATE(gemm_store(a->xb, B * S, ldd, a->wih_bf16, 3 * Hd, ldd, D, 1, 0, 128, a->bih, 0, a->gi, ldg, 0, kIdentity, 0, kNoDrop, -1, 0, st));
+    if (a->x_lo_bf16 != nullptr) {
+        // accurate mode: the news vectors enter as a hi/lo bf16 pair, gi = x_hi . W_ih^T + b + x_lo . W_ih^T.  Two passes over the
+        // SAME resident weights with fp32 accumulation into gi: a K-concatenated single pass doubles K, which shrinks the weight-
+        // stationary slices to N = 80 and costs 0.86 ms instead of 2 x 0.23
+        NR_PROPAGATE(rows_to_bf16_lo(a->x, B, S, D, a->x_s_b, a->x_s_t, a->x_s_c, a->x_lo_bf16, ldd, st));
+        NR_PROPAGATE(gemm_store(a->x_lo_bf16, B * S, ldd, a->wih_bf16, 3 * Hd, ldd, D, 1, 0, 128, nullptr, 0, a->gi, ldg, 0, kIdentity, 0, kNoDrop,
+                                -1, 0, st, nullptr, 0, 0, 1));
     }
     // h_0
     NR_CHECK_CUDA(cudaMemcpyAsync(a->hs, a->h0, sizeof(float) * BH, cudaMemcpyDeviceToDevice, st));

@@ -88,6 +88,7 @@ struct EpiStore {
     static constexpr int kScratchBytes = 1024 + kTileStoreBytes;
     CUtensorMap tm_out;  // bf16 output as a TMA tensor (32 x 32 boxes, SWIZZLE_64B); valid when use_tma
     CUtensorMap tm_lo;   // low plane of the columns >= lo_col0 (bf16(y - bf16(y))), its column 0 = output column lo_col0
+    int accumulate;      // fp32 output only: out += result
     int lo_col0;         // < 0: no low plane
     __nv_bfloat16* lo_out;  // the same plane for the (rare) partial chunks that leave through plain stores; pitch ld_lo
     int ld_lo;
@@ -217,11 +218,18 @@ struct EpiStore {
                         float* o = static_cast<float*>(out) + orow * ld + col;
                         if (nvalid == 16) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                            for (int j = 0; j < 16; j += 4) {
+                                float4 v4 = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                                if (accumulate) {  // out += : second pass of a split-operand product (x_lo . W^T on top of x_hi . W^T)
+                                    const float4 o4 = *reinterpret_cast<const float4*>(o + j);
+                                    v4.x += o4.x; v4.y += o4.y; v4.z += o4.z; v4.w += o4.w;
+                                }
+                                *reinterpret_cast<float4*>(o + j) = v4;
+                            }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (j < nvalid) o[j] = y[j];
+                                if (j < nvalid) o[j] = accumulate ? o[j] + y[j] : y[j];
                         }
                     }
                 }

@@ -21,7 +21,8 @@ struct RowMapCfg {  // see RowMap in nr_epilogues.cuh; seg_in == 0 => identity
 int gemm_store(const void* A, int M, int lda, const void* W, int N, int ldw, int K, int taps, int w_tap_rows,
                int rows_per_tile, const float* bias, int relu, void* out, int ld_out, int out_bf16, RowMapCfg rm,
                int zero_pad_rows, DropoutCfg drop, int ones_col, int ones_zero_upto, cudaStream_t stream,
-               void* lo_out = nullptr, int ld_lo = 0, int lo_col0 = 0);
+               void* lo_out = nullptr, int ld_lo = 0, int lo_col0 = 0, int accumulate = 0);
+// accumulate (fp32 output only): out += A . W^T (+ bias) instead of out =
 // lo_out (bf16 [M][ld_lo], identity rows, bf16 output only): columns [lo_col0, N) additionally leave as a LOW plane,
 // lo[r][c - lo_col0] = bf16(y - bf16(y)), so that a consumer can read y as a hi/lo bf16 pair (~16 mantissa bits)
 
@@ -103,6 +104,8 @@ int gru_fwd_persistent(int B, int S, int Hd, int ldh, int ldg, const float* gi, 
                        const long long* len, float* gh, float* hs, void* hb, float* out, cudaStream_t stream);
 
 // precise user encoder (NRMS precise mode): hi/lo K-concatenated operand rows, fp32 attention with hi/lo context planes
+int rows_to_bf16_lo(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col, void* dst, int ld,
+                    cudaStream_t stream);
 int rows_to_bf16_hilo(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col, void* dst,
                       int ld, cudaStream_t stream);
 int mhsa_f32_fwd(const float* qkv, int ld, int sec, long long n_seq, int T, int heads, int dk, void* c_hi, void* c_lo, int ldc,

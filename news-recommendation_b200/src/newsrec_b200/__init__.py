@@ -76,7 +76,7 @@ class GruFwdArgs(C.Structure):
         ("x", _vp), ("x_s_b", _ll), ("x_s_t", _ll), ("x_s_c", _ll),
         ("len", _vp), ("h0", _vp), ("wih_bf16", _vp), ("whh_bf16", _vp), ("bih", _vp), ("bhh", _vp),
         ("xb", _vp), ("gi", _vp), ("gh", _vp), ("hs", _vp), ("hb", _vp), ("out", _vp),
-        ("wih_kcat_bf16", _vp), ("x_kcat_bf16", _vp),
+        ("x_lo_bf16", _vp),
     ]
 
 

@@ -43,12 +43,10 @@ class GruLastHiddenFn(torch.autograd.Function):
         a.len, a.h0 = _p(lengths), _p(h0)
         a.wih_bf16, a.whh_bf16, a.bih, a.bhh = _p(ops["wih"]), _p(ops["whh"]), _p(ops["bih"]), _p(ops["bhh"])
         a.xb, a.gi, a.gh, a.hs, a.hb, a.out = _p(xb), _p(gi), _p(gh), _p(hs), _p(hb), _p(out)
-        x_kcat = None
-        if accurate:  # news vectors enter the input projection as a hi/lo bf16 pair against [W_ih | W_ih]
-            kcat = cache.get(prefix + ".kcat", (Wih,), lambda Wih: cast_pad(
-                torch.cat((torch.nn.functional.pad(Wih.float(), (0, ldd - D)),) * 2, dim=1), 2 * ldd))
-            x_kcat = torch.empty((B * S, 2 * ldd), dtype=torch.bfloat16, device=dev)
-            a.wih_kcat_bf16, a.x_kcat_bf16 = _p(kcat), _p(x_kcat)
+        x_lo = None
+        if accurate:  # news vectors enter the input projection as a hi/lo bf16 pair (second pass over W_ih)
+            x_lo = torch.empty((B * S, ldd), dtype=torch.bfloat16, device=dev)
+            a.x_lo_bf16 = _p(x_lo)
         check(lib.nr_gru_fwd(C.byref(a), _stream()), "nr_gru_fwd")
         ctx.save_for_backward(xb, gi, gh, hs, hb, lengths)
         ctx.meta = dict(B=B, S=S, D=D, Hd=Hd, ops=ops)
