@@ -80,6 +80,11 @@ class FlatGradients:
             # NCCL's channel CTAs need SMs while the weight-gradient GEMM runs (it would otherwise hold all of them)
             from . import load_library
             load_library().nr_reserve_sms_for_comm(int(os.environ.get("NEWSREC_COMM_SMS", "32")))
+        # opt-in (NEWSREC_COMM_BF16=1): the embedding-gradient slice crosses the wire as bf16 (half the all-reduce time; every
+        # rank's contribution is rounded to bf16 before the average -- not bit-compatible with the fp32 reduction, hence off by default)
+        self._wire = None
+        if self._side is not None and os.environ.get("NEWSREC_COMM_BF16") == "1":
+            self._wire = torch.empty(self.big_numel, dtype=torch.bfloat16, device=dev)
 
     def zero(self):
         self.flat.zero_()
@@ -99,7 +104,12 @@ class FlatGradients:
             # early slice: starts when the event the backward recorded behind the scatter GEMM fires
             self._side.wait_event(self._event)
             with torch.cuda.stream(self._side):
-                dist.all_reduce(self.flat[:self.big_numel], op=dist.ReduceOp.AVG)
+                if self._wire is not None:
+                    self._wire.copy_(self.flat[:self.big_numel])
+                    dist.all_reduce(self._wire, op=dist.ReduceOp.AVG)
+                    self.flat[:self.big_numel].copy_(self._wire)
+                else:
+                    dist.all_reduce(self.flat[:self.big_numel], op=dist.ReduceOp.AVG)
             if self.big_numel < self.flat.numel():
                 dist.all_reduce(self.flat[self.big_numel:], op=dist.ReduceOp.AVG)
             main.wait_stream(self._side)
