@@ -98,6 +98,50 @@ def test_operand_cache_rebuilds_only_when_the_parameter_changes():
     assert len(calls) == 2 and float(out[0]) == 1.0
 
 
+def test_operand_cache_invalidate_keeps_parameter_independent_workspaces():
+    """bench.py drops the parameter-derived operands every step (what an optimizer update does through the version counters);
+    workspaces keyed by no parameter (persistent gradient accumulators) must survive."""
+    from newsrec_b200.ops import OperandCache
+    cache, calls = OperandCache(), []
+    p = torch.nn.Parameter(torch.zeros(4))
+    cache.get("w", (p,), lambda t: calls.append("w") or t.clone())
+    ws = cache.get("ws", (), lambda: calls.append("ws") or torch.zeros(2))
+    cache.invalidate_operands()
+    cache.get("w", (p,), lambda t: calls.append("w") or t.clone())
+    assert cache.get("ws", (), lambda: calls.append("ws") or torch.zeros(2)) is ws
+    assert calls == ["w", "ws", "w"]
+
+
+def test_qkv_sections_pad_to_a_16_byte_phase():
+    """Q | K | V sections start at multiples of 8 columns (abi.cu qkv_section): the packed projection operands carry zero rows
+    at the section padding, the gradient slices skip it."""
+    from newsrec_b200.ops import qkv_pitches, stack_qkv
+    assert qkv_pitches(300) == (304, 912) and qkv_pitches(40) == (40, 128) and qkv_pitches(100) == (104, 320)
+    Wq, Wk, Wv = (torch.full((300, 300), float(i + 1)) for i in range(3))
+    W = stack_qkv(Wq, Wk, Wv)
+    assert W.shape == (912, 300)
+    for i in range(3):
+        assert bool((W[i * 304:i * 304 + 300] == i + 1).all()) and bool((W[i * 304 + 300:(i + 1) * 304] == 0).all())
+    b = stack_qkv(torch.ones(300), 2 * torch.ones(300), 3 * torch.ones(300))
+    assert b.shape == (912,) and float(b[303]) == 0.0 and float(b[304]) == 2.0 and float(b[911]) == 0.0
+    assert stack_qkv(torch.ones(40, 40), torch.ones(40, 40), torch.ones(40, 40)).shape == (120, 40)  # d % 8 == 0: no padding
+
+
+def test_precision_knob_defaults_and_validation():
+    """config.precision: "accurate" by default for NRMS and LSTUR (the blueprint's 1e-3 tolerance), "fast" on request;
+    fused_news_encoder selects the one-kernel front end; anything else is rejected."""
+    import config as cfgmod
+    from newsrec_b200 import NewsrecError
+    from newsrec_b200.ops import precision_mode
+    assert precision_mode(cfgmod.NRMSConfig) == os.environ.get("NEWSREC_PRECISION", "accurate")
+    assert getattr(cfgmod.LSTURConfig, "precision") == os.environ.get("NEWSREC_PRECISION", "accurate")
+    assert precision_mode(type("C", (), {"precision": "fast"})) == "fast"
+    assert precision_mode(type("C", (), {"precision": "fast", "fused_news_encoder": True})) == "fused"
+    assert precision_mode(type("C", (), {})) == "fast"  # a config without the knob (NAML / TANR): plain bf16 storage
+    with pytest.raises(NewsrecError):
+        precision_mode(type("C", (), {"precision": "exact"}))
+
+
 def test_hot_path_raises_without_cuda_instead_of_falling_back():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
