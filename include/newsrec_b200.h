@@ -60,6 +60,9 @@ int nr_profile_report(char* buf, int cap);
 /* ---- operand preparation ------------------------------------------------------------------------- */
 /* fp32 [R][C] (pitch lds) -> zero padded bf16 [R][ld]; transpose!=0: dst is [C][ld] with dst[c][r]=src[r][c] */
 int nr_cast_pad_bf16(const float* src, int R, int C, int lds, void* dst_bf16, int ld, int transpose, void* stream);
+/* the same for up to 8 matrices in ONE launch (host arrays of length n; the operands of an encoder are rebuilt together) */
+int nr_cast_pad_bf16_many(int n, const float* const* src, const int* R, const int* C, const int* lds, void* const* dst_bf16,
+                          const int* ld, const int* transpose, void* stream);
 /* fp32 rows [n][D] with element strides -> bf16 [n][ld] + ones column */
 int nr_rows_to_bf16(const float* src, long long n, int D, long long s_row, long long s_col, void* dst_bf16, int ld,
                     void* stream);

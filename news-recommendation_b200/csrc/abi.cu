@@ -38,6 +38,11 @@ void nr_profile_enable(int on) { prof_enable(on); }
 void nr_profile_context(const char* ctx) { prof_context(ctx ? ctx : ""); }
 int nr_profile_report(char* buf, int cap) { return prof_report(buf, cap); }
 
+int nr_cast_pad_bf16_many(int n, const float* const* src, const int* R, const int* C, const int* lds, void* const* dst, const int* ld,
+                          const int* transpose, void* stream) {
+    NR_REQUIRE(src && R && C && lds && dst && ld && transpose, "nr_cast_pad_bf16_many: null argument array");
+    return cast_pad_bf16_many(n, src, R, C, lds, dst, ld, transpose, S(stream));
+}
 int nr_cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, int transpose, void* stream) {
     NR_REQUIRE(src && dst && R >= 0 && C >= 0 && ld % 8 == 0 && ld >= (transpose ? R : C),
                "nr_cast_pad_bf16: R=%d C=%d ld=%d transpose=%d", R, C, ld, transpose);

@@ -192,11 +192,9 @@ mhsa_title_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             float sm[3][4], dp[3][4];
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
-                sm[nt][0] = sm[nt][1] = sm[nt][2] = sm[nt][3] = 0.f;
-                dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
-                mma_bf16(sm[nt], aq, kb16[nt]);     // S  = Q K^T
+                mma_bf16_z(sm[nt], aq, kb16[nt]);   // S  = Q K^T
                 mma_bf16_k8(sm[nt], aq8, &kb8[nt]);
-                mma_bf16(dp[nt], ag, vb16[nt]);     // dA = dCtx V^T
+                mma_bf16_z(dp[nt], ag, vb16[nt]);   // dA = dCtx V^T
                 mma_bf16_k8(dp[nt], ag8, &vb8[nt]);
             }
             // softmax over the 20 live key columns (fp32, exp(S)/(sum exp(S) + 1e-8) in its stable form), then dS
@@ -277,8 +275,8 @@ mhsa_title_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             if (mt == 0 && it >= kOut) f_wait(&oempty[o], ((it / kOut) - 1) & 1, 73);  // the store of title it-2 has drained this tile
 #pragma unroll
             for (int nd = 0; nd < 3; ++nd) {
-                float dq[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_bf16(dq, a16, kt16[nd]);
+                float dq[4];
+                mma_bf16_z(dq, a16, kt16[nd]);
                 mma_bf16_k8(dq, a8, &kt8[nd]);
                 const bool cok = nd == 1 || (nd == 0 ? c0ok : c2ok);
                 const uint32_t oa = ob + (mt * 16 + g) * pq + gb + 16 * nd + 4 * t4;
@@ -319,10 +317,10 @@ mhsa_title_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             const bool row0 = mt == 0 || g < 4;
 #pragma unroll
             for (int nd = 0; nd < 3; ++nd) {
-                float dk[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_bf16(dk, ad, qt16[nd]);
+                float dk[4], dv[4];
+                mma_bf16_z(dk, ad, qt16[nd]);
                 mma_bf16_k8(dk, ad8, &qt8[nd]);
-                mma_bf16(dv, ap, gt16[nd]);
+                mma_bf16_z(dv, ap, gt16[nd]);
                 mma_bf16_k8(dv, ap8, &gt8[nd]);
                 const bool cok = nd == 1 || (nd == 0 ? c0ok : c2ok);
                 const uint32_t oa = ob + p.sec2 + (mt * 16 + g) * pq + gb + 16 * nd + 4 * t4;
@@ -484,8 +482,7 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             float sm[3][4];
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
-                sm[nt][0] = sm[nt][1] = sm[nt][2] = sm[nt][3] = 0.f;
-                mma_bf16(sm[nt], aq, kb16[nt]);
+                mma_bf16_z(sm[nt], aq, kb16[nt]);
                 mma_bf16_k8(sm[nt], aq8, &kb8[nt]);
             }
             const bool row0 = mt == 0 || g < 4;
@@ -542,14 +539,16 @@ mhsa_title_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             if (mt == 0 && it >= kOut) f_wait(&oempty[o], ((it / kOut) - 1) & 1, 83);
 #pragma unroll
             for (int nd = 0; nd < 3; ++nd) {
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                float c[4];
                 if (HILO) {  // small terms first
-                    mma_bf16(c, b16, vt16[nd]);
+                    mma_bf16_z(c, b16, vt16[nd]);
                     mma_bf16_k8(c, b8, &vt8[nd]);
                     mma_bf16(c, a16, vl16[nd]);
                     mma_bf16_k8(c, a8, &vl8[nd]);
+                    mma_bf16(c, a16, vt16[nd]);
+                } else {
+                    mma_bf16_z(c, a16, vt16[nd]);
                 }
-                mma_bf16(c, a16, vt16[nd]);
                 mma_bf16_k8(c, a8, &vt8[nd]);
                 const bool cok = nd == 1 || (nd == 0 ? c0ok : c2ok);
                 const uint32_t oa = ob + (mt * 16 + g) * pc + gb + 16 * nd + 4 * t4;

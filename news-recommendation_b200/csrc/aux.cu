@@ -73,6 +73,54 @@ int cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, in
     return 0;
 }
 
+// Several small operand casts in ONE launch (blockIdx.y = matrix): the packed / transposed projection and pooling weights of
+// an encoder are four matrices of a few hundred rows each -- as four launches they cost more in launch gaps than in work,
+// and they are rebuilt after every optimizer step.
+constexpr int kCastMany = 8;
+struct CastManyArgs {
+    const float* src[kCastMany];
+    __nv_bfloat16* dst[kCastMany];
+    int R[kCastMany], C[kCastMany], lds[kCastMany], ld[kCastMany], transpose[kCastMany];
+};
+__global__ void __launch_bounds__(256) cast_pad_many_kernel(CastManyArgs a) {
+    const int m = blockIdx.y;
+    const float* __restrict__ src = a.src[m];
+    __nv_bfloat16* __restrict__ dst = a.dst[m];
+    const int R = a.R[m], C = a.C[m], lds = a.lds[m], ld = a.ld[m], transpose = a.transpose[m];
+    const long long total = static_cast<long long>(transpose ? C : R) * ld;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const long long r = i / ld;
+        const int c = static_cast<int>(i - r * ld);
+        float v = 0.f;
+        if (!transpose) {
+            if (c < C) v = src[r * lds + c];
+        } else {
+            if (c < R) v = src[static_cast<long long>(c) * lds + r];
+        }
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+int cast_pad_bf16_many(int n, const float* const* src, const int* R, const int* C, const int* lds, void* const* dst, const int* ld,
+                       const int* transpose, cudaStream_t stream) {
+    NR_REQUIRE(n >= 0 && n <= kCastMany, "cast_pad_bf16_many: %d matrices (at most %d per call)", n, kCastMany);
+    if (n == 0) return 0;
+    CastManyArgs a;
+    long long biggest = 0;
+    for (int i = 0; i < n; ++i) {
+        NR_REQUIRE(src[i] && dst[i] && R[i] >= 1 && C[i] >= 1 && ld[i] >= (transpose[i] ? R[i] : C[i]), "cast_pad_bf16_many: bad matrix %d", i);
+        a.src[i] = src[i];
+        a.dst[i] = static_cast<__nv_bfloat16*>(dst[i]);
+        a.R[i] = R[i], a.C[i] = C[i], a.lds[i] = lds[i], a.ld[i] = ld[i], a.transpose[i] = transpose[i];
+        biggest = std::max(biggest, static_cast<long long>(transpose[i] ? C[i] : R[i]) * ld[i]);
+    }
+    ProfScope ps("cast_pad_many", n, static_cast<int>(std::min<long long>(biggest, 1 << 30)), 0, stream);
+    const dim3 grid(static_cast<unsigned>(std::min<long long>((biggest + 255) / 256, 148 * 4)), static_cast<unsigned>(n));
+    cast_pad_many_kernel<<<grid, 256, 0, stream>>>(a);
+    ++g_launches;
+    NR_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // fp32 rows [n_seq][T][D] (arbitrary element strides) -> bf16 rows [n_seq*T x ld] with a ones column at D.
 // One thread per 8-column chunk column, a block walks kRowsThreads / chunks rows per iteration (no division in the loop).
 constexpr int kRowsThreads = 320;

@@ -54,6 +54,9 @@ int gemm_tn_accumulate(const void* A, int Kr, int Ma, int lda, const void* B, in
 // ---- memory-bound companions (aux.cu) --------------------------------------------------------------
 // fp32 [R x C] (pitch lds) -> bf16 [R x ld] zero padded; transpose: out[c][r] = in[r][c] (out is [C x ld])
 int cast_pad_bf16(const float* src, int R, int C, int lds, void* dst, int ld, int transpose, cudaStream_t stream);
+// up to 8 such casts in one launch
+int cast_pad_bf16_many(int n, const float* const* src, const int* R, const int* C, const int* lds, void* const* dst, const int* ld,
+                       const int* transpose, cudaStream_t stream);
 // fp32 rows [n_seq][T][D] with element strides -> bf16 [n_seq*T x ld], ones column at D, zeros after
 int rows_to_bf16(const float* src, long long n_seq, int T, int D, long long s_seq, long long s_tok, long long s_col,
                  void* dst, int ld, cudaStream_t stream);

@@ -108,6 +108,7 @@ SIGNATURES = {
     "nr_profile_context": (None, [C.c_char_p]),
     "nr_profile_report": (_i, [C.c_char_p, _i]),
     "nr_cast_pad_bf16": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp]),
+    "nr_cast_pad_bf16_many": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nr_rows_to_bf16": (_i, [_vp, _ll, _i, _ll, _ll, _vp, _i, _vp]),
     "nr_gather_rows": (_i, [_vp, _ll, _i, _vp, _i, _i, _i, _vp, _i, _f, _ull, _vp, _vp]),
     "nr_linear": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp]),

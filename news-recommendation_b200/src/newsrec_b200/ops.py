@@ -144,6 +144,20 @@ def stack_qkv(mq, mk, mv):
     return torch.cat(parts, dim=0)
 
 
+def cast_pad_many(specs):
+    """[(fp32 [R][C] tensor, ld, transpose), ...] (at most 8) -> the zero padded bf16 operands, ONE launch for all of them."""
+    lib = load_library()
+    n = len(specs)
+    srcs = [t.contiguous().float() for t, _, _ in specs]
+    dsts = [torch.empty(((s.shape[1] if tr else s.shape[0]), ld), dtype=torch.bfloat16, device=s.device) for s, (_, ld, tr) in zip(srcs, specs)]
+    arr_i = lambda vals: (C.c_int * n)(*vals)
+    check(lib.nr_cast_pad_bf16_many(n, (C.c_void_p * n)(*[s.data_ptr() for s in srcs]), arr_i([s.shape[0] for s in srcs]),
+                                    arr_i([s.shape[1] for s in srcs]), arr_i([s.shape[1] for s in srcs]),
+                                    (C.c_void_p * n)(*[t.data_ptr() for t in dsts]), arr_i([ld for _, ld, _ in specs]),
+                                    arr_i([int(tr) for _, _, tr in specs]), _stream()), "nr_cast_pad_bf16_many")
+    return dsts
+
+
 def mhsa_operands(cache: OperandCache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
     d, q = Wq.shape[0], Wa.shape[0]
     ldx, ldq = ru8(d + 1), ru16(q)
@@ -151,9 +165,8 @@ def mhsa_operands(cache: OperandCache, prefix, Wq, bq, Wk, bk, Wv, bv, Wa, ba, q
 
     def build(Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv):
         wqkv = stack_qkv(Wq, Wk, Wv)
-        return dict(wqkv=cast_pad(wqkv, ldx), wqkvT=cast_pad(wqkv, ld3, transpose=True),
-                    bqkv=stack_qkv(bq, bk, bv).contiguous(),
-                    wa=cast_pad(Wa, ldx), waT=cast_pad(Wa, ldq, transpose=True),
+        w, wT, wa, waT = cast_pad_many([(wqkv, ldx, False), (wqkv, ld3, True), (Wa, ldx, False), (Wa, ldq, True)])
+        return dict(wqkv=w, wqkvT=wT, bqkv=stack_qkv(bq, bk, bv).contiguous(), wa=wa, waT=waT,
                     ba=ba.float().contiguous(), qv=qv.float().contiguous())
 
     return cache.get(prefix, (Wq, bq, Wk, bk, Wv, bv, Wa, ba, qv), build)
