@@ -190,7 +190,7 @@ def _ddp_worker(rank, world, port, q):
     loss = ((a.sum() + b.sum()) * x[lo:hi]).mean()
     loss.backward()
     fg.all_reduce_mean()
-    q.put((r, a.grad.clone(), b.grad.clone()))
+    q.put((r, a.grad.tolist(), b.grad.tolist()))  # plain lists: a tensor would travel as a shared-memory handle that dies with this process
     torch.distributed.destroy_process_group()
 
 
@@ -234,7 +234,7 @@ def test_flat_gradient_all_reduce_equals_single_process_mean_gloo():
         assert p.exitcode == 0
     want = torch.arange(8.0).mean()   # d/dtheta of mean_i (theta_sum * x_i) over the GLOBAL batch
     for _, ga, gb in got:
-        assert torch.allclose(ga, torch.full((5, 3), float(want))) and torch.allclose(gb, torch.full((7,), float(want)))
+        assert torch.allclose(torch.tensor(ga), torch.full((5, 3), float(want))) and torch.allclose(torch.tensor(gb), torch.full((7,), float(want)))
 
 
 def test_bench_synthetic_batches_are_mind_shaped():
